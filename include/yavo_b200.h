@@ -1,0 +1,163 @@
+/*
+ * yavo_b200.h — C ABI of the B200-native (sm_100a) ORB-style front end of YA_VO.
+ *
+ * The reference (kartikmadhira1/YA_VO) has no FFI or plugin layer: its hot path is the public
+ * member functions of three concrete C++ classes.  This header is the boundary a binding of
+ * that path would use; every entry point names the reference interface it replaces
+ * (paths relative to the reference checkout).  The C++ classes in ya_vo_b200/host/ keep the
+ * reference signatures and call these functions; ya_vo_b200/capi.py binds them with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross the boundary
+ *   - every function returns 0 on success, a negative yavo_status otherwise; the message is
+ *     available from yavo_last_error(ctx) (yavo_last_error(NULL) for yavo_create failures)
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *   - coordinates follow the reference: a point is (x = row, y = col)
+ *   - a context is bound to one device and one stream; calls on one context must not overlap
+ *     (the reference's hot path is only ever entered from one thread, src/main.cc:11);
+ *     use one context per GPU / host thread
+ *   - host pointers may be pageable; uploads are staged through pinned memory
+ */
+#ifndef YAVO_B200_H
+#define YAVO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct yavo_ctx yavo_ctx;
+
+typedef enum yavo_status {
+    YAVO_OK = 0,
+    YAVO_ERR_INVALID = -1,    /* bad argument */
+    YAVO_ERR_CUDA = -2,       /* CUDA runtime error (message has the detail) */
+    YAVO_ERR_CAPACITY = -3,   /* a device buffer sized at yavo_create was too small */
+    YAVO_ERR_STATE = -4       /* call sequence error (e.g. slot never uploaded) */
+} yavo_status;
+
+/* Reference constants (include/FastDetector.hpp:32-38, src/FastDetector.cc:147, src/LoopHandler.cc:7) */
+#define YAVO_FAST_THRESHOLD 40
+#define YAVO_FAST_RUN 12
+#define YAVO_FAST_MAX_KEYPOINTS 2000
+#define YAVO_BRIEF_TESTS 256
+#define YAVO_DESC_BYTES 32
+
+/* ---- context ---------------------------------------------------------------------------------- */
+
+/* One context per GPU.  n_slots device-resident frames of at most max_rows x max_cols pixels;
+ * max_kp keypoints kept per frame (the reference's fastCornerNumThreshold, include/FastDetector.hpp:36);
+ * max_cand = capacity of the per-frame FAST candidate list (0 = (max_rows-8)*(max_cols-8)/4,
+ * i.e. every fourth interior pixel).  */
+int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp, int max_cand,
+                yavo_ctx **out);
+void yavo_destroy(yavo_ctx *ctx);
+const char *yavo_last_error(const yavo_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+long long yavo_kernel_launches(const yavo_ctx *ctx);
+/* block until everything queued on the context's stream has finished */
+int yavo_sync(yavo_ctx *ctx);
+/* the context's cudaStream_t (as void*), so callers can record their own CUDA events on it */
+void *yavo_get_stream(yavo_ctx *ctx);
+/* measurement: when on, every kernel launch is bracketed by a CUDA event pair on the context's stream.
+ * yavo_profile_collect synchronises and returns, per kernel class
+ * {0 repitch, 1 detect_blur, 2 compact_score, 3 select_topk, 4 brief, 5 match_partial, 6 match_reduce},
+ * the summed device time in ms and the number of launches since the last collect / set_profiling. */
+int yavo_set_profiling(yavo_ctx *ctx, int on);
+int yavo_profile_collect(yavo_ctx *ctx, double *ms_per_class, int *launches_per_class, int n_classes);
+
+/* ---- Image (include/Image.hpp:14-28, src/Image.cc:8-17) ---------------------------------------- */
+
+/* Image::Image(const cv::Mat&): deep copy of an 8-bit single-channel frame into device slot `slot`.
+ * `stride` is the host row pitch in bytes (cols for a continuous Mat).  Pageable memory is packed
+ * into pinned staging before the call returns; a continuous frame in pinned (cudaHostAlloc /
+ * cudaHostRegister) memory is copied asynchronously straight from the caller's buffer, which must
+ * then stay unchanged until the next yavo_sync / fetch on this context. */
+int yavo_upload(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows, int cols, int stride);
+/* n continuous frames (n x rows x cols) into slots [slot0, slot0+n) */
+int yavo_upload_batch(yavo_ctx *ctx, int slot0, int n, const uint8_t *pixels, int rows, int cols);
+/* same, from pixels already in device memory (row pitch `pitch` bytes, frame pitch rows*pitch) */
+int yavo_upload_from_device(yavo_ctx *ctx, int slot0, int n, const void *d_pixels, int rows, int cols,
+                            size_t pitch);
+/* Image::getPixelVal / rawImage read-back (tests): copies slot pixels to a continuous host buffer */
+int yavo_download(yavo_ctx *ctx, int slot, uint8_t *pixels, int rows, int cols);
+
+/* ---- FastDetector (include/FastDetector.hpp:17-55, src/FastDetector.cc) ------------------------ */
+
+/* FastDetector::getBresenhamCirclePoints (src/FastDetector.cc:50-112): the 16 ring points around
+ * (xc, yc) in ring order, out_xy = {x0,y0,...,x15,y15}.  Host-side constant table. */
+void yavo_ring_points(int xc, int yc, int32_t *out_xy);
+
+/* FastDetector::getFastFeatures (src/FastDetector.cc:277-369): segment test over the interior,
+ * Harris response of every passing pixel, reference ordering (std::sort by response, descending,
+ * replayed exactly including its treatment of tied responses), first max_kp points.
+ *   out_rows/out_cols/out_scores: capacity max_kp each (out_scores may be NULL)
+ *   *n_out: points written, *n_cand: pixels that passed the segment test (both may be NULL)
+ * max_kp <= 0 selects the context's max_kp.  The blurred plane BRIEF needs is produced by the
+ * same kernel and cached in the slot. */
+int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int32_t *out_cols,
+                     float *out_scores, int *n_out, int *n_cand);
+/* the unsorted candidate list in scan (row-major) order, as the reference's retCorners holds it
+ * before the sort (src/FastDetector.cc:298-335); for parity tests. capacity `cap` entries. */
+int yavo_fast_candidates(yavo_ctx *ctx, int slot, int cap, int32_t *out_rows, int32_t *out_cols,
+                         float *out_scores, int *n_cand);
+
+/* ---- Brief (include/BriefDescriptor.hpp:41-68, src/BriefDescriptor.cc) ------------------------- */
+
+/* Brief::preComputeOffsets result (src/BriefDescriptor.cc:4-20): 256 x {drow1,dcol1,drow2,dcol2},
+ * each in [-8, 8].  The host wrapper draws the table as the reference does and passes it here. */
+int yavo_set_brief_offsets(yavo_ctx *ctx, const int32_t *offsets /* 1024 */);
+
+/* cv::GaussianBlur(rawImage, 9x9, 2.5) as Brief::computeBrief applies it (src/BriefDescriptor.cc:90):
+ * read-back of the slot's smoothed plane (computed on demand); for parity tests. */
+int yavo_blurred(yavo_ctx *ctx, int slot, uint8_t *out, int rows, int cols);
+
+/* Brief::computeBrief (src/BriefDescriptor.cc:86-124) for n points (x=row, y=col), in input order.
+ *   out_desc: n x 32 bytes, bit j of the descriptor in byte j/8, bit j%8 (:108-117)
+ *   out_valid: n bytes, 1 where checkBoundry (:128-136) admits the point; descriptors of rejected
+ *              points are zero and the caller drops them (the reference does not append them)
+ *   *n_oob (may be NULL): admitted points with a test read at linear index >= rows*cols
+ *              (undefined behaviour in the reference; such reads are defined as pixel value 0) */
+int yavo_brief_describe(yavo_ctx *ctx, int slot, const int32_t *rows, const int32_t *cols, int n,
+                        uint8_t *out_desc, uint8_t *out_valid, int *n_oob);
+
+/* Brief::matchFeatures (src/BriefDescriptor.cc:163-183) on two descriptor sets (n x 32 bytes):
+ * for every query i the train index with the smallest Hamming distance (:139-160), lowest index
+ * among equal minima; n2 == 0 gives idx -1 and dist INT_MAX.
+ * Extensions with no reference counterpart (may be NULL): out_second = second smallest distance
+ * per query (ratio test), out_rev_idx[j] = best query for train j (cross-check). */
+int yavo_match(yavo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
+               int32_t *out_idx, int32_t *out_dist, int32_t *out_second, int32_t *out_rev_idx);
+
+/* Brief::removeOutliers (src/BriefDescriptor.cc:213-231): keep[i] = dist[i] < max(2*min(dist), threshold).
+ * O(n) host arithmetic on the distances yavo_match returned; returns the kept count (>= 0). */
+int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *keep);
+
+/* ---- batch front end (LoopHandler::insertFrameFeatures over many frames, src/LoopHandler.cc:468-485,
+ *      plus matchFeatures(frame f-1, frame f), :189,534) -------------------------------------------- */
+
+/* Runs detect -> top-K -> describe on slots [slot0, slot0+n) and, if do_match, matches the kept
+ * descriptors of slot f-1 (queries) against slot f (train) for f in (slot0, slot0+n).  Results stay
+ * in device memory; nothing is copied to the host.  Frames must all have the same size. */
+int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match);
+
+/* Copies the results of yavo_frontend_batch for n slots to host arrays (any may be NULL):
+ *   n_kp[n]; rows/cols/scores [n x max_kp]; desc [n x max_kp x 32]; only keypoints admitted by
+ *   checkBoundry are kept, compacted in order, as Brief::computeBrief appends them;
+ *   match_idx/match_dist [n x max_kp]: entry (f, i) is the match of keypoint i of slot f-1 in slot f
+ *   (row 0 of the batch is unused). */
+int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols,
+                     float *scores, uint8_t *desc, int32_t *match_idx, int32_t *match_dist);
+
+/* convenience for streaming callers: upload + frontend + fetch of one batch of host frames with the
+ * copies inside (what bench.py's e2e leg times). */
+int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
+                            int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores,
+                            uint8_t *desc, int32_t *match_idx, int32_t *match_dist);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YAVO_B200_H */

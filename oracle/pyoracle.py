@@ -126,10 +126,10 @@ def std_sort_desc(scores, payload):
     return s, p
 
 
-def introsort_topk(scores, payload, k):
+def introsort_topk(scores, payload, k, depth=-1):
     s = np.ascontiguousarray(scores, np.float32).copy()
     p = np.ascontiguousarray(payload, np.int32).copy()
-    lib().yavo_oracle_introsort_topk(_p(s), _p(p), s.size, int(k))
+    lib().yavo_oracle_introsort_topk_depth(_p(s), _p(p), s.size, int(k), int(depth))
     return s, p
 
 

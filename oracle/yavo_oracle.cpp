@@ -449,11 +449,15 @@ void yavo_oracle_std_sort_desc(float *scores, int32_t *payload, int n) {
 }
 
 void yavo_oracle_introsort_topk(float *scores, int32_t *payload, int n, int k) {
+    yavo_oracle_introsort_topk_depth(scores, payload, n, k, -1);
+}
+
+void yavo_oracle_introsort_topk_depth(float *scores, int32_t *payload, int n, int k, int depth) {
     if (n == 0) return;
     std::vector<SP> v(n);
     for (int i = 0; i < n; i++) v[i] = {scores[i], payload[i]};
     int lg = 31 - __builtin_clz((unsigned)n);
-    introsort_loop_topk(v.data(), 0, n, 2 * lg, k);
+    introsort_loop_topk(v.data(), 0, n, depth >= 0 ? depth : 2 * lg, k);
     // __final_insertion_sort == stable insertion sort; only the prefix that can reach [0,k) matters
     int lim = std::min(n, k + 16);
     for (int i = 1; i < lim; i++) {

@@ -57,6 +57,8 @@ void yavo_oracle_std_sort_desc(float *scores, int32_t *payload, int n);
 /* transparent restatement of libstdc++'s introsort restricted to the ranges that
  * decide the first k outputs (the model of the CUDA select kernel) */
 void yavo_oracle_introsort_topk(float *scores, int32_t *payload, int n, int k);
+/* same with an explicit initial depth limit (forces the std::make_heap/std::sort_heap fallback) */
+void yavo_oracle_introsort_topk_depth(float *scores, int32_t *payload, int n, int k, int depth);
 
 /* cv::GaussianBlur(u8, 9x9, 2.5) as OpenCV 4.x computes it (fixed point), BORDER_REFLECT_101 */
 void yavo_oracle_gaussian_blur(const uint8_t *img, int H, int W, uint8_t *out);

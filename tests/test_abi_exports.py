@@ -1,0 +1,59 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/yavo_b200.h declares;
+without a GPU the product fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+
+def declared_symbols():
+    from ya_vo_b200 import capi
+    txt = open(capi.HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(yavo_[a-z_0-9]+)\s*\(", txt)))
+
+
+def test_library_exports_header(cuda_lib):
+    names = declared_symbols()
+    assert set(names) == set(cuda_lib.EXPORTS)
+    L = C.CDLL(cuda_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_header_cites_reference_interfaces(cuda_lib):
+    txt = open(cuda_lib.HEADER).read()
+    for cite in ("src/FastDetector.cc:277-369", "src/BriefDescriptor.cc:86-124", "src/BriefDescriptor.cc:163-183",
+                 "src/Image.cc:8-17", "src/BriefDescriptor.cc:213-231"):
+        assert cite in txt
+
+
+def test_sass_is_sm100a_without_tensor_ops(cuda_lib):
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", cuda_lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+
+
+def test_no_cpu_fallback_without_device(cuda_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(cuda_lib.YavoError):
+        cuda_lib.Context()
+
+
+def test_host_side_scalars(cuda_lib, oracle):
+    import numpy as np
+    assert np.array_equal(cuda_lib.ring_points(25, 25), oracle.ring(25, 25))
+    d = np.array([5, 9, 10, 19, 20, 40], np.int32)
+    assert np.array_equal(cuda_lib.remove_outliers(d, 20), oracle.remove_outliers(d, 20))
+
+
+def test_product_does_not_import_oracle():
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ya_vo_b200")
+    for dp, dn, fn in os.walk(root):
+        for f in fn:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", ".cpp")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "pyoracle" not in txt and "yavo_oracle" not in txt and "libyavo_oracle" not in txt, f

@@ -1,0 +1,207 @@
+"""GPU: the CUDA path, called through the C ABI, against the oracle — bit-exact."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from ya_vo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def ctx(cuda_lib, offsets):
+    c = cuda_lib.Context(device=0, n_slots=8, max_rows=376, max_cols=1241, max_kp=2000)
+    c.set_brief_offsets(offsets)
+    yield c
+    c.close()
+
+
+FRAMES = [("U", 0, 376, 1241), ("G30", 1, 376, 1241), ("B4", 2, 376, 1241), ("U", 5, 37, 50), ("U", 6, 41, 133),
+          ("U", 7, 9, 9), ("U", 8, 12, 300), ("G30", 9, 376, 1241), ("U", 10, 200, 128), ("U", 11, 33, 129)]
+
+
+def test_upload_download_roundtrip(ctx):
+    img = synth.synth_frame("U", 42, 100, 333)
+    ctx.upload(0, img)
+    assert np.array_equal(ctx.download(0), img)
+    strided = synth.synth_frame("U", 43, 64, 200)[:, 10:150]
+    ctx.upload(1, np.ascontiguousarray(strided))
+    assert np.array_equal(ctx.download(1), strided)
+
+
+@pytest.mark.parametrize("kind,seed,H,W", FRAMES)
+def test_blur_bit_exact(ctx, oracle, kind, seed, H, W):
+    img = synth.synth_frame(kind, seed, H, W)
+    ctx.upload(0, img)
+    assert np.array_equal(ctx.blurred(0), oracle.gaussian_blur(img))
+
+
+def test_blur_against_cv2_golden(ctx, kitti):
+    g = np.load(os.path.join(GOLDEN, "blur_golden.npz"))
+    for n in sorted(k[:-3] for k in g.files if k.endswith("_in") and "_sha_" not in k):
+        ctx.upload(0, g[n + "_in"])
+        assert np.array_equal(ctx.blurred(0), g[n + "_out"]), n
+    ctx.upload(0, kitti)
+    assert sha(ctx.blurred(0)) == str(g["kitti_sha_out"])
+
+
+@pytest.mark.parametrize("kind,seed,H,W", FRAMES)
+def test_fast_candidates_bit_exact(ctx, oracle, kind, seed, H, W):
+    """positions in scan order and float32 score bits (src/FastDetector.cc:298-335)."""
+    img = synth.synth_frame(kind, seed, H, W)
+    ctx.upload(0, img)
+    r, c, s = ctx.fast_candidates(0)
+    er, ec, es = oracle.fast_candidates(img)
+    assert np.array_equal(r, er) and np.array_equal(c, ec)
+    assert np.array_equal(s.view(np.uint32), es.view(np.uint32))
+
+
+def test_fast_candidates_kitti(ctx, oracle, kitti):
+    ctx.upload(0, kitti)
+    r, c, s = ctx.fast_candidates(0)
+    er, ec, es = oracle.fast_candidates(kitti)
+    assert r.size == 3791
+    assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind,seed,H,W", FRAMES)
+def test_fast_detect_order_bit_exact(ctx, oracle, kind, seed, H, W):
+    """keypoints in the reference's std::sort order, including tied responses (:343-362)."""
+    img = synth.synth_frame(kind, seed, H, W)
+    ctx.upload(0, img)
+    r, c, s, nc = ctx.fast_detect(0)
+    er, ec, es, enc = oracle.fast_detect(img, 2000)
+    assert nc == enc and r.size == er.size
+    assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
+
+
+def test_fast_detect_kitti_and_small_caps(ctx, oracle, kitti):
+    ctx.upload(0, kitti)
+    for K in (2000, 1, 17, 500):
+        r, c, s, nc = ctx.fast_detect(0, K)
+        er, ec, es, enc = oracle.fast_detect(kitti, K)
+        assert nc == 3791 and np.array_equal(r, er) and np.array_equal(c, ec)
+    flat = np.full((40, 60), 9, np.uint8)
+    ctx.upload(1, flat)
+    r, c, s, nc = ctx.fast_detect(1)
+    assert nc == 0 and r.size == 0
+
+
+def test_fast_detect_heavy_ties(ctx, oracle):
+    """blocky frames: many candidates share a response, the order is decided by introsort's history."""
+    tied = 0
+    for seed in range(20, 26):
+        img = synth.synth_frame("B4", seed)
+        ctx.upload(0, img)
+        r, c, s, nc = ctx.fast_detect(0)
+        er, ec, es, _ = oracle.fast_detect(img, 2000)
+        tied += int((np.diff(es) == 0).sum())
+        assert np.array_equal(r, er) and np.array_equal(c, ec)
+    assert tied > 0
+
+
+@pytest.mark.parametrize("kind,seed,H,W", FRAMES[:6])
+def test_brief_bit_exact(ctx, oracle, offsets, kind, seed, H, W):
+    img = synth.synth_frame(kind, seed, H, W)
+    ctx.upload(0, img)
+    er, ec, es, _ = oracle.fast_detect(img, 2000)
+    # FAST points plus arbitrary ones (computeBrief accepts any list: src/LoopHandler.cc:488-510)
+    rng = np.random.default_rng(seed)
+    rows = np.concatenate([er, rng.integers(0, H, 64), [8, H - 8, H - 8, 8]]).astype(np.int32)
+    cols = np.concatenate([ec, rng.integers(0, W, 64), [8, W - 8, 8, W - 8]]).astype(np.int32)
+    d, v, oob = ctx.brief_describe(0, rows, cols)
+    ed, ev, eoob = oracle.brief(img, offsets, rows, cols)
+    assert np.array_equal(v, ev) and np.array_equal(d, ed) and oob == eoob
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (50, 70), (2000, 2000), (333, 4097), (4096, 129), (2000, 0)])
+def test_match_bit_exact(ctx, oracle, n1, n2):
+    d1 = synth.synth_descriptors(n1, n1 * 131 + n2)
+    d2 = synth.planted_descriptors(d1, n2, 7) if n2 else synth.synth_descriptors(0, 1)
+    if n2 > 45:
+        d2[40] = d2[10]  # duplicated train descriptor: lowest index must win
+    idx, dist, sec, rev = ctx.match(d1, d2, extensions=True)
+    eidx, edist, esec, erev = oracle.match(d1, d2, extensions=True)
+    assert np.array_equal(idx, eidx) and np.array_equal(dist, edist)
+    assert np.array_equal(sec, esec)
+    assert np.array_equal(rev, erev)
+
+
+def test_frontend_batch_matches_oracle_pipeline(cuda_lib, oracle, offsets, kitti):
+    """configs 2/3 in miniature: consecutive frames, FAST+BRIEF on each, match f-1 -> f."""
+    a = synth.synth_frame("G30", 1000)
+    frames = np.stack([a, synth.shifted_pair(a, 1), kitti, synth.synth_frame("B4", 1002), synth.synth_frame("U", 3)])
+    n = frames.shape[0]
+    with cuda_lib.Context(device=0, n_slots=n, max_rows=376, max_cols=1241, max_kp=2000) as c:
+        c.set_brief_offsets(offsets)
+        out = c.process_host_batch(frames, do_match=True)
+    exp = oracle.pipeline(frames, offsets, 2000, True, nthreads=4)
+    assert np.array_equal(out["n_kp"], exp["n_kp"])
+    for f in range(n):
+        k = exp["n_kp"][f]
+        assert np.array_equal(out["rows"][f, :k], exp["rows"][f, :k])
+        assert np.array_equal(out["cols"][f, :k], exp["cols"][f, :k])
+        assert np.array_equal(out["scores"][f, :k].view(np.uint32), exp["scores"][f, :k].view(np.uint32))
+        assert np.array_equal(out["desc"][f, :k], exp["desc"][f, :k])
+        if f > 0:
+            kq = exp["n_kp"][f - 1]
+            assert np.array_equal(out["match_idx"][f, :kq], exp["match_idx"][f, :kq])
+            assert np.array_equal(out["match_dist"][f, :kq], exp["match_dist"][f, :kq])
+    # the shifted pair has true matches: most survive removeOutliers(…, 20)
+    keep = cuda_lib.remove_outliers(out["match_dist"][1, :exp["n_kp"][0]], 20)
+    assert keep.sum() > 100
+
+
+def test_reference_style_pipeline(cuda_lib, oracle, offsets):
+    """tests/BriefDescriptorTest.cc:9-64 call order through the class mirror."""
+    from ya_vo_b200.frontend import Brief, FastDetector, Image
+    a = synth.synth_frame("G30", 77)
+    b = synth.shifted_pair(a, 78)
+    brief = Brief(256, offsets=offsets)
+    t1, t2 = Image(a), Image(b)
+    fd = FastDetector(12, 50)
+    f1 = fd.getFastFeatures(t1)
+    f2 = fd.getFastFeatures(t2)
+    brief.computeBrief(f1, t1)
+    brief.computeBrief(f2, t2)
+    matches = brief.matchFeatures(t1, t2)
+    filt = []
+    brief.removeOutliers(matches, filt, 20.0)
+    er, ec, es, _ = oracle.fast_detect(a, 2000)
+    assert f1 == list(zip(er.tolist(), ec.tolist()))
+    ed, ev, _ = oracle.brief(a, offsets, er, ec)
+    assert len(t1.keypoints) == int(ev.sum())
+    assert [k.id for k in t1.keypoints] == np.nonzero(ev)[0].tolist()
+    assert np.array_equal(np.array([k.featVec for k in t1.keypoints]), ed[ev])
+    assert len(matches) == len(t1.keypoints)
+    assert len(filt) > 100 and all(m.pt1.matched and m.pt2.matched for m in filt)
+
+
+def test_known_answers_through_mirror(cuda_lib):
+    """tests/FastDetectorTest.cc:6-80 and tests/ImageTest.cc:23-37 against the class mirror."""
+    from ya_vo_b200.frontend import FastDetector, Image
+    bres = np.load(os.path.join(GOLDEN, "bresenham_50x50.npy"))
+    img = Image(np.zeros((50, 50), np.uint8))
+    fd = FastDetector(12, 50)
+    pts = fd.getBresenhamCirclePoints(img, 25, 25)
+    assert len(pts) == 16
+    for p in pts:
+        fd.putPixel(img, p)
+    diff = img.rawImage.astype(np.int16) - bres.astype(np.int16)
+    assert diff.min() >= -255 and np.abs(np.clip(diff, 0, 255)).max() <= 1  # cv::subtract saturates at 0
+    gold = Image(bres)
+    assert all(gold.getPixelVal(p[0], p[1]) == 255 for p in pts)
+    assert fd.checkContiguousPixels(img.getPixelVal(25, 25), pts, img) is True
+    fd.putPixel(img, (25, 25))
+    assert fd.checkContiguousPixels(img.getPixelVal(25, 25), pts, img) is False
+    img2 = Image(np.zeros((50, 50), np.uint8))
+    for p in pts[:11]:
+        fd.putPixel(img2, p)
+    assert fd.checkContiguousPixels(img2.getPixelVal(25, 25), pts, img2) is False

@@ -1,0 +1,264 @@
+"""ctypes binding of the C ABI in include/yavo_b200.h (ya_vo_b200/csrc/libyavo_b200.so).
+
+This is the product boundary: plain pointers and sizes, no torch types.  The library is built
+in-tree by build() (nvcc, sm_100a only) and there is no CPU path — on a machine without a CUDA
+device `Context(...)` raises YavoError.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_CSRC, "libyavo_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "yavo_b200.h")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-fmad=false", "-shared", "-Xcompiler", "-fPIC"]
+
+EXPORTS = [
+    "yavo_create", "yavo_destroy", "yavo_last_error", "yavo_kernel_launches", "yavo_sync",
+    "yavo_get_stream", "yavo_set_profiling", "yavo_profile_collect",
+    "yavo_upload", "yavo_upload_batch", "yavo_upload_from_device", "yavo_download",
+    "yavo_ring_points", "yavo_fast_detect", "yavo_fast_candidates",
+    "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
+    "yavo_match", "yavo_remove_outliers",
+    "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch",
+]
+
+
+class YavoError(RuntimeError):
+    pass
+
+
+def _sources():
+    return [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".h"))] + [HEADER]
+
+
+def build(force=False, verbose=False):
+    """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in _sources())
+    if not (force or stale):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "yavo_capi.cu")]
+    subprocess.check_call(cmd, cwd=_CSRC)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Loads the CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise YavoError("libyavo_b200.so is missing: run ya_vo_b200.capi.build() (nvcc, sm_100a). "
+                            "There is no CPU implementation to fall back to.")
+        L = C.CDLL(LIB_PATH)
+        L.yavo_last_error.restype = C.c_char_p
+        L.yavo_last_error.argtypes = [C.c_void_p]
+        L.yavo_kernel_launches.restype = C.c_longlong
+        L.yavo_kernel_launches.argtypes = [C.c_void_p]
+        L.yavo_destroy.restype = None
+        L.yavo_destroy.argtypes = [C.c_void_p]
+        L.yavo_ring_points.restype = None
+        L.yavo_get_stream.restype = C.c_void_p
+        L.yavo_get_stream.argtypes = [C.c_void_p]
+        L.yavo_upload_from_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    """One device, one stream, `n_slots` device-resident frames (include/yavo_b200.h: yavo_create)."""
+
+    def __init__(self, device=0, n_slots=2, max_rows=376, max_cols=1241, max_kp=2000, max_cand=0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.yavo_create(int(device), int(n_slots), int(max_rows), int(max_cols), int(max_kp), int(max_cand),
+                                 C.byref(h))
+        if rc != 0:
+            raise YavoError("yavo_create failed (%d): %s" % (rc, self._L.yavo_last_error(None).decode()))
+        self._h = h
+        self.device, self.n_slots, self.max_rows, self.max_cols, self.max_kp = device, n_slots, max_rows, max_cols, max_kp
+        self._shape = {}
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.yavo_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise YavoError("yavo error %d: %s" % (rc, self._L.yavo_last_error(self._h).decode()))
+        return rc
+
+    @property
+    def kernel_launches(self):
+        return int(self._L.yavo_kernel_launches(self._h))
+
+    def sync(self):
+        self._ck(self._L.yavo_sync(self._h))
+
+    @property
+    def stream(self):
+        """cudaStream_t of the context as an integer (wrap with torch.cuda.ExternalStream to record events)."""
+        return int(self._L.yavo_get_stream(self._h) or 0)
+
+    KERNEL_CLASSES = ("repitch", "detect_blur", "compact_score", "select_topk", "brief", "match_partial", "match_reduce")
+
+    def set_profiling(self, on):
+        self._ck(self._L.yavo_set_profiling(self._h, int(bool(on))))
+
+    def profile_collect(self):
+        n = len(self.KERNEL_CLASSES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int * n)()
+        self._ck(self._L.yavo_profile_collect(self._h, ms, cnt, n))
+        return {k: (ms[i], cnt[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+
+    # ---- Image ----
+    def upload(self, slot, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        assert img.ndim == 2
+        self._ck(self._L.yavo_upload(self._h, int(slot), _p(img), img.shape[0], img.shape[1], img.strides[0]))
+        self._shape[slot] = img.shape
+
+    def upload_batch(self, slot0, frames):
+        assert frames.dtype == np.uint8 and frames.ndim == 3 and frames.flags.c_contiguous
+        n, H, W = frames.shape
+        self._ck(self._L.yavo_upload_batch(self._h, int(slot0), n, _p(frames), H, W))
+        for i in range(n):
+            self._shape[slot0 + i] = (H, W)
+
+    def upload_from_device(self, slot0, n, dev_ptr, rows, cols, pitch):
+        self._ck(self._L.yavo_upload_from_device(self._h, int(slot0), int(n), C.c_void_p(int(dev_ptr)), int(rows),
+                                                 int(cols), C.c_size_t(int(pitch))))
+        for i in range(n):
+            self._shape[slot0 + i] = (rows, cols)
+
+    def download(self, slot):
+        H, W = self._shape[slot]
+        out = np.empty((H, W), np.uint8)
+        self._ck(self._L.yavo_download(self._h, int(slot), _p(out), H, W))
+        return out
+
+    # ---- FastDetector ----
+    def fast_detect(self, slot, max_kp=0):
+        K = max_kp if max_kp > 0 else self.max_kp
+        rows = np.empty(K, np.int32)
+        cols = np.empty(K, np.int32)
+        sc = np.empty(K, np.float32)
+        n = C.c_int()
+        nc = C.c_int()
+        self._ck(self._L.yavo_fast_detect(self._h, int(slot), int(max_kp), _p(rows), _p(cols), _p(sc), C.byref(n),
+                                          C.byref(nc)))
+        return rows[:n.value].copy(), cols[:n.value].copy(), sc[:n.value].copy(), nc.value
+
+    def fast_candidates(self, slot, cap=None):
+        H, W = self._shape[slot]
+        cap = cap or H * W
+        rows = np.empty(cap, np.int32)
+        cols = np.empty(cap, np.int32)
+        sc = np.empty(cap, np.float32)
+        nc = C.c_int()
+        self._ck(self._L.yavo_fast_candidates(self._h, int(slot), int(cap), _p(rows), _p(cols), _p(sc), C.byref(nc)))
+        n = min(nc.value, cap)
+        return rows[:n].copy(), cols[:n].copy(), sc[:n].copy()
+
+    # ---- Brief ----
+    def set_brief_offsets(self, offsets):
+        off = np.ascontiguousarray(offsets, np.int32).reshape(-1)
+        assert off.size == 1024
+        self._ck(self._L.yavo_set_brief_offsets(self._h, _p(off)))
+
+    def blurred(self, slot):
+        H, W = self._shape[slot]
+        out = np.empty((H, W), np.uint8)
+        self._ck(self._L.yavo_blurred(self._h, int(slot), _p(out), H, W))
+        return out
+
+    def brief_describe(self, slot, rows, cols):
+        rows = np.ascontiguousarray(rows, np.int32)
+        cols = np.ascontiguousarray(cols, np.int32)
+        n = rows.size
+        desc = np.zeros((n, 32), np.uint8)
+        valid = np.zeros(n, np.uint8)
+        oob = C.c_int()
+        self._ck(self._L.yavo_brief_describe(self._h, int(slot), _p(rows), _p(cols), n, _p(desc), _p(valid),
+                                             C.byref(oob)))
+        return desc, valid.astype(bool), oob.value
+
+    def match(self, d1, d2, extensions=False):
+        d1 = np.ascontiguousarray(d1, np.uint8).reshape(-1, 32)
+        d2 = np.ascontiguousarray(d2, np.uint8).reshape(-1, 32)
+        n1, n2 = d1.shape[0], d2.shape[0]
+        idx = np.zeros(n1, np.int32)
+        dist = np.zeros(n1, np.int32)
+        if not extensions:
+            self._ck(self._L.yavo_match(self._h, _p(d1), n1, _p(d2), n2, _p(idx), _p(dist), None, None))
+            return idx, dist
+        sec = np.zeros(n1, np.int32)
+        rev = np.zeros(n2, np.int32)
+        self._ck(self._L.yavo_match(self._h, _p(d1), n1, _p(d2), n2, _p(idx), _p(dist), _p(sec), _p(rev)))
+        return idx, dist, sec, rev
+
+    # ---- batch ----
+    def frontend_batch(self, slot0, n, do_match=True):
+        self._ck(self._L.yavo_frontend_batch(self._h, int(slot0), int(n), int(do_match)))
+
+    def alloc_batch_outputs(self, n, pinned=False):
+        K = self.max_kp
+        return dict(n_kp=np.zeros(n, np.int32), rows=np.zeros((n, K), np.int32), cols=np.zeros((n, K), np.int32),
+                    scores=np.zeros((n, K), np.float32), desc=np.zeros((n, K, 32), np.uint8),
+                    match_idx=np.zeros((n, K), np.int32), match_dist=np.zeros((n, K), np.int32))
+
+    def fetch_batch(self, slot0, n, out=None):
+        out = out or self.alloc_batch_outputs(n)
+        self._ck(self._L.yavo_fetch_batch(self._h, int(slot0), int(n), _p(out["n_kp"]), _p(out["rows"]), _p(out["cols"]),
+                                          _p(out["scores"]), _p(out["desc"]), _p(out["match_idx"]),
+                                          _p(out["match_dist"])))
+        return out
+
+    def process_host_batch(self, frames, do_match=True, out=None):
+        n, H, W = frames.shape
+        out = out or self.alloc_batch_outputs(n)
+        self._ck(self._L.yavo_process_host_batch(self._h, _p(frames), n, H, W, int(do_match), _p(out["n_kp"]),
+                                                 _p(out["rows"]), _p(out["cols"]), _p(out["scores"]), _p(out["desc"]),
+                                                 _p(out["match_idx"]), _p(out["match_dist"])))
+        for i in range(n):
+            self._shape[i] = (H, W)
+        return out
+
+
+def ring_points(xc, yc):
+    out = np.zeros(32, np.int32)
+    lib().yavo_ring_points(int(xc), int(yc), _p(out))
+    return out.reshape(16, 2)
+
+
+def remove_outliers(dist, threshold=20):
+    dist = np.ascontiguousarray(dist, np.int32)
+    keep = np.zeros(dist.size, np.uint8)
+    lib().yavo_remove_outliers(_p(dist), dist.size, int(threshold), _p(keep))
+    return keep.astype(bool)

@@ -1,0 +1,764 @@
+// yavo_capi.cu — the C ABI of include/yavo_b200.h on top of the kernels in yavo_kernels.cuh.
+// One context = one device, one stream, device-resident frame slots plus the per-slot work
+// buffers.  No CPU fallback: every compute entry point launches the CUDA kernels or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/yavo_b200.h"
+#include "yavo_kernels.cuh"
+
+using namespace yavo;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct yavo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n_slots = 0, max_rows = 0, max_cols = 0, max_kp = 0, max_cand = 0;
+    int pitch = 0;       // device row pitch in bytes (multiple of 128)
+    int rows_alloc = 0;  // rows per slot
+    int mask_words = 0;  // pitch / 32
+    size_t frame_stride = 0;
+    std::vector<int> slot_rows, slot_cols;
+    std::vector<char> slot_blur_valid;  // blurred plane of the slot is current
+    // device buffers (per slot)
+    uint8_t *d_frames = nullptr, *d_blur = nullptr;
+    uint32_t *d_mask = nullptr;
+    int *d_rowcnt = nullptr;
+    yavo_ent *d_cand = nullptr;
+    int *d_ncand = nullptr;
+    uint32_t *d_scratch = nullptr;
+    int32_t *d_kp_row = nullptr, *d_kp_col = nullptr;
+    float *d_kp_score = nullptr;
+    int *d_nkp = nullptr;
+    int32_t *d_bk_row = nullptr, *d_bk_col = nullptr, *d_bk_id = nullptr;
+    float *d_bk_score = nullptr;
+    int *d_nbk = nullptr;
+    uint32_t *d_desc = nullptr;  // per slot max_kp x 8 words (compacted order)
+    int32_t *d_midx = nullptr, *d_mdist = nullptr;
+    int *d_status = nullptr, *d_noob = nullptr;
+    uint32_t *d_offs = nullptr;
+    bool offs_set = false;
+    // scratch for the explicit-point / explicit-descriptor entry points
+    int32_t *d_pt_row = nullptr, *d_pt_col = nullptr;
+    uint32_t *d_pt_desc = nullptr;
+    uint8_t *d_pt_valid = nullptr;
+    int pt_cap = 0;
+    uint32_t *d_mq = nullptr, *d_mt = nullptr;
+    int mq_cap = 0, mt_cap = 0;
+    int32_t *d_mo_idx = nullptr, *d_mo_dist = nullptr, *d_mo_sec = nullptr;
+    int mo_cap = 0;
+    uint32_t *d_part_key = nullptr, *d_part_sec = nullptr;
+    size_t part_cap = 0;
+    // dense device staging for uploads (H2D runs as one contiguous copy, a kernel re-pitches)
+    uint8_t *d_raw = nullptr;
+    size_t raw_bytes = 0;
+    // pinned staging
+    uint8_t *h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    int *h_small = nullptr;  // 64 ints
+    long long launches = 0;
+    // optional per-kernel timing (CUDA events on the context's stream around every launch)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<int> ev_class;  // class of pair i (events 2i, 2i+1)
+    std::string err;
+};
+
+enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_COUNT };
+
+namespace {
+
+void prof_events(yavo_ctx *c, int cls, cudaEvent_t *e0, cudaEvent_t *e1) {
+    while (c->ev_pool.size() < c->ev_used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        c->ev_pool.push_back(e);
+    }
+    *e0 = c->ev_pool[c->ev_used];
+    *e1 = c->ev_pool[c->ev_used + 1];
+    c->ev_used += 2;
+    c->ev_class.push_back(cls);
+}
+
+int fail(yavo_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, YAVO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+// PROF(cls, launch): optional event pair around one kernel launch
+#define PROF(cls, ...)                                                    \
+    do {                                                                  \
+        cudaEvent_t e0_ = nullptr, e1_ = nullptr;                         \
+        if (ctx->profiling) prof_events(ctx, cls, &e0_, &e1_);            \
+        if (e0_) cudaEventRecord(e0_, ctx->stream);                       \
+        __VA_ARGS__;                                                      \
+        if (e1_) cudaEventRecord(e1_, ctx->stream);                       \
+    } while (0)
+
+#define CK_LAUNCH()                                                                                          \
+    do {                                                                                                     \
+        ctx->launches++;                                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                                 \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, YAVO_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_),      \
+                        __FILE__, __LINE__);                                                                 \
+    } while (0)
+
+template <typename T>
+cudaError_t dalloc(T **p, size_t n) {
+    return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T));
+}
+
+size_t select_smem_bytes() { return ((sizeof(SelShared) + 15) & ~size_t(15)) + sizeof(yavo_ent) * SEL_SMEM_ENTS; }
+
+int ensure_stage(yavo_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->h_stage_bytes) return 0;
+    if (ctx->h_stage) CK(cudaFreeHost(ctx->h_stage));
+    ctx->h_stage = nullptr;
+    ctx->h_stage_bytes = 0;
+    CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_stage), bytes));
+    ctx->h_stage_bytes = bytes;
+    return 0;
+}
+
+int ensure_raw(yavo_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->raw_bytes) return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_raw) CK(cudaFree(ctx->d_raw));
+    ctx->d_raw = nullptr;
+    ctx->raw_bytes = 0;
+    CK(dalloc(&ctx->d_raw, bytes));
+    ctx->raw_bytes = bytes;
+    return 0;
+}
+
+bool is_pinned_host(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// dense (n x rows x src_pitch) device pixels -> pitched frame slots
+int launch_repitch(yavo_ctx *ctx, const uint8_t *d_src, size_t src_pitch, int slot0, int n, int rows, int cols) {
+    dim3 grid((ctx->pitch / 4 + 127) / 128, rows, n);
+    PROF(KC_REPITCH, repitch_kernel<<<grid, 128, 0, ctx->stream>>>(d_src, src_pitch, src_pitch * rows,
+                                                  ctx->d_frames + ctx->frame_stride * slot0, ctx->pitch,
+                                                  ctx->frame_stride, cols));
+    CK_LAUNCH();
+    for (int i = 0; i < n; i++) {
+        ctx->slot_rows[slot0 + i] = rows;
+        ctx->slot_cols[slot0 + i] = cols;
+        ctx->slot_blur_valid[slot0 + i] = 0;
+    }
+    return 0;
+}
+
+// host pixels (row pitch `stride`) for n frames -> slots
+int upload_host(yavo_ctx *ctx, int slot0, int n, const uint8_t *pixels, int rows, int cols, int stride) {
+    const size_t fbytes = (size_t)rows * cols, total = fbytes * n;
+    if (int r = ensure_raw(ctx, total)) return r;
+    if (stride == cols && is_pinned_host(pixels)) {
+        CK(cudaMemcpyAsync(ctx->d_raw, pixels, total, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        // pageable (or strided) source: pack into pinned staging first; the staging buffer is
+        // reused, so wait for the copy that last read it
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (int r = ensure_stage(ctx, total)) return r;
+        if (stride == cols) memcpy(ctx->h_stage, pixels, total);
+        else
+            for (size_t r = 0; r < (size_t)rows * n; r++)
+                memcpy(ctx->h_stage + r * cols, pixels + r * stride, cols);
+        CK(cudaMemcpyAsync(ctx->d_raw, ctx->h_stage, total, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    return launch_repitch(ctx, ctx->d_raw, cols, slot0, n, rows, cols);
+}
+
+int check_slot(yavo_ctx *ctx, int slot, int n = 1) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    if (slot < 0 || n < 0 || slot + n > ctx->n_slots)
+        return fail(ctx, YAVO_ERR_INVALID, "slot range [%d,%d) outside [0,%d)", slot, slot + n, ctx->n_slots);
+    return 0;
+}
+
+int check_uploaded(yavo_ctx *ctx, int slot0, int n) {
+    for (int s = slot0; s < slot0 + n; s++) {
+        if (ctx->slot_rows[s] <= 0) return fail(ctx, YAVO_ERR_STATE, "slot %d holds no frame", s);
+        if (ctx->slot_rows[s] != ctx->slot_rows[slot0] || ctx->slot_cols[s] != ctx->slot_cols[slot0])
+            return fail(ctx, YAVO_ERR_INVALID, "slots %d and %d hold frames of different sizes", slot0, s);
+    }
+    return 0;
+}
+
+// K1 (+K2) over slots [slot0, slot0+n)
+int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
+    const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
+    const size_t fs = ctx->frame_stride;
+    const uint8_t *frames = ctx->d_frames + fs * slot0;
+    uint8_t *blur = ctx->d_blur + fs * slot0;
+    uint32_t *mask = ctx->d_mask + (size_t)slot0 * ctx->rows_alloc * ctx->mask_words;
+    int *rowcnt = ctx->d_rowcnt + (size_t)slot0 * ctx->rows_alloc;
+    dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
+    if (do_fast) CK(cudaMemsetAsync(rowcnt, 0, sizeof(int) * (size_t)n * ctx->rows_alloc, ctx->stream));
+    if (do_fast && do_blur)
+        PROF(KC_DETECT, detect_blur_kernel<true, true><<<grid, K1_THREADS, 0, ctx->stream>>>(
+            frames, fs, ctx->pitch, H, W, blur, mask, ctx->mask_words, rowcnt, ctx->rows_alloc));
+    else if (do_fast)
+        PROF(KC_DETECT, detect_blur_kernel<true, false><<<grid, K1_THREADS, 0, ctx->stream>>>(
+            frames, fs, ctx->pitch, H, W, blur, mask, ctx->mask_words, rowcnt, ctx->rows_alloc));
+    else
+        PROF(KC_DETECT, detect_blur_kernel<false, true><<<grid, K1_THREADS, 0, ctx->stream>>>(
+            frames, fs, ctx->pitch, H, W, blur, mask, ctx->mask_words, rowcnt, ctx->rows_alloc));
+    CK_LAUNCH();
+    if (do_blur)
+        for (int s = slot0; s < slot0 + n; s++) ctx->slot_blur_valid[s] = 1;
+    if (do_fast) {
+        dim3 g2((H + K2_ROWS - 1) / K2_ROWS, n);
+        PROF(KC_COMPACT, compact_score_kernel<<<g2, K2_THREADS, 0, ctx->stream>>>(
+            frames, fs, ctx->pitch, H, W, mask, ctx->mask_words, rowcnt, ctx->rows_alloc,
+            ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0));
+        CK_LAUNCH();
+    }
+    return 0;
+}
+
+// K3 over slots [slot0, slot0+n)
+int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
+    const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
+    const size_t o = (size_t)slot0 * ctx->max_kp;
+    PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->stream>>>(
+        ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
+        ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp, ctx->d_kp_row + o,
+        ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
+        ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->d_status));
+    CK_LAUNCH();
+    return 0;
+}
+
+int check_status(yavo_ctx *ctx) {
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_small[0] != 0) {
+        CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+        return fail(ctx, YAVO_ERR_CAPACITY,
+                    "FAST candidate list overflowed max_cand=%d; create the context with a larger max_cand",
+                    ctx->max_cand);
+    }
+    return 0;
+}
+
+int choose_chunks(int nq, int nt, int pairs) {
+    // enough CTAs to cover the 148 SMs a few times over, at least 256 train descriptors per chunk
+    const int qblocks = std::max(1, (nq + MQ - 1) / MQ) * std::max(1, pairs);
+    int want = (148 * 4 + qblocks - 1) / qblocks;
+    int maxc = std::max(1, nt / 256);
+    return std::max(1, std::min(want, maxc));
+}
+
+int ensure_partials(yavo_ctx *ctx, size_t n) {
+    if (n <= ctx->part_cap) return 0;
+    if (ctx->d_part_key) CK(cudaFree(ctx->d_part_key));
+    if (ctx->d_part_sec) CK(cudaFree(ctx->d_part_sec));
+    ctx->d_part_key = ctx->d_part_sec = nullptr;
+    ctx->part_cap = 0;
+    CK(dalloc(&ctx->d_part_key, n));
+    CK(dalloc(&ctx->d_part_sec, n));
+    ctx->part_cap = n;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *yavo_last_error(const yavo_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+long long yavo_kernel_launches(const yavo_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp, int max_cand, yavo_ctx **out) {
+    yavo_ctx *ctx = nullptr;  // CK() reports through g_create_error while ctx is null
+    if (!out) return fail(nullptr, YAVO_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_slots < 1 || max_rows < 1 || max_cols < 1 || max_kp < 1 || max_rows > 65535 || max_cols > 65535)
+        return fail(nullptr, YAVO_ERR_INVALID, "bad sizes: n_slots=%d max_rows=%d max_cols=%d max_kp=%d", n_slots,
+                    max_rows, max_cols, max_kp);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, YAVO_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, YAVO_ERR_INVALID, "device %d of %d", device, ndev);
+    CK(cudaSetDevice(device));
+    yavo_ctx *c = new yavo_ctx();
+    c->device = device;
+    c->n_slots = n_slots;
+    c->max_rows = max_rows;
+    c->max_cols = max_cols;
+    c->max_kp = max_kp;
+    if (max_cand <= 0) max_cand = std::max(1024, (std::max(max_rows - 8, 1) * std::max(max_cols - 8, 1)) / 4);
+    c->max_cand = max_cand;
+    c->pitch = ((max_cols + TW - 1) / TW) * TW;
+    c->rows_alloc = max_rows;
+    c->mask_words = c->pitch / 32;
+    c->frame_stride = (size_t)c->pitch * c->rows_alloc;
+    c->slot_rows.assign(n_slots, 0);
+    c->slot_cols.assign(n_slots, 0);
+    c->slot_blur_valid.assign(n_slots, 0);
+    ctx = c;
+#define CKC(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            fail(nullptr, YAVO_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));              \
+            yavo_destroy(c);                                                                           \
+            return YAVO_ERR_CUDA;                                                                      \
+        }                                                                                              \
+    } while (0)
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    const size_t S = n_slots;
+    CKC(dalloc(&c->d_frames, S * c->frame_stride));
+    CKC(dalloc(&c->d_blur, S * c->frame_stride));
+    CKC(dalloc(&c->d_mask, S * c->rows_alloc * c->mask_words));
+    CKC(dalloc(&c->d_rowcnt, S * c->rows_alloc));
+    CKC(dalloc(&c->d_cand, S * c->max_cand));
+    CKC(dalloc(&c->d_ncand, S));
+    CKC(dalloc(&c->d_scratch, S * (c->max_cand + 4)));
+    CKC(dalloc(&c->d_kp_row, S * max_kp));
+    CKC(dalloc(&c->d_kp_col, S * max_kp));
+    CKC(dalloc(&c->d_kp_score, S * max_kp));
+    CKC(dalloc(&c->d_nkp, S));
+    CKC(dalloc(&c->d_bk_row, S * max_kp));
+    CKC(dalloc(&c->d_bk_col, S * max_kp));
+    CKC(dalloc(&c->d_bk_score, S * max_kp));
+    CKC(dalloc(&c->d_bk_id, S * max_kp));
+    CKC(dalloc(&c->d_nbk, S));
+    CKC(dalloc(&c->d_desc, S * max_kp * 8));
+    CKC(dalloc(&c->d_midx, S * max_kp));
+    CKC(dalloc(&c->d_mdist, S * max_kp));
+    CKC(dalloc(&c->d_status, 1));
+    CKC(dalloc(&c->d_noob, 1));
+    CKC(dalloc(&c->d_offs, 256));
+    CKC(cudaMemset(c->d_frames, 0, S * c->frame_stride));
+    CKC(cudaMemset(c->d_status, 0, sizeof(int)));
+    CKC(cudaMemset(c->d_nbk, 0, S * sizeof(int)));
+    CKC(cudaMemset(c->d_nkp, 0, S * sizeof(int)));
+    CKC(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), 64 * sizeof(int)));
+    CKC(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)select_smem_bytes()));
+#undef CKC
+    *out = c;
+    return YAVO_OK;
+}
+
+void yavo_destroy(yavo_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void *bufs[] = {c->d_frames, c->d_blur,    c->d_mask,    c->d_rowcnt,   c->d_cand,     c->d_ncand,  c->d_scratch,
+                    c->d_kp_row, c->d_kp_col,  c->d_kp_score, c->d_nkp,     c->d_bk_row,   c->d_bk_col, c->d_bk_score,
+                    c->d_bk_id,  c->d_nbk,     c->d_desc,    c->d_midx,     c->d_mdist,    c->d_status, c->d_noob,
+                    c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
+                    c->d_mo_idx, c->d_mo_dist, c->d_mo_sec,  c->d_part_key, c->d_part_sec, c->d_raw};
+    for (void *b : bufs)
+        if (b) cudaFree(b);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_small) cudaFreeHost(c->h_small);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void *yavo_get_stream(yavo_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int yavo_set_profiling(yavo_ctx *ctx, int on) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    ctx->profiling = on != 0;
+    ctx->ev_used = 0;
+    ctx->ev_class.clear();
+    return 0;
+}
+
+int yavo_profile_collect(yavo_ctx *ctx, double *ms_per_class, int *launches_per_class, int n_classes) {
+    if (!ctx || !ms_per_class || !launches_per_class) return YAVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < n_classes; k++) { ms_per_class[k] = 0.0; launches_per_class[k] = 0; }
+    for (size_t i = 0; i < ctx->ev_class.size(); i++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->ev_pool[2 * i], ctx->ev_pool[2 * i + 1]));
+        const int k = ctx->ev_class[i];
+        if (k < n_classes) { ms_per_class[k] += ms; launches_per_class[k]++; }
+    }
+    ctx->ev_used = 0;
+    ctx->ev_class.clear();
+    return 0;
+}
+
+int yavo_sync(yavo_ctx *ctx) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- Image --------------------------------------------------------------------------------------
+
+int yavo_upload(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows, int cols, int stride) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (!pixels || rows < 1 || cols < 1 || rows > ctx->max_rows || cols > ctx->max_cols || stride < cols)
+        return fail(ctx, YAVO_ERR_INVALID, "bad frame %dx%d stride %d (context max %dx%d)", rows, cols, stride,
+                    ctx->max_rows, ctx->max_cols);
+    CK(cudaSetDevice(ctx->device));
+    return upload_host(ctx, slot, 1, pixels, rows, cols, stride);
+}
+
+int yavo_upload_batch(yavo_ctx *ctx, int slot0, int n, const uint8_t *pixels, int rows, int cols) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (n == 0) return 0;
+    if (!pixels || rows < 1 || cols < 1 || rows > ctx->max_rows || cols > ctx->max_cols)
+        return fail(ctx, YAVO_ERR_INVALID, "bad frame size %dx%d", rows, cols);
+    CK(cudaSetDevice(ctx->device));
+    return upload_host(ctx, slot0, n, pixels, rows, cols, cols);
+}
+
+int yavo_upload_from_device(yavo_ctx *ctx, int slot0, int n, const void *d_pixels, int rows, int cols,
+                            size_t pitch) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (n == 0) return 0;
+    if (!d_pixels || rows < 1 || cols < 1 || rows > ctx->max_rows || cols > ctx->max_cols || pitch < (size_t)cols)
+        return fail(ctx, YAVO_ERR_INVALID, "bad device frame %dx%d pitch %zu", rows, cols, pitch);
+    CK(cudaSetDevice(ctx->device));
+    return launch_repitch(ctx, static_cast<const uint8_t *>(d_pixels), pitch, slot0, n, rows, cols);
+}
+
+int yavo_download(yavo_ctx *ctx, int slot, uint8_t *pixels, int rows, int cols) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (!pixels || rows != ctx->slot_rows[slot] || cols != ctx->slot_cols[slot])
+        return fail(ctx, YAVO_ERR_INVALID, "slot %d holds %dx%d, asked for %dx%d", slot, ctx->slot_rows[slot],
+                    ctx->slot_cols[slot], rows, cols);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(pixels, cols, ctx->d_frames + ctx->frame_stride * slot, ctx->pitch, cols, rows,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- FastDetector ---------------------------------------------------------------------------------
+
+void yavo_ring_points(int xc, int yc, int32_t *out_xy) {
+    // net result of the reference's set-based generator for radius 3 (src/FastDetector.cc:50-112)
+    static const int8_t ring[16][2] = {{0, -3}, {1, -3}, {2, -2}, {3, -1}, {3, 0},  {3, 1},  {2, 2},   {1, 3},
+                                       {0, 3},  {-1, 3}, {-2, 2}, {-3, 1}, {-3, 0}, {-3, -1}, {-2, -2}, {-1, -3}};
+    for (int k = 0; k < 16; k++) {
+        out_xy[2 * k] = xc + ring[k][0];
+        out_xy[2 * k + 1] = yc + ring[k][1];
+    }
+}
+
+int yavo_fast_candidates(yavo_ctx *ctx, int slot, int cap, int32_t *out_rows, int32_t *out_cols,
+                         float *out_scores, int *n_cand) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (int r = check_uploaded(ctx, slot, 1)) return r;
+    CK(cudaSetDevice(ctx->device));
+    if (int r = launch_detect(ctx, slot, 1, true, true)) return r;
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_ncand + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int n = ctx->h_small[0];
+    if (n_cand) *n_cand = n;
+    if (n > ctx->max_cand)
+        return fail(ctx, YAVO_ERR_CAPACITY, "%d FAST candidates exceed max_cand=%d", n, ctx->max_cand);
+    const int m = std::min(n, cap);
+    if (m > 0) {
+        std::vector<yavo_ent> h(m);
+        CK(cudaMemcpyAsync(h.data(), ctx->d_cand + (size_t)slot * ctx->max_cand, sizeof(yavo_ent) * m,
+                           cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < m; i++) {
+            const uint32_t p = (uint32_t)h[i];
+            if (out_rows) out_rows[i] = (int32_t)(p >> 16);
+            if (out_cols) out_cols[i] = (int32_t)(p & 0xffffu);
+            if (out_scores) out_scores[i] = yavo_ent_score(h[i]);
+        }
+    }
+    return 0;
+}
+
+int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int32_t *out_cols,
+                     float *out_scores, int *n_out, int *n_cand) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (int r = check_uploaded(ctx, slot, 1)) return r;
+    if (max_kp <= 0) max_kp = ctx->max_kp;
+    if (max_kp > ctx->max_kp)
+        return fail(ctx, YAVO_ERR_CAPACITY, "max_kp %d exceeds the context's %d", max_kp, ctx->max_kp);
+    CK(cudaSetDevice(ctx->device));
+    if (int r = launch_detect(ctx, slot, 1, true, true)) return r;
+    if (int r = launch_select(ctx, slot, 1, max_kp)) return r;
+    CK(cudaMemcpyAsync(ctx->h_small + 1, ctx->d_ncand + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small + 2, ctx->d_nkp + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    if (int r = check_status(ctx)) return r;  // synchronises
+    const int n = ctx->h_small[2];
+    if (n_cand) *n_cand = ctx->h_small[1];
+    if (n_out) *n_out = n;
+    const size_t o = (size_t)slot * ctx->max_kp;
+    if (n > 0) {
+        if (out_rows) CK(cudaMemcpyAsync(out_rows, ctx->d_kp_row + o, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_cols) CK(cudaMemcpyAsync(out_cols, ctx->d_kp_col + o, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_scores)
+            CK(cudaMemcpyAsync(out_scores, ctx->d_kp_score + o, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+// ---- Brief ----------------------------------------------------------------------------------------
+
+int yavo_set_brief_offsets(yavo_ctx *ctx, const int32_t *offsets) {
+    if (!ctx || !offsets) return YAVO_ERR_INVALID;
+    uint32_t packed[256];
+    for (int j = 0; j < 256; j++) {
+        uint32_t w = 0;
+        for (int k = 0; k < 4; k++) {
+            const int v = offsets[4 * j + k];
+            if (v < -8 || v > 8) return fail(ctx, YAVO_ERR_INVALID, "offset %d of test %d outside [-8,8]", v, j);
+            w |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
+        }
+        packed[j] = w;
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_offs, packed, sizeof packed, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->offs_set = true;
+    return 0;
+}
+
+static int ensure_blur(yavo_ctx *ctx, int slot) {
+    if (ctx->slot_blur_valid[slot]) return 0;
+    return launch_detect(ctx, slot, 1, false, true);
+}
+
+int yavo_blurred(yavo_ctx *ctx, int slot, uint8_t *out, int rows, int cols) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (int r = check_uploaded(ctx, slot, 1)) return r;
+    if (!out || rows != ctx->slot_rows[slot] || cols != ctx->slot_cols[slot])
+        return fail(ctx, YAVO_ERR_INVALID, "slot %d holds %dx%d", slot, ctx->slot_rows[slot], ctx->slot_cols[slot]);
+    CK(cudaSetDevice(ctx->device));
+    if (int r = ensure_blur(ctx, slot)) return r;
+    CK(cudaMemcpy2DAsync(out, cols, ctx->d_blur + ctx->frame_stride * slot, ctx->pitch, cols, rows,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int yavo_brief_describe(yavo_ctx *ctx, int slot, const int32_t *rows, const int32_t *cols, int n,
+                        uint8_t *out_desc, uint8_t *out_valid, int *n_oob) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (int r = check_uploaded(ctx, slot, 1)) return r;
+    if (n < 0 || (n > 0 && (!rows || !cols || !out_desc))) return fail(ctx, YAVO_ERR_INVALID, "bad point list");
+    if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
+    if (n_oob) *n_oob = 0;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    if (n > ctx->pt_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_pt_row) CK(cudaFree(ctx->d_pt_row));
+        if (ctx->d_pt_col) CK(cudaFree(ctx->d_pt_col));
+        if (ctx->d_pt_desc) CK(cudaFree(ctx->d_pt_desc));
+        if (ctx->d_pt_valid) CK(cudaFree(ctx->d_pt_valid));
+        ctx->d_pt_row = ctx->d_pt_col = nullptr;
+        ctx->d_pt_desc = nullptr;
+        ctx->d_pt_valid = nullptr;
+        ctx->pt_cap = 0;
+        const int cap = std::max(n, 4096);
+        CK(dalloc(&ctx->d_pt_row, cap));
+        CK(dalloc(&ctx->d_pt_col, cap));
+        CK(dalloc(&ctx->d_pt_desc, (size_t)cap * 8));
+        CK(dalloc(&ctx->d_pt_valid, cap));
+        ctx->pt_cap = cap;
+    }
+    if (int r = ensure_blur(ctx, slot)) return r;
+    const int H = ctx->slot_rows[slot], W = ctx->slot_cols[slot];
+    CK(cudaMemcpyAsync(ctx->d_pt_row, rows, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_pt_col, cols, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_noob, 0, sizeof(int), ctx->stream));
+    dim3 grid((n + K4_THREADS / 32 - 1) / (K4_THREADS / 32), 1);
+    PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(ctx->d_blur + ctx->frame_stride * slot, ctx->frame_stride,
+                                                       ctx->pitch, H, W, ctx->d_offs, ctx->d_pt_row, ctx->d_pt_col,
+                                                       nullptr, n, n, ctx->d_pt_desc, ctx->d_pt_valid, ctx->d_noob));
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(out_desc, ctx->d_pt_desc, 32 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_valid) CK(cudaMemcpyAsync(out_valid, ctx->d_pt_valid, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_noob, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n_oob) *n_oob = ctx->h_small[0];
+    return 0;
+}
+
+static int match_device(yavo_ctx *ctx, const uint32_t *dq, int n1, const uint32_t *dt, int n2, int32_t *o_idx,
+                        int32_t *o_dist, int32_t *o_sec) {
+    const int chunks = choose_chunks(n1, n2, 1);
+    const int chunk = std::max(1, (std::max(n2, 1) + chunks - 1) / chunks);
+    if (int r = ensure_partials(ctx, (size_t)n1 * chunks)) return r;
+    dim3 grid((n1 + MQ - 1) / MQ, chunks, 1);
+    PROF(KC_MATCH, match_partial_kernel<<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk, chunks, n1,
+                                                       ctx->d_part_key, ctx->d_part_sec));
+    CK_LAUNCH();
+    PROF(KC_MATCH_REDUCE, match_reduce_kernel<<<dim3((n1 + 127) / 128, 1), 128, 0, ctx->stream>>>(
+        ctx->d_part_key, ctx->d_part_sec, nullptr, n1, 0, nullptr, n2, 0, chunk, chunks, n1, o_idx, o_dist, o_sec));
+    CK_LAUNCH();
+    return 0;
+}
+
+int yavo_match(yavo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2, int32_t *out_idx,
+               int32_t *out_dist, int32_t *out_second, int32_t *out_rev_idx) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    if (n1 < 0 || n2 < 0 || (n1 > 0 && (!d1 || !out_idx || !out_dist)) || (n2 > 0 && !d2))
+        return fail(ctx, YAVO_ERR_INVALID, "bad descriptor sets");
+    if (n1 >= (1 << 22) || n2 >= (1 << 22)) return fail(ctx, YAVO_ERR_CAPACITY, "descriptor sets are limited to 2^22-1");
+    CK(cudaSetDevice(ctx->device));
+    if (n1 > ctx->mq_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_mq) CK(cudaFree(ctx->d_mq));
+        ctx->d_mq = nullptr; ctx->mq_cap = 0;
+        CK(dalloc(&ctx->d_mq, (size_t)n1 * 8));
+        ctx->mq_cap = n1;
+    }
+    if (n2 > ctx->mt_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_mt) CK(cudaFree(ctx->d_mt));
+        ctx->d_mt = nullptr; ctx->mt_cap = 0;
+        CK(dalloc(&ctx->d_mt, (size_t)n2 * 8));
+        ctx->mt_cap = n2;
+    }
+    const int mo = std::max(n1, n2);
+    if (mo > ctx->mo_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_mo_idx) CK(cudaFree(ctx->d_mo_idx));
+        if (ctx->d_mo_dist) CK(cudaFree(ctx->d_mo_dist));
+        if (ctx->d_mo_sec) CK(cudaFree(ctx->d_mo_sec));
+        ctx->d_mo_idx = ctx->d_mo_dist = ctx->d_mo_sec = nullptr; ctx->mo_cap = 0;
+        CK(dalloc(&ctx->d_mo_idx, mo));
+        CK(dalloc(&ctx->d_mo_dist, mo));
+        CK(dalloc(&ctx->d_mo_sec, mo));
+        ctx->mo_cap = mo;
+    }
+    if (n1 > 0) CK(cudaMemcpyAsync(ctx->d_mq, d1, 32 * (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
+    if (n2 > 0) CK(cudaMemcpyAsync(ctx->d_mt, d2, 32 * (size_t)n2, cudaMemcpyHostToDevice, ctx->stream));
+    if (n1 > 0) {
+        if (int r = match_device(ctx, ctx->d_mq, n1, ctx->d_mt, n2, ctx->d_mo_idx, ctx->d_mo_dist, ctx->d_mo_sec)) return r;
+        CK(cudaMemcpyAsync(out_idx, ctx->d_mo_idx, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out_dist, ctx->d_mo_dist, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
+        if (out_second) CK(cudaMemcpyAsync(out_second, ctx->d_mo_sec, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (out_rev_idx && n2 > 0) {
+        // cross-check extension: the same kernel with the roles swapped
+        if (int r = match_device(ctx, ctx->d_mt, n2, ctx->d_mq, n1, ctx->d_mo_idx, ctx->d_mo_dist, ctx->d_mo_sec)) return r;
+        CK(cudaMemcpyAsync(out_rev_idx, ctx->d_mo_idx, 4 * (size_t)n2, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *keep) {
+    if (n <= 0 || !dist || !keep) return 0;  // the reference dereferences end() on an empty list (UB)
+    int mn = INT_MAX;
+    for (int i = 0; i < n; i++) mn = std::min(mn, dist[i]);
+    const long long lim = std::max(2LL * mn, (long long)threshold);
+    int kept = 0;
+    for (int i = 0; i < n; i++) {
+        keep[i] = dist[i] < lim ? 1 : 0;
+        kept += keep[i];
+    }
+    return kept;
+}
+
+// ---- batch front end -------------------------------------------------------------------------------
+
+int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (n == 0) return 0;
+    if (int r = check_uploaded(ctx, slot0, n)) return r;
+    if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
+    if (int r = launch_detect(ctx, slot0, n, true, true)) return r;
+    if (int r = launch_select(ctx, slot0, n, ctx->max_kp)) return r;
+    const size_t o = (size_t)slot0 * ctx->max_kp;
+    {
+        dim3 grid((ctx->max_kp + K4_THREADS / 32 - 1) / (K4_THREADS / 32), n);
+        PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(
+            ctx->d_blur + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, H, W, ctx->d_offs,
+            ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_nbk + slot0, 0, ctx->max_kp, ctx->d_desc + o * 8, nullptr,
+            nullptr));
+        CK_LAUNCH();
+    }
+    if (do_match && n > 1) {
+        const int pairs = n - 1;
+        const int chunks = choose_chunks(ctx->max_kp, ctx->max_kp, pairs);
+        const int chunk = (ctx->max_kp + chunks - 1) / chunks;
+        if (int r = ensure_partials(ctx, (size_t)pairs * ctx->max_kp * chunks)) return r;
+        // pair p: queries = slot0+p, train = slot0+p+1; results stored at the train slot
+        dim3 grid((ctx->max_kp + MQ - 1) / MQ, chunks, pairs);
+        PROF(KC_MATCH, match_partial_kernel<<<grid, MQ, 0, ctx->stream>>>(
+            ctx->d_desc + o * 8, ctx->d_nbk + slot0, 0, ctx->d_desc + o * 8, ctx->d_nbk + slot0, 0,
+            (size_t)ctx->max_kp * 8, 0, 1, chunk, chunks, ctx->max_kp, ctx->d_part_key, ctx->d_part_sec));
+        CK_LAUNCH();
+        PROF(KC_MATCH_REDUCE, match_reduce_kernel<<<dim3((ctx->max_kp + 127) / 128, pairs), 128, 0, ctx->stream>>>(
+            ctx->d_part_key, ctx->d_part_sec, ctx->d_nbk + slot0, 0, 0, ctx->d_nbk + slot0, 0, 1, chunk, chunks,
+            ctx->max_kp, ctx->d_midx + o + ctx->max_kp, ctx->d_mdist + o + ctx->max_kp, nullptr));
+        CK_LAUNCH();
+    }
+    return 0;
+}
+
+int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols, float *scores,
+                     uint8_t *desc, int32_t *match_idx, int32_t *match_dist) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (n == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t o = (size_t)slot0 * ctx->max_kp, cnt = (size_t)n * ctx->max_kp;
+    if (n_kp) CK(cudaMemcpyAsync(n_kp, ctx->d_nbk + slot0, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rows) CK(cudaMemcpyAsync(rows, ctx->d_bk_row + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (cols) CK(cudaMemcpyAsync(cols, ctx->d_bk_col + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scores) CK(cudaMemcpyAsync(scores, ctx->d_bk_score + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (desc) CK(cudaMemcpyAsync(desc, ctx->d_desc + o * 8, 32 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (match_idx) CK(cudaMemcpyAsync(match_idx, ctx->d_midx + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (match_dist) CK(cudaMemcpyAsync(match_dist, ctx->d_mdist + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    return check_status(ctx);  // synchronises; reports a candidate-list overflow
+}
+
+int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
+                            int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores, uint8_t *desc,
+                            int32_t *match_idx, int32_t *match_dist) {
+    if (int r = yavo_upload_batch(ctx, 0, n, pixels, rows, cols)) return r;
+    if (int r = yavo_frontend_batch(ctx, 0, n, do_match)) return r;
+    return yavo_fetch_batch(ctx, 0, n, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist);
+}
+
+}  // extern "C"

@@ -1,0 +1,717 @@
+// yavo_kernels.cuh — sm_100a kernels of the YA_VO front end (detect+blur, compact+score, exact
+// top-K select, BRIEF, Hamming match).  No tensor cores: the whole path is byte/integer work
+// (VABSDIFF4 / IDP.4A / IDP.2A / POPC / LOP3) staged through shared memory.  See DESIGN.md for the
+// data layout and the roofline that bounds each kernel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fast_core.h"
+#include "select_serial.h"
+
+namespace yavo {
+
+// ================================================================================================
+// K0  re-pitch: dense uploaded pixels -> frame slots whose row pitch is a multiple of 128 bytes.
+// Image::Image deep-copies the pixels (reference src/Image.cc:8-13); here the copy lands in HBM in
+// the layout K1 reads with aligned word loads.  One thread per destination word.
+// ================================================================================================
+__global__ void repitch_kernel(const uint8_t *__restrict__ src, size_t src_pitch, size_t src_frame,
+                               uint8_t *__restrict__ dst, int dst_pitch, size_t dst_frame, int cols) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (4 * w >= dst_pitch) return;
+    const uint8_t *s = src + (size_t)blockIdx.z * src_frame + (size_t)blockIdx.y * src_pitch;
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int c = 4 * w + b;
+        if (c < cols) v |= (uint32_t)__ldg(s + c) << (8 * b);
+    }
+    reinterpret_cast<uint32_t *>(dst + (size_t)blockIdx.z * dst_frame + (size_t)blockIdx.y * dst_pitch)[w] = v;
+}
+
+// ================================================================================================
+// K1  detect + blur
+// One CTA per 128x32 pixel tile of one frame.  The tile plus a 4-pixel halo is staged in shared
+// memory as aligned 32-bit words (frame rows are stored with a pitch that is a multiple of 128 so
+// every tile row starts word-aligned and is read with coalesced 4-byte loads).  Two products come
+// out of the single read of the pixels:
+//   * the FAST segment-test bitmask (1 bit per pixel, one word per 32 pixels) and per-row corner
+//     counts (reference src/FastDetector.cc:298-320); 4 pixels per thread with byte-SIMD
+//   * the 9x9 sigma-2.5 fixed-point Gaussian of the tile (reference src/BriefDescriptor.cc:90),
+//     horizontal pass by IDP.4A into 16-bit vertical pairs, vertical pass by IDP.2A
+// ================================================================================================
+constexpr int TW = 128;            // tile width  (pixels)
+constexpr int TH = 32;             // tile height (pixels)
+constexpr int HALO = 4;
+constexpr int SW = (TW + 2 * HALO) / 4;  // 34 words per staged row
+constexpr int SH = TH + 2 * HALO;        // 40 staged rows
+constexpr int K1_THREADS = 256;
+
+__device__ __forceinline__ int reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+template <bool DO_FAST, bool DO_BLUR>
+__global__ void __launch_bounds__(K1_THREADS)
+detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
+                   uint8_t *__restrict__ blur, uint32_t *__restrict__ mask, int mask_words,
+                   int *__restrict__ rowcnt, int rows_alloc) {
+    __shared__ uint32_t tile[SH][SW + 1];          // +1 word: rows land on different banks
+    __shared__ uint4 hpair[SH / 2][TW / 4];        // [row pair][quad] -> 4 x (h[even] | h[odd] << 16)
+
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const uint8_t *img = frames + (size_t)f * frame_stride;
+    const int tid = threadIdx.x;
+
+    // ---- stage tile rows y0-4 .. y0+35 (reflected into the image), cols x0-4 .. x0+131 ----------
+    const int pitch_w = pitch >> 2;
+    const int wbase = (x0 - HALO) >> 2;  // may be -1 for the first tile column
+    for (int i = tid; i < SH * SW; i += K1_THREADS) {
+        const int tr = i / SW, tw = i - tr * SW;
+        const int gr = reflect101(y0 - HALO + tr, H);
+        int gw = wbase + tw;
+        gw = gw < 0 ? 0 : (gw >= pitch_w ? pitch_w - 1 : gw);
+        tile[tr][tw] = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gr * pitch) + gw);
+    }
+    const bool edge_cols = DO_BLUR && (x0 == 0 || x0 + TW + HALO > W);
+    if (edge_cols) {
+        __syncthreads();
+        // BORDER_REFLECT_101 for the columns outside [0,W) that valid outputs can read
+        // (x0-4..-1 on the left, W..W+3 on the right)
+        uint8_t *tb = reinterpret_cast<uint8_t *>(&tile[0][0]);
+        for (int i = tid; i < SH * 8; i += K1_THREADS) {
+            const int tr = i >> 3, j = i & 7;
+            const int gc = (j < 4) ? (j - 4) : (W + j - 4);
+            const int tc = gc - (x0 - HALO);
+            if (tc < 0 || tc >= TW + 2 * HALO) continue;
+            if (j < 4 && x0 != 0) continue;
+            const int gr = reflect101(y0 - HALO + tr, H);
+            tb[tr * (SW + 1) * 4 + tc] = __ldg(img + (size_t)gr * pitch + reflect101(gc, W));
+        }
+    }
+    __syncthreads();
+
+    const int lane = tid & 31, warp = tid >> 5;
+
+    if (DO_BLUR) {
+        // horizontal pass: (SH/2) row pairs x 32 quads; thread -> one quad of one row pair
+        for (int i = tid; i < (SH / 2) * (TW / 4); i += K1_THREADS) {
+            const int rp = i >> 5, q = i & 31;
+            const uint32_t *ra = &tile[2 * rp][q + 1];
+            const uint32_t *rb = &tile[2 * rp + 1][q + 1];
+            uint32_t ha[4], hb[4];
+            yavo_blur_h4(ra[-1], ra[0], ra[1], ha);
+            yavo_blur_h4(rb[-1], rb[0], rb[1], hb);
+            hpair[rp][q] = make_uint4(ha[0] | (hb[0] << 16), ha[1] | (hb[1] << 16),
+                                      ha[2] | (hb[2] << 16), ha[3] | (hb[3] << 16));
+        }
+    }
+
+    if (DO_FAST) {
+        // segment test: warp -> tile row, lane -> quad; 8 lanes assemble one 32-pixel mask word
+        for (int tr = warp; tr < TH; tr += K1_THREADS / 32) {
+            const int gr = y0 + tr;
+            uint32_t nib = 0;
+            if (gr >= 4 && gr < H - 4) {  // warp-uniform
+                const int sr = tr + HALO;
+                bool pre;
+                nib = yavo_fast4(&tile[sr - 3][lane + 1], &tile[sr - 2][lane + 1], &tile[sr - 1][lane + 1],
+                                 &tile[sr][lane + 1], &tile[sr + 1][lane + 1], &tile[sr + 2][lane + 1],
+                                 &tile[sr + 3][lane + 1], &pre);
+                // interior columns only: 4 <= col < W-4
+                const int gc = x0 + 4 * lane;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (gc + b < 4 || gc + b >= W - 4) nib &= ~(1u << b);
+            }
+            uint32_t v = nib << (4 * (lane & 7));
+            v |= __shfl_xor_sync(0xffffffffu, v, 1);
+            v |= __shfl_xor_sync(0xffffffffu, v, 2);
+            v |= __shfl_xor_sync(0xffffffffu, v, 4);
+            if (gr < H) {
+                if ((lane & 7) == 0)
+                    mask[((size_t)f * rows_alloc + gr) * mask_words + (x0 >> 5) + (lane >> 3)] = v;
+                // row total for this tile: lanes 0,8,16,24 hold the four words
+                int c = ((lane & 7) == 0) ? __popc(v) : 0;
+                c += __shfl_xor_sync(0xffffffffu, c, 8);
+                c += __shfl_xor_sync(0xffffffffu, c, 16);
+                if (lane == 0 && c) atomicAdd(&rowcnt[(size_t)f * rows_alloc + gr], c);
+            }
+        }
+    }
+
+    if (DO_BLUR) {
+        __syncthreads();
+        // vertical pass: output row pairs (tile rows 2j, 2j+1) x 32 quads
+        for (int i = tid; i < (TH / 2) * (TW / 4); i += K1_THREADS) {
+            const int j = i >> 5, q = i & 31;
+            // output tile row t = 2j -> staged row s = t + 4; taps s-4 .. s+5 = staged rows 2j .. 2j+9
+            uint4 p[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) p[k] = hpair[j + k][q];
+            uint32_t o0[4], o1[4];
+            {
+                const uint32_t P[5] = {p[0].x, p[1].x, p[2].x, p[3].x, p[4].x};
+                yavo_blur_v2(P, &o0[0], &o1[0]);
+            }
+            {
+                const uint32_t P[5] = {p[0].y, p[1].y, p[2].y, p[3].y, p[4].y};
+                yavo_blur_v2(P, &o0[1], &o1[1]);
+            }
+            {
+                const uint32_t P[5] = {p[0].z, p[1].z, p[2].z, p[3].z, p[4].z};
+                yavo_blur_v2(P, &o0[2], &o1[2]);
+            }
+            {
+                const uint32_t P[5] = {p[0].w, p[1].w, p[2].w, p[3].w, p[4].w};
+                yavo_blur_v2(P, &o0[3], &o1[3]);
+            }
+            const int gr = y0 + 2 * j, gc = x0 + 4 * q;
+            if (gc < pitch) {
+                uint8_t *dst = blur + (size_t)f * frame_stride + (size_t)gr * pitch + gc;
+                if (gr < H)
+                    *reinterpret_cast<uint32_t *>(dst) = o0[0] | (o0[1] << 8) | (o0[2] << 16) | (o0[3] << 24);
+                if (gr + 1 < H)
+                    *reinterpret_cast<uint32_t *>(dst + pitch) = o1[0] | (o1[1] << 8) | (o1[2] << 16) | (o1[3] << 24);
+            }
+        }
+    }
+}
+
+// ================================================================================================
+// K2  compact + score
+// Turns the corner bitmask into the candidate list in scan (row-major) order — the order the
+// reference appends to retCorners (src/FastDetector.cc:298-324) — and computes the Harris response
+// (:244-273) of each candidate from the raw pixels (5x5 window, L2-resident).
+// grid (row slabs, frames); one warp per row.
+// ================================================================================================
+constexpr int K2_THREADS = 256;
+constexpr int K2_ROWS = K2_THREADS / 32;
+
+__global__ void __launch_bounds__(K2_THREADS)
+compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
+                     const uint32_t *__restrict__ mask, int mask_words, const int *__restrict__ rowcnt,
+                     int rows_alloc, yavo_ent *__restrict__ cand, int max_cand, int *__restrict__ ncand) {
+    __shared__ int red[K2_THREADS / 32];
+    __shared__ int rowoff[K2_ROWS + 1];
+    const int f = blockIdx.y;
+    const int r0 = blockIdx.x * K2_ROWS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int *rc = rowcnt + (size_t)f * rows_alloc;
+
+    // candidates in rows above this slab
+    int s = 0;
+    for (int r = tid; r < r0; r += K2_THREADS) s += rc[r];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int base = 0;
+        for (int w = 0; w < K2_THREADS / 32; w++) base += red[w];
+        rowoff[0] = base;
+        for (int k = 0; k < K2_ROWS; k++) {
+            const int r = r0 + k;
+            rowoff[k + 1] = rowoff[k] + (r < H ? rc[r] : 0);
+        }
+        if (blockIdx.x == gridDim.x - 1) ncand[f] = rowoff[K2_ROWS];
+    }
+    __syncthreads();
+
+    const int row = r0 + warp;
+    if (row >= H) return;
+    int pos = rowoff[warp];
+    if (rowoff[warp + 1] == pos) return;  // empty row
+    const uint8_t *img = frames + (size_t)f * frame_stride;
+    const uint32_t *mrow = mask + ((size_t)f * rows_alloc + row) * mask_words;
+    const int nwords = (W + 31) >> 5;
+    for (int w0 = 0; w0 < nwords; w0 += 32) {
+        const int wi = w0 + lane;
+        uint32_t m = (wi < nwords) ? mrow[wi] : 0u;
+        const int c = __popc(m);
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        int p = pos + incl - c;
+        pos += __shfl_sync(0xffffffffu, incl, 31);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            const int col = wi * 32 + b;
+            if (p < max_cand) {
+                int a, bb, cc;
+                yavo_structure_tensor(
+                    [&](int r, int cidx) { return (int)__ldg(img + (size_t)r * pitch + cidx); }, row, col, &a,
+                    &bb, &cc);
+                cand[(size_t)f * max_cand + p] =
+                    yavo_make_ent(yavo_harris_from_tensor(a, bb, cc), ((uint32_t)row << 16) | (uint32_t)col);
+            }
+            p++;
+        }
+    }
+}
+
+// ================================================================================================
+// K3  exact top-K select  (std::sort replay; see select_serial.h)
+// One CTA per frame.  Level-synchronous replay of libstdc++'s introsort partition tree over the
+// candidate list, pruned to ranges that start below K.  Large ranges are partitioned by the whole
+// CTA, medium ones by single warps, ranges of <= SEL_SERIAL elements by single threads.  A
+// partition is the parallel form of __unguarded_partition: the i-th element from the left that
+// does not sort before the pivot (L_i) is swapped with the i-th element from the right that the
+// pivot does not sort before (R_i) while L_i < R_i; with m such swaps the cut is
+// min(L_{m+1}, R_m).  Stopper positions are found by rank (ballot + scan) and scattered into a
+// scratch list; the swaps are independent.
+// ================================================================================================
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int SEL_SMEM_ENTS = 4096;     // candidates kept in shared memory once the active prefix fits
+constexpr int SEL_WARP_MAX = 256;       // ranges up to this size are partitioned by one warp
+constexpr int SEL_SERIAL = 32;          // ranges up to this size are finished by one thread
+constexpr int SEL_QCAP = 256;           // per-level range queue
+constexpr int SEL_SCAP = 1024;          // serial work list
+
+struct SelRange {
+    int f, l, d;
+};
+
+struct SelShared {
+    SelRange q[2][SEL_QCAP];
+    SelRange serial[SEL_SCAP];
+    uint16_t wscratch[SEL_WARPS][2][SEL_WARP_MAX / 2 + 2];
+    int qn[2];
+    int nserial;
+    int wtot[SEL_WARPS];
+    int bcast[4];
+};
+
+// children of a partition / initial range: route by size
+__device__ __forceinline__ void sel_route(SelShared &S, int nq, yavo_ent *A, int f, int l, int d, int K) {
+    if (f >= K || l - f <= 1) return;
+    const int n = l - f;
+    if (n <= SEL_SERIAL) {
+        const int i = atomicAdd(&S.nserial, 1);
+        if (i < SEL_SCAP) S.serial[i] = {f, l, d};
+        else { atomicSub(&S.nserial, 1); yavo_serial_introsort(A, f, l, d, K); }
+    } else if (d == 0) {
+        // depth limit reached: libstdc++ heapsorts the range; single thread, off the common path
+        yavo_serial_heapsort(A, f, l);
+    } else {
+        const int i = atomicAdd(&S.qn[nq], 1);
+        if (i < SEL_QCAP) S.q[nq][i] = {f, l, d};
+        else { atomicSub(&S.qn[nq], 1); yavo_serial_introsort(A, f, l, d, K); }
+    }
+}
+
+// whole-CTA partition of [f,l); returns the cut to every thread.  Lpos/Rpos: global scratch.
+__device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint32_t *Lpos, uint32_t *Rpos) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = l - f;
+    if (tid == 0) yavo_median_to_first(A, f, l);
+    __syncthreads();
+    const yavo_ent piv = A[f];
+    const int cap = n / 2 + 1;
+    int runL = 0, runR = 0;
+    for (int base = 0; base < n - 1; base += SEL_THREADS) {
+        const int i = base + tid;
+        const bool in = i < n - 1;
+        const int pL = f + 1 + i, pR = l - 1 - i;
+        const bool sL = in && !yavo_before(A[pL], piv);
+        const bool sR = in && !yavo_before(piv, A[pR]);
+        const unsigned bL = __ballot_sync(0xffffffffu, sL), bR = __ballot_sync(0xffffffffu, sR);
+        if (lane == 0) S.wtot[warp] = __popc(bL) | (__popc(bR) << 16);
+        __syncthreads();
+        int preL = 0, preR = 0, totL = 0, totR = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_WARPS; w++) {
+            const int t = S.wtot[w];
+            if (w < warp) { preL += t & 0xffff; preR += t >> 16; }
+            totL += t & 0xffff;
+            totR += t >> 16;
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        const int rL = runL + preL + __popc(bL & lt), rR = runR + preR + __popc(bR & lt);
+        if (sL && rL < cap) Lpos[rL] = pL;
+        if (sR && rR < cap) Rpos[rR] = pR;
+        runL += totL;
+        runR += totR;
+        __syncthreads();
+    }
+    const int nL = min(runL, cap), nR = min(runR, cap);
+    const int npairs = min(nL, nR);
+    int cnt = 0;
+    for (int i = tid; i < npairs; i += SEL_THREADS) {
+        const uint32_t a = Lpos[i], b = Rpos[i];
+        if (a < b) {
+            const yavo_ent t = A[a];
+            A[a] = A[b];
+            A[b] = t;
+            cnt++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) S.wtot[warp] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0;
+        for (int w = 0; w < SEL_WARPS; w++) m += S.wtot[w];
+        uint32_t cut = 0xffffffffu;
+        if (m < nL) cut = Lpos[m];
+        if (m >= 1) cut = min(cut, Rpos[m - 1]);
+        S.bcast[0] = (int)cut;
+    }
+    __syncthreads();
+    const int cut = S.bcast[0];
+    __syncthreads();
+    return cut;
+}
+
+// single-warp partition of [f,l), n <= SEL_WARP_MAX; positions relative to f in 16-bit scratch
+__device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *Lpos = S.wscratch[warp][0], *Rpos = S.wscratch[warp][1];
+    const int n = l - f;
+    if (lane == 0) yavo_median_to_first(A, f, l);
+    __syncwarp();
+    const yavo_ent piv = A[f];
+    const int cap = n / 2 + 1;
+    int runL = 0, runR = 0;
+    for (int base = 0; base < n - 1; base += 32) {
+        const int i = base + lane;
+        const bool in = i < n - 1;
+        const bool sL = in && !yavo_before(A[f + 1 + i], piv);
+        const bool sR = in && !yavo_before(piv, A[l - 1 - i]);
+        const unsigned bL = __ballot_sync(0xffffffffu, sL), bR = __ballot_sync(0xffffffffu, sR);
+        const unsigned lt = (1u << lane) - 1u;
+        const int rL = runL + __popc(bL & lt), rR = runR + __popc(bR & lt);
+        if (sL && rL < cap) Lpos[rL] = (uint16_t)(1 + i);
+        if (sR && rR < cap) Rpos[rR] = (uint16_t)(n - 1 - i);
+        runL += __popc(bL);
+        runR += __popc(bR);
+    }
+    __syncwarp();
+    const int nL = min(runL, cap), nR = min(runR, cap);
+    const int npairs = min(nL, nR);
+    int cnt = 0;
+    for (int i = lane; i < npairs; i += 32) {
+        const int a = Lpos[i], b = Rpos[i];
+        if (a < b) {
+            const yavo_ent t = A[f + a];
+            A[f + a] = A[f + b];
+            A[f + b] = t;
+            cnt++;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    int cut = 0x7fffffff;
+    if (cnt < nL) cut = Lpos[cnt];
+    if (cnt >= 1) cut = min(cut, (int)Rpos[cnt - 1]);
+    __syncwarp();
+    return f + cut;
+}
+
+// checkBoundry of reference src/BriefDescriptor.cc:128-136 as computeBrief calls it (:97)
+__device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
+    return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
+                   uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
+                   int32_t *__restrict__ kp_row, int32_t *__restrict__ kp_col, float *__restrict__ kp_score,
+                   int *__restrict__ nkp,
+                   // compacted (checkBoundry-admitted) list that BRIEF / the matcher consume
+                   int32_t *__restrict__ bk_row, int32_t *__restrict__ bk_col, float *__restrict__ bk_score,
+                   int32_t *__restrict__ bk_id, int *__restrict__ nbk, int *__restrict__ status) {
+    extern __shared__ __align__(16) unsigned char sel_smem_raw[];
+    SelShared &S = *reinterpret_cast<SelShared *>(sel_smem_raw);
+    yavo_ent *sbuf = reinterpret_cast<yavo_ent *>(sel_smem_raw + ((sizeof(SelShared) + 15) & ~size_t(15)));
+
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int N = ncand[f];
+    if (N > max_cand) {  // candidate buffer overflow: report, never return a silently truncated order
+        if (tid == 0) { atomicExch(status, 1); nkp[f] = 0; nbk[f] = 0; }
+        return;
+    }
+    yavo_ent *G = cand_all + (size_t)f * max_cand;
+    uint32_t *Lpos = scratch_all + (size_t)blockIdx.x * (size_t)(max_cand + 4);
+    uint32_t *Rpos = Lpos + (max_cand / 2 + 2);
+
+    yavo_ent *A = G;
+    bool in_smem = false;
+    if (tid == 0) { S.qn[0] = S.qn[1] = 0; S.nserial = 0; }
+    __syncthreads();
+    if (N <= SEL_SMEM_ENTS) {
+        for (int i = tid; i < N; i += SEL_THREADS) sbuf[i] = G[i];
+        A = sbuf;
+        in_smem = true;
+        __syncthreads();
+    }
+    if (tid == 0 && N > 1) {
+        const int depth = 2 * (31 - __clz(N));
+        sel_route(S, 0, A, 0, N, depth, K);
+    }
+    __syncthreads();
+
+    int cur = 0;
+    while (S.qn[cur] > 0) {
+        const int nq = S.qn[cur];
+        const int nxt = cur ^ 1;
+        // move the active prefix into shared memory as soon as it fits
+        if (!in_smem) {
+            int E = 0;
+            for (int i = 0; i < nq; i++) E = max(E, S.q[cur][i].l);
+            for (int i = 0; i < S.nserial; i++) E = max(E, S.serial[i].l);
+            E = max(E, min(N, K));  // everything that can still move or be output
+            if (E <= SEL_SMEM_ENTS) {
+                for (int i = tid; i < E; i += SEL_THREADS) sbuf[i] = G[i];
+                A = sbuf;
+                in_smem = true;
+                __syncthreads();
+            }
+        }
+        // (a) large ranges: the whole CTA, one after another
+        for (int i = 0; i < nq; i++) {
+            const SelRange r = S.q[cur][i];
+            if (r.l - r.f <= SEL_WARP_MAX) continue;
+            const int cut = sel_block_partition(S, A, r.f, r.l, Lpos, Rpos);
+            if (tid == 0) sel_route(S, nxt, A, cut, r.l, r.d - 1, K);
+            if (tid == 32) sel_route(S, nxt, A, r.f, cut, r.d - 1, K);
+        }
+        // (b) medium ranges: one warp each
+        for (int i = warp; i < nq; i += SEL_WARPS) {
+            const SelRange r = S.q[cur][i];
+            if (r.l - r.f > SEL_WARP_MAX) continue;
+            const int cut = sel_warp_partition(S, A, r.f, r.l);
+            if (lane == 0) sel_route(S, nxt, A, cut, r.l, r.d - 1, K);
+            if (lane == 1) sel_route(S, nxt, A, r.f, cut, r.d - 1, K);
+        }
+        __syncthreads();
+        if (tid == 0) S.qn[cur] = 0;
+        cur = nxt;
+        __syncthreads();
+    }
+    // (c) small ranges: one thread each (introsort tail + the final insertion sort)
+    {
+        const int ns = min(S.nserial, SEL_SCAP);
+        for (int i = tid; i < ns; i += SEL_THREADS) {
+            const SelRange r = S.serial[i];
+            yavo_serial_introsort(A, r.f, r.l, r.d, K);
+        }
+    }
+    __syncthreads();
+
+    // ---- outputs: first min(N,K) in order, plus the checkBoundry-compacted list -------------------
+    const int nout = min(N, K);
+    int run = 0;
+    for (int base = 0; base < nout; base += SEL_THREADS) {
+        const int i = base + tid;
+        bool ok = false;
+        int row = 0, col = 0;
+        float sc = 0.f;
+        if (i < nout) {
+            const yavo_ent e = A[i];
+            row = (int)((uint32_t)e >> 16);
+            col = (int)((uint32_t)e & 0xffffu);
+            sc = yavo_ent_score(e);
+            kp_row[(size_t)f * kp_stride + i] = row;
+            kp_col[(size_t)f * kp_stride + i] = col;
+            kp_score[(size_t)f * kp_stride + i] = sc;
+            ok = brief_admits(row, col, H, W);
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) S.wtot[warp] = __popc(b);
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < SEL_WARPS; w++) {
+            const int t = S.wtot[w];
+            if (w < warp) pre += t;
+            tot += t;
+        }
+        if (ok) {
+            const int j = run + pre + __popc(b & ((1u << lane) - 1u));
+            bk_row[(size_t)f * kp_stride + j] = row;
+            bk_col[(size_t)f * kp_stride + j] = col;
+            bk_score[(size_t)f * kp_stride + j] = sc;
+            bk_id[(size_t)f * kp_stride + j] = i;
+        }
+        run += tot;
+        __syncthreads();
+    }
+    if (tid == 0) { nkp[f] = nout; nbk[f] = run; }
+}
+
+// ================================================================================================
+// K4  BRIEF  (reference src/BriefDescriptor.cc:86-124)
+// One warp per keypoint.  Lane l evaluates tests l, l+32, ..., l+224 on the smoothed plane; a
+// ballot per group of 32 tests yields descriptor word w directly (bit j of the descriptor is bit
+// j%32 of word j/32, i.e. byte j/8 bit j%8 little-endian — the reference layout).
+// Reads follow Image::getPixelVal's unchecked linear indexing (src/Image.cc:15-17): a column index
+// equal to W wraps to column 0 of the next row; a linear index >= H*W (undefined behaviour in the
+// reference) reads as 0 and is counted.
+// ================================================================================================
+constexpr int K4_THREADS = 256;
+
+__device__ __forceinline__ int brief_sample(const uint8_t *S, int pitch, int H, int W, int r, int c, bool *oob) {
+    if (c >= W) { c -= W; r += 1; }
+    if (r >= H) { *oob = true; return 0; }
+    return (int)__ldg(S + (size_t)r * pitch + c);
+}
+
+// offsets packed one test per word: byte0 = drow1, byte1 = dcol1, byte2 = drow2, byte3 = dcol2 (int8)
+__global__ void __launch_bounds__(K4_THREADS)
+brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, int H, int W,
+             const uint32_t *__restrict__ offs, const int32_t *__restrict__ rows,
+             const int32_t *__restrict__ cols, const int *__restrict__ n_per_frame, int n_fixed,
+             int kp_stride, uint32_t *__restrict__ desc, uint8_t *__restrict__ valid,
+             int *__restrict__ n_oob) {
+    __shared__ uint32_t soff[256];
+    for (int i = threadIdx.x; i < 256; i += K4_THREADS) soff[i] = offs[i];
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int n = n_per_frame ? n_per_frame[f] : n_fixed;
+    const int lane = threadIdx.x & 31;
+    const int kp = blockIdx.x * (K4_THREADS / 32) + (threadIdx.x >> 5);
+    if (kp >= n) return;
+    const int row = rows[(size_t)f * kp_stride + kp], col = cols[(size_t)f * kp_stride + kp];
+    uint32_t *d = desc + ((size_t)f * kp_stride + kp) * 8;
+    const bool ok = brief_admits(row, col, H, W);
+    if (valid && lane == 0) valid[(size_t)f * kp_stride + kp] = ok ? 1 : 0;
+    if (!ok) {
+        if (lane < 8) d[lane] = 0u;
+        return;
+    }
+    const uint8_t *S = blur + (size_t)f * frame_stride;
+    bool oob = false;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const uint32_t o = soff[32 * w + lane];
+        const int r1 = row + (int)(int8_t)(o & 0xff), c1 = col + (int)(int8_t)((o >> 8) & 0xff);
+        const int r2 = row + (int)(int8_t)((o >> 16) & 0xff), c2 = col + (int)(int8_t)(o >> 24);
+        const int va = brief_sample(S, pitch, H, W, r1, c1, &oob);
+        const int vb = brief_sample(S, pitch, H, W, r2, c2, &oob);
+        const unsigned word = __ballot_sync(0xffffffffu, va > vb);
+        if (lane == w) mine = word;
+    }
+    if (lane < 8) d[lane] = mine;
+    if (n_oob) {
+        const unsigned any = __ballot_sync(0xffffffffu, oob);
+        if (lane == 0 && any) atomicAdd(n_oob, 1);
+    }
+}
+
+// ================================================================================================
+// K5  Hamming match  (reference src/BriefDescriptor.cc:139-183)
+// Brute force over 256-bit descriptors held as 8 x u32.  A CTA owns MQ queries (one per thread,
+// descriptor in registers) and one chunk of the train set, staged through shared memory in tiles
+// and read as broadcast 128-bit loads; XOR + POPC per word.  Every thread keeps
+// key = dist << 22 | j, whose minimum is the reference's "first minimum wins" rule, and the second
+// smallest distance.  Chunk partials are combined by a small reduce kernel (deterministic, no
+// atomics).
+// ================================================================================================
+constexpr int MQ = 128;        // queries per CTA == threads
+constexpr int MT = 128;        // train descriptors per shared-memory tile
+constexpr uint32_t MATCH_NONE = 0xffffffffu;
+
+__global__ void __launch_bounds__(MQ)
+match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
+                     const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
+                     size_t set_stride_words, int q_set_offset, int t_set_offset, int chunk,
+                     int n_chunks, int out_stride, uint32_t *__restrict__ part_key,
+                     uint32_t *__restrict__ part_sec) {
+    __shared__ uint4 st[MT][2];
+    const int pair = blockIdx.z;
+    const uint32_t *dq = dq_all + (size_t)(pair + q_set_offset) * set_stride_words;
+    const uint32_t *dt = dt_all + (size_t)(pair + t_set_offset) * set_stride_words;
+    const int nq = nq_all ? nq_all[pair + q_set_offset] : nq_fixed;
+    const int nt = nt_all ? nt_all[pair + t_set_offset] : nt_fixed;
+    const int q0 = blockIdx.x * MQ;
+    if (q0 >= nq) return;
+    const int c = blockIdx.y;
+    const int j0 = c * chunk, j1 = min(nt, j0 + chunk);
+    const int q = q0 + threadIdx.x;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (q < nq) {
+        a0 = __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)q * 8));
+        a1 = __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)q * 8) + 1);
+    }
+    uint32_t best = MATCH_NONE, sec = MATCH_NONE;  // best: packed key; sec: distance only
+    for (int t0 = j0; t0 < j1; t0 += MT) {
+        const int nt_tile = min(MT, j1 - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nt_tile * 2; i += MQ)
+            st[i >> 1][i & 1] = __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)t0 * 8) + i);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < nt_tile; j++) {
+            const uint4 b0 = st[j][0], b1 = st[j][1];
+            const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) +
+                               __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
+                               __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+            const uint32_t key = (d << 22) | (uint32_t)(t0 + j);
+            // strict '<' on ascending j == min over key; second = second smallest distance
+            const uint32_t bd = best >> 22;
+            if (key < best) {
+                sec = (best == MATCH_NONE) ? sec : bd;
+                best = key;
+            } else if (d < sec) {
+                sec = d;
+            }
+        }
+    }
+    if (q < nq) {
+        part_key[((size_t)pair * out_stride + q) * n_chunks + c] = best;
+        part_sec[((size_t)pair * out_stride + q) * n_chunks + c] = sec;
+    }
+}
+
+__global__ void match_reduce_kernel(const uint32_t *__restrict__ part_key, const uint32_t *__restrict__ part_sec,
+                                    const int *__restrict__ nq_all, int nq_fixed, int q_set_offset,
+                                    const int *__restrict__ nt_all, int nt_fixed, int t_set_offset, int chunk,
+                                    int n_chunks, int out_stride, int32_t *__restrict__ out_idx,
+                                    int32_t *__restrict__ out_dist, int32_t *__restrict__ out_second) {
+    const int pair = blockIdx.y;
+    const int nq = nq_all ? nq_all[pair + q_set_offset] : nq_fixed;
+    const int nt = nt_all ? nt_all[pair + t_set_offset] : nt_fixed;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const int used = (nt + chunk - 1) / chunk;  // chunks that held any train descriptor
+    uint32_t best = MATCH_NONE, sec = MATCH_NONE;
+    for (int c = 0; c < used && c < n_chunks; c++) {
+        const uint32_t k = part_key[((size_t)pair * out_stride + q) * n_chunks + c];
+        const uint32_t s = part_sec[((size_t)pair * out_stride + q) * n_chunks + c];
+        if (k == MATCH_NONE) continue;
+        const uint32_t kd = k >> 22;
+        if (k < best) {
+            // old best distance becomes a second-best candidate, as does this chunk's second
+            uint32_t ns = (best == MATCH_NONE) ? sec : min(sec, best >> 22);
+            sec = min(ns, s);
+            best = k;
+        } else {
+            sec = min(sec, min(kd, s));
+        }
+    }
+    const size_t o = (size_t)pair * out_stride + q;
+    if (best == MATCH_NONE) {  // empty train set: reference leaves kp2 = (0,0,0), distance INT_MAX
+        out_idx[o] = -1;
+        out_dist[o] = 0x7fffffff;
+        if (out_second) out_second[o] = 0x7fffffff;
+    } else {
+        out_idx[o] = (int32_t)(best & 0x3fffffu);
+        out_dist[o] = (int32_t)(best >> 22);
+        if (out_second) out_second[o] = (sec == MATCH_NONE) ? 0x7fffffff : (int32_t)sec;
+    }
+}
+
+}  // namespace yavo
