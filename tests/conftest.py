@@ -44,7 +44,7 @@ def emul():
     srcs = [os.path.join(d, "emul_core.cpp"), os.path.join(ROOT, "ya_vo_b200", "csrc", "fast_core.h"),
             os.path.join(ROOT, "ya_vo_b200", "csrc", "select_serial.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, srcs[0]])
+        subprocess.check_call(["/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-std=c++17", "-o", so, srcs[0]])
     L = C.CDLL(so)
     L.emul_harris.restype = C.c_float
     L.emul_score_from_tensor.restype = C.c_float

@@ -109,7 +109,9 @@ class Mat {
     void create(int r, int c, int type) {
         rows = r; cols = c; type_ = type;
         step = (size_t)c * elemSize();
-        buf_ = std::shared_ptr<uchar>(new uchar[std::max<size_t>(step * r, 1)], std::default_delete<uchar[]>());
+        // 64 KiB of zeroed slack after the pixels: Image::getPixelVal-style unchecked linear reads slightly past
+        // the end (the reference's BRIEF does this when row + 8 == H) see zeros instead of heap contents
+        buf_ = std::shared_ptr<uchar>(new uchar[step * r + 65536](), std::default_delete<uchar[]>());
         data = buf_.get();
     }
     int type() const { return type_; }
