@@ -151,8 +151,14 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match);
 int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols,
                      float *scores, uint8_t *desc, int32_t *match_idx, int32_t *match_dist);
 
-/* convenience for streaming callers: upload + frontend + fetch of one batch of host frames with the
- * copies inside (what bench.py's e2e leg times). */
+/* frames per pipeline stage of yavo_process_host_batch (default 32) */
+int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames);
+
+/* streaming callers: upload + frontend + fetch of one batch of host frames into slots [0, n), with the
+ * copies inside (what bench.py's e2e leg times).  When `pixels` is pinned host memory the batch is cut
+ * into stages and the H2D copy of stage c+1, the kernels of stage c and the D2H copy of stage c-1 run on
+ * three streams; pageable memory goes through the staging buffer without overlap.  Returns after all
+ * results are in the host arrays. */
 int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
                             int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores,
                             uint8_t *desc, int32_t *match_idx, int32_t *match_dist);

@@ -67,6 +67,11 @@ struct yavo_ctx {
     size_t h_stage_bytes = 0;
     int *h_small = nullptr;  // 64 ints
     long long launches = 0;
+    // copy/compute overlap of yavo_process_host_batch
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_repitched[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_done;
+    int pipeline_chunk = 32;
     // optional per-kernel timing (CUDA events on the context's stream around every launch)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -390,6 +395,13 @@ void yavo_destroy(yavo_ctx *c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_repitched[i]) cudaEventDestroy(c->ev_repitched[i]);
+    }
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -625,7 +637,7 @@ static int match_device(yavo_ctx *ctx, const uint32_t *dq, int n1, const uint32_
     const int chunk = std::max(1, (std::max(n2, 1) + chunks - 1) / chunks);
     if (int r = ensure_partials(ctx, (size_t)n1 * chunks)) return r;
     dim3 grid((n1 + MQ - 1) / MQ, chunks, 1);
-    PROF(KC_MATCH, match_partial_kernel<<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk, chunks, n1,
+    PROF(KC_MATCH, match_partial_kernel<true><<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk, chunks, n1,
                                                        ctx->d_part_key, ctx->d_part_sec));
     CK_LAUNCH();
     PROF(KC_MATCH_REDUCE, match_reduce_kernel<<<dim3((n1 + 127) / 128, 1), 128, 0, ctx->stream>>>(
@@ -700,12 +712,9 @@ int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *kee
 
 // ---- batch front end -------------------------------------------------------------------------------
 
-int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match) {
-    if (int r = check_slot(ctx, slot0, n)) return r;
-    if (n == 0) return 0;
-    if (int r = check_uploaded(ctx, slot0, n)) return r;
-    if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
-    CK(cudaSetDevice(ctx->device));
+// detect -> select -> describe on slots [slot0, slot0+n); match pairs (p, p+1) that END inside the range.
+// link_prev also matches (slot0-1, slot0), whose query descriptors an earlier call left in place.
+static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool link_prev) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     if (int r = launch_detect(ctx, slot0, n, true, true)) return r;
     if (int r = launch_select(ctx, slot0, n, ctx->max_kp)) return r;
@@ -718,23 +727,34 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match) {
             nullptr));
         CK_LAUNCH();
     }
-    if (do_match && n > 1) {
-        const int pairs = n - 1;
+    const int m0 = (link_prev && slot0 > 0) ? slot0 - 1 : slot0;  // first query slot
+    const int pairs = slot0 + n - 1 - m0;
+    if (do_match && pairs > 0) {
+        const size_t mo = (size_t)m0 * ctx->max_kp;
         const int chunks = choose_chunks(ctx->max_kp, ctx->max_kp, pairs);
         const int chunk = (ctx->max_kp + chunks - 1) / chunks;
         if (int r = ensure_partials(ctx, (size_t)pairs * ctx->max_kp * chunks)) return r;
-        // pair p: queries = slot0+p, train = slot0+p+1; results stored at the train slot
+        // pair p: queries = slot m0+p, train = slot m0+p+1; results stored at the train slot
         dim3 grid((ctx->max_kp + MQ - 1) / MQ, chunks, pairs);
-        PROF(KC_MATCH, match_partial_kernel<<<grid, MQ, 0, ctx->stream>>>(
-            ctx->d_desc + o * 8, ctx->d_nbk + slot0, 0, ctx->d_desc + o * 8, ctx->d_nbk + slot0, 0,
+        PROF(KC_MATCH, match_partial_kernel<false><<<grid, MQ, 0, ctx->stream>>>(
+            ctx->d_desc + mo * 8, ctx->d_nbk + m0, 0, ctx->d_desc + mo * 8, ctx->d_nbk + m0, 0,
             (size_t)ctx->max_kp * 8, 0, 1, chunk, chunks, ctx->max_kp, ctx->d_part_key, ctx->d_part_sec));
         CK_LAUNCH();
         PROF(KC_MATCH_REDUCE, match_reduce_kernel<<<dim3((ctx->max_kp + 127) / 128, pairs), 128, 0, ctx->stream>>>(
-            ctx->d_part_key, ctx->d_part_sec, ctx->d_nbk + slot0, 0, 0, ctx->d_nbk + slot0, 0, 1, chunk, chunks,
-            ctx->max_kp, ctx->d_midx + o + ctx->max_kp, ctx->d_mdist + o + ctx->max_kp, nullptr));
+            ctx->d_part_key, ctx->d_part_sec, ctx->d_nbk + m0, 0, 0, ctx->d_nbk + m0, 0, 1, chunk, chunks,
+            ctx->max_kp, ctx->d_midx + mo + ctx->max_kp, ctx->d_mdist + mo + ctx->max_kp, nullptr));
         CK_LAUNCH();
     }
     return 0;
+}
+
+int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (n == 0) return 0;
+    if (int r = check_uploaded(ctx, slot0, n)) return r;
+    if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
+    CK(cudaSetDevice(ctx->device));
+    return frontend_range(ctx, slot0, n, do_match != 0, false);
 }
 
 int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols, float *scores,
@@ -753,12 +773,78 @@ int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *ro
     return check_status(ctx);  // synchronises; reports a candidate-list overflow
 }
 
+// D2H of the results of slots [slot0, slot0+n) on `st`, into host arrays whose row 0 is slot `base`
+static int fetch_async(yavo_ctx *ctx, cudaStream_t st, int base, int slot0, int n, int32_t *n_kp, int32_t *rows,
+                       int32_t *cols, float *scores, uint8_t *desc, int32_t *match_idx, int32_t *match_dist) {
+    const size_t o = (size_t)slot0 * ctx->max_kp, cnt = (size_t)n * ctx->max_kp, h = (size_t)(slot0 - base) * ctx->max_kp;
+    if (n_kp) CK(cudaMemcpyAsync(n_kp + (slot0 - base), ctx->d_nbk + slot0, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (rows) CK(cudaMemcpyAsync(rows + h, ctx->d_bk_row + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
+    if (cols) CK(cudaMemcpyAsync(cols + h, ctx->d_bk_col + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
+    if (scores) CK(cudaMemcpyAsync(scores + h, ctx->d_bk_score + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
+    if (desc) CK(cudaMemcpyAsync(desc + h * 32, ctx->d_desc + o * 8, 32 * cnt, cudaMemcpyDeviceToHost, st));
+    if (match_idx) CK(cudaMemcpyAsync(match_idx + h, ctx->d_midx + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
+    if (match_dist) CK(cudaMemcpyAsync(match_dist + h, ctx->d_mdist + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
+    return 0;
+}
+
 int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
                             int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores, uint8_t *desc,
                             int32_t *match_idx, int32_t *match_dist) {
-    if (int r = yavo_upload_batch(ctx, 0, n, pixels, rows, cols)) return r;
-    if (int r = yavo_frontend_batch(ctx, 0, n, do_match)) return r;
-    return yavo_fetch_batch(ctx, 0, n, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist);
+    if (int r = check_slot(ctx, 0, n)) return r;
+    if (n == 0) return 0;
+    if (!pixels || rows < 1 || cols < 1 || rows > ctx->max_rows || cols > ctx->max_cols)
+        return fail(ctx, YAVO_ERR_INVALID, "bad frame size %dx%d", rows, cols);
+    if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
+    CK(cudaSetDevice(ctx->device));
+    if (!is_pinned_host(pixels)) {
+        // pageable frames: packed through the pinned staging buffer, no overlap
+        if (int r = upload_host(ctx, 0, n, pixels, rows, cols, cols)) return r;
+        if (int r = frontend_range(ctx, 0, n, do_match != 0, false)) return r;
+        return yavo_fetch_batch(ctx, 0, n, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist);
+    }
+    // pinned frames: three streams.  Chunk c's pixels cross PCIe (s_h2d) while chunk c-1 is in the kernels
+    // (ctx->stream) and chunk c-2's keypoints / descriptors / matches go back (s_d2h).
+    if (!ctx->s_h2d) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_repitched[i], cudaEventDisableTiming));
+        }
+    }
+    const int C = std::max(1, std::min(ctx->pipeline_chunk, n));
+    const int nchunks = (n + C - 1) / C;
+    while ((int)ctx->ev_done.size() < nchunks) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->ev_done.push_back(e);
+    }
+    const size_t fbytes = (size_t)rows * cols;
+    if (int r = ensure_raw(ctx, 2 * (size_t)C * fbytes)) return r;
+    for (int c = 0; c < nchunks; c++) {
+        const int buf = c & 1, s0 = c * C, nc = std::min(C, n - s0);
+        uint8_t *raw = ctx->d_raw + (size_t)buf * C * fbytes;
+        if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_repitched[buf], 0));
+        CK(cudaMemcpyAsync(raw, pixels + (size_t)s0 * fbytes, (size_t)nc * fbytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
+        if (int r = launch_repitch(ctx, raw, cols, s0, nc, rows, cols)) return r;
+        CK(cudaEventRecord(ctx->ev_repitched[buf], ctx->stream));
+        if (int r = frontend_range(ctx, s0, nc, do_match != 0, c > 0)) return r;
+        CK(cudaEventRecord(ctx->ev_done[c], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[c], 0));
+        if (int r = fetch_async(ctx, ctx->s_d2h, 0, s0, nc, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist))
+            return r;
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    return check_status(ctx);
+}
+
+/* frames per pipeline stage of yavo_process_host_batch (default 32) */
+int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames) {
+    if (!ctx || frames < 1) return YAVO_ERR_INVALID;
+    ctx->pipeline_chunk = frames;
+    return 0;
 }
 
 }  // extern "C"

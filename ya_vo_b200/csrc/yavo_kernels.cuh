@@ -576,7 +576,13 @@ brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, i
              int kp_stride, uint32_t *__restrict__ desc, uint8_t *__restrict__ valid,
              int *__restrict__ n_oob) {
     __shared__ uint32_t soff[256];
-    for (int i = threadIdx.x; i < 256; i += K4_THREADS) soff[i] = offs[i];
+    __shared__ int2 slin[256];  // the same tests as byte offsets from the keypoint's pixel
+    for (int i = threadIdx.x; i < 256; i += K4_THREADS) {
+        const uint32_t o = offs[i];
+        soff[i] = o;
+        slin[i] = make_int2((int)(int8_t)(o & 0xff) * pitch + (int)(int8_t)((o >> 8) & 0xff),
+                            (int)(int8_t)((o >> 16) & 0xff) * pitch + (int)(int8_t)(o >> 24));
+    }
     __syncthreads();
     const int f = blockIdx.y;
     const int n = n_per_frame ? n_per_frame[f] : n_fixed;
@@ -594,15 +600,26 @@ brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, i
     const uint8_t *S = blur + (size_t)f * frame_stride;
     bool oob = false;
     uint32_t mine = 0;
+    if (row + 8 < H && col + 8 < W) {
+        // interior keypoint (warp-uniform): no sample can wrap or leave the buffer, plain linear offsets
+        const uint8_t *base = S + (size_t)row * pitch + col;
 #pragma unroll
-    for (int w = 0; w < 8; w++) {
-        const uint32_t o = soff[32 * w + lane];
-        const int r1 = row + (int)(int8_t)(o & 0xff), c1 = col + (int)(int8_t)((o >> 8) & 0xff);
-        const int r2 = row + (int)(int8_t)((o >> 16) & 0xff), c2 = col + (int)(int8_t)(o >> 24);
-        const int va = brief_sample(S, pitch, H, W, r1, c1, &oob);
-        const int vb = brief_sample(S, pitch, H, W, r2, c2, &oob);
-        const unsigned word = __ballot_sync(0xffffffffu, va > vb);
-        if (lane == w) mine = word;
+        for (int w = 0; w < 8; w++) {
+            const int2 lo = slin[32 * w + lane];
+            const unsigned word = __ballot_sync(0xffffffffu, __ldg(base + lo.x) > __ldg(base + lo.y));
+            if (lane == w) mine = word;
+        }
+    } else {
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const uint32_t o = soff[32 * w + lane];
+            const int r1 = row + (int)(int8_t)(o & 0xff), c1 = col + (int)(int8_t)((o >> 8) & 0xff);
+            const int r2 = row + (int)(int8_t)((o >> 16) & 0xff), c2 = col + (int)(int8_t)(o >> 24);
+            const int va = brief_sample(S, pitch, H, W, r1, c1, &oob);
+            const int vb = brief_sample(S, pitch, H, W, r2, c2, &oob);
+            const unsigned word = __ballot_sync(0xffffffffu, va > vb);
+            if (lane == w) mine = word;
+        }
     }
     if (lane < 8) d[lane] = mine;
     if (n_oob) {
@@ -615,15 +632,38 @@ brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, i
 // K5  Hamming match  (reference src/BriefDescriptor.cc:139-183)
 // Brute force over 256-bit descriptors held as 8 x u32.  A CTA owns MQ queries (one per thread,
 // descriptor in registers) and one chunk of the train set, staged through shared memory in tiles
-// and read as broadcast 128-bit loads; XOR + POPC per word.  Every thread keeps
-// key = dist << 22 | j, whose minimum is the reference's "first minimum wins" rule, and the second
-// smallest distance.  Chunk partials are combined by a small reduce kernel (deterministic, no
-// atomics).
+// and read as broadcast 128-bit loads.  Every thread keeps key = dist << 22 | j, whose minimum
+// (one VIMNMX) is the reference's "first minimum wins" rule; the second smallest distance is
+// tracked only when the caller asks for it (SECOND).  Chunk partials are combined by a small
+// reduce kernel (deterministic, no atomics).
+//
+// Pipe balance: the POPC (XU) pipe issues 16 lanes/clk/SM, the integer ALU 64.  A plain
+// 8 x (XOR, POPC) per pair is XU-bound at 2 pairs/clk/SM (measured 1.75, ncu: XU 91 %).  Three
+// carry-save adders (2 LOP3 each) first compress the eight XOR words to two weight-1 and three
+// weight-2 words, so a pair costs 5 POPC + 14 LOP3 instead of 8 POPC + 8 LOP3 — both pipes end up
+// about equally loaded (5/16 vs ~18/64 clk) and the bound moves to ~3.2 pairs/clk/SM.
 // ================================================================================================
 constexpr int MQ = 128;        // queries per CTA == threads
 constexpr int MT = 128;        // train descriptors per shared-memory tile
 constexpr uint32_t MATCH_NONE = 0xffffffffu;
 
+// carry-save adder on 32 independent bit columns: a + b + c = sum + 2 * carry
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry) {
+    sum = a ^ b ^ c;                  // LOP3 0x96
+    carry = (a & b) | (c & (a ^ b));  // LOP3 0xE8
+}
+
+__device__ __forceinline__ uint32_t hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
+    const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
+    const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
+    uint32_t s1, c1, s2, c2, s3, c3;
+    csa(x0, x1, x2, s1, c1);
+    csa(x3, x4, x5, s2, c2);
+    csa(s1, s2, x6, s3, c3);
+    return (__popc(s3) + __popc(x7)) + 2u * (__popc(c1) + __popc(c2) + __popc(c3));
+}
+
+template <bool SECOND>
 __global__ void __launch_bounds__(MQ)
 match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
                      const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
@@ -655,24 +695,24 @@ match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict_
         __syncthreads();
 #pragma unroll 4
         for (int j = 0; j < nt_tile; j++) {
-            const uint4 b0 = st[j][0], b1 = st[j][1];
-            const uint32_t d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) +
-                               __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) +
-                               __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
-            const uint32_t key = (d << 22) | (uint32_t)(t0 + j);
-            // strict '<' on ascending j == min over key; second = second smallest distance
-            const uint32_t bd = best >> 22;
-            if (key < best) {
-                sec = (best == MATCH_NONE) ? sec : bd;
-                best = key;
-            } else if (d < sec) {
-                sec = d;
+            const uint32_t d = hamming256(a0, a1, st[j][0], st[j][1]);
+            const uint32_t key = (d << 22) + (uint32_t)(t0 + j);
+            if (SECOND) {
+                // ascending j and strict '<' == min over key; sec = second smallest distance
+                if (key < best) {
+                    sec = (best == MATCH_NONE) ? sec : (best >> 22);
+                    best = key;
+                } else if (d < sec) {
+                    sec = d;
+                }
+            } else {
+                best = min(best, key);
             }
         }
     }
     if (q < nq) {
         part_key[((size_t)pair * out_stride + q) * n_chunks + c] = best;
-        part_sec[((size_t)pair * out_stride + q) * n_chunks + c] = sec;
+        if (SECOND) part_sec[((size_t)pair * out_stride + q) * n_chunks + c] = sec;
     }
 }
 
@@ -690,7 +730,7 @@ __global__ void match_reduce_kernel(const uint32_t *__restrict__ part_key, const
     uint32_t best = MATCH_NONE, sec = MATCH_NONE;
     for (int c = 0; c < used && c < n_chunks; c++) {
         const uint32_t k = part_key[((size_t)pair * out_stride + q) * n_chunks + c];
-        const uint32_t s = part_sec[((size_t)pair * out_stride + q) * n_chunks + c];
+        const uint32_t s = out_second ? part_sec[((size_t)pair * out_stride + q) * n_chunks + c] : MATCH_NONE;
         if (k == MATCH_NONE) continue;
         const uint32_t kd = k >> 22;
         if (k < best) {
