@@ -754,7 +754,12 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match) {
     if (int r = check_uploaded(ctx, slot0, n)) return r;
     if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
     CK(cudaSetDevice(ctx->device));
-    return frontend_range(ctx, slot0, n, do_match != 0, false);
+    // sub-batches sized so that a sub-batch's pixels and blurred planes are still in the 126 MB L2 when the
+    // scoring and BRIEF kernels come back for them (about 32 MB of pitched pixels per sub-batch)
+    const int sub = std::max(1, (int)std::min<size_t>((size_t)n, (32u << 20) / ctx->frame_stride));
+    for (int s0 = 0; s0 < n; s0 += sub)
+        if (int r = frontend_range(ctx, slot0 + s0, std::min(sub, n - s0), do_match != 0, s0 > 0)) return r;
+    return 0;
 }
 
 int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols, float *scores,

@@ -68,14 +68,19 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     const int tid = threadIdx.x;
 
     // ---- stage tile rows y0-4 .. y0+35 (reflected into the image), cols x0-4 .. x0+131 ----------
+    // one warp per staged row: lane l loads word l (128 contiguous bytes), lanes 0/1 the two tail words
     const int pitch_w = pitch >> 2;
     const int wbase = (x0 - HALO) >> 2;  // may be -1 for the first tile column
-    for (int i = tid; i < SH * SW; i += K1_THREADS) {
-        const int tr = i / SW, tw = i - tr * SW;
-        const int gr = reflect101(y0 - HALO + tr, H);
-        int gw = wbase + tw;
-        gw = gw < 0 ? 0 : (gw >= pitch_w ? pitch_w - 1 : gw);
-        tile[tr][tw] = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)gr * pitch) + gw);
+    {
+        const int ln = tid & 31;
+        const int gw0 = max(wbase + ln, 0);                          // only word -1 can be negative
+        const int gw1 = min(wbase + 32 + ln, pitch_w - 1);           // tail words 32, 33
+        for (int tr = tid >> 5; tr < SH; tr += K1_THREADS / 32) {
+            const int gr = reflect101(y0 - HALO + tr, H);
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)gr * pitch);
+            tile[tr][ln] = __ldg(src + min(gw0, pitch_w - 1));
+            if (ln < SW - 32) tile[tr][32 + ln] = __ldg(src + gw1);
+        }
     }
     const bool edge_cols = DO_BLUR && (x0 == 0 || x0 + TW + HALO > W);
     if (edge_cols) {
@@ -113,6 +118,10 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
 
     if (DO_FAST) {
         // segment test: warp -> tile row, lane -> quad; 8 lanes assemble one 32-pixel mask word
+        uint32_t colmask = 0;  // interior columns only: 4 <= col < W-4
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+            if (x0 + 4 * lane + b >= 4 && x0 + 4 * lane + b < W - 4) colmask |= 1u << b;
         for (int tr = warp; tr < TH; tr += K1_THREADS / 32) {
             const int gr = y0 + tr;
             uint32_t nib = 0;
@@ -122,11 +131,7 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
                 nib = yavo_fast4(&tile[sr - 3][lane + 1], &tile[sr - 2][lane + 1], &tile[sr - 1][lane + 1],
                                  &tile[sr][lane + 1], &tile[sr + 1][lane + 1], &tile[sr + 2][lane + 1],
                                  &tile[sr + 3][lane + 1], &pre);
-                // interior columns only: 4 <= col < W-4
-                const int gc = x0 + 4 * lane;
-#pragma unroll
-                for (int b = 0; b < 4; b++)
-                    if (gc + b < 4 || gc + b >= W - 4) nib &= ~(1u << b);
+                nib &= colmask;
             }
             uint32_t v = nib << (4 * (lane & 7));
             v |= __shfl_xor_sync(0xffffffffu, v, 1);
