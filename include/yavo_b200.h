@@ -153,6 +153,9 @@ int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *ro
 
 /* frames per pipeline stage of yavo_process_host_batch (default 32) */
 int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames);
+/* frames per kernel sub-batch inside yavo_frontend_batch (0 = automatic: about 32 MB of pixels, so a
+ * sub-batch's pixels and blurred planes stay L2-resident between the kernels that touch them) */
+int yavo_set_sub_batch(yavo_ctx *ctx, int frames);
 
 /* streaming callers: upload + frontend + fetch of one batch of host frames into slots [0, n), with the
  * copies inside (what bench.py's e2e leg times).  When `pixels` is pinned host memory the batch is cut

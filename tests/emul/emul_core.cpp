@@ -90,7 +90,7 @@ void emul_blur(const uint8_t *img, int H, int W, uint8_t *out) {
 }
 
 // ---- model of select_topk_kernel: same routing rules, same partition formulation ------------------
-static const int WARP_MAX = 256, SERIAL = 32;
+static const int SERIAL = YAVO_SORT_THRESHOLD;  // ranges of <= 16 elements: stable sort (the kernel's warp rank sort)
 
 static int model_partition(yavo_ent *A, int f, int l) {
     yavo_median_to_first(A, f, l);
@@ -139,7 +139,7 @@ void emul_select(float *scores, int32_t *payload, int n, int K) {
         }
         cur.swap(nxt);
     }
-    for (auto &r : serial) yavo_serial_introsort(A.data(), r.f, r.l, r.d, K);
+    for (auto &r : serial) std::stable_sort(A.begin() + r.f, A.begin() + r.l, [](yavo_ent a, yavo_ent b) { return yavo_before(a, b); });
     for (int i = 0; i < n; i++) {
         scores[i] = yavo_ent_score(A[i]);
         payload[i] = (int32_t)(uint32_t)A[i];

@@ -25,7 +25,7 @@ EXPORTS = [
     "yavo_ring_points", "yavo_fast_detect", "yavo_fast_candidates",
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
-    "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_set_pipeline_chunk",
+    "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
 ]
 
 
@@ -239,6 +239,9 @@ class Context:
                                           _p(out["scores"]), _p(out["desc"]), _p(out["match_idx"]),
                                           _p(out["match_dist"])))
         return out
+
+    def set_sub_batch(self, frames):
+        self._ck(self._L.yavo_set_sub_batch(self._h, int(frames)))
 
     def set_pipeline_chunk(self, frames):
         self._ck(self._L.yavo_set_pipeline_chunk(self._h, int(frames)))

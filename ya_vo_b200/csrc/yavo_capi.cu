@@ -72,6 +72,7 @@ struct yavo_ctx {
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_repitched[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_done;
     int pipeline_chunk = 32;
+    int sub_batch = 0;  // frames per kernel sub-batch of yavo_frontend_batch (0 = about 32 MB of pixels)
     // optional per-kernel timing (CUDA events on the context's stream around every launch)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -756,7 +757,8 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match) {
     CK(cudaSetDevice(ctx->device));
     // sub-batches sized so that a sub-batch's pixels and blurred planes are still in the 126 MB L2 when the
     // scoring and BRIEF kernels come back for them (about 32 MB of pitched pixels per sub-batch)
-    const int sub = std::max(1, (int)std::min<size_t>((size_t)n, (32u << 20) / ctx->frame_stride));
+    const int sub = ctx->sub_batch > 0 ? std::min(ctx->sub_batch, n)
+                                       : std::max(1, (int)std::min<size_t>((size_t)n, (32u << 20) / ctx->frame_stride));
     for (int s0 = 0; s0 < n; s0 += sub)
         if (int r = frontend_range(ctx, slot0 + s0, std::min(sub, n - s0), do_match != 0, s0 > 0)) return r;
     return 0;
@@ -843,6 +845,12 @@ int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int row
     }
     CK(cudaStreamSynchronize(ctx->s_d2h));
     return check_status(ctx);
+}
+
+int yavo_set_sub_batch(yavo_ctx *ctx, int frames) {
+    if (!ctx || frames < 0) return YAVO_ERR_INVALID;
+    ctx->sub_batch = frames;
+    return 0;
 }
 
 /* frames per pipeline stage of yavo_process_host_batch (default 32) */

@@ -265,53 +265,83 @@ compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, in
 
 // ================================================================================================
 // K3  exact top-K select  (std::sort replay; see select_serial.h)
-// One CTA per frame.  Level-synchronous replay of libstdc++'s introsort partition tree over the
-// candidate list, pruned to ranges that start below K.  Large ranges are partitioned by the whole
-// CTA, medium ones by single warps, ranges of <= SEL_SERIAL elements by single threads.  A
-// partition is the parallel form of __unguarded_partition: the i-th element from the left that
+// One CTA per frame.  Replays libstdc++'s introsort partition tree over the candidate list (in scan
+// order), pruned to ranges that start below K, so the first K outputs come out in exactly the order
+// the reference's std::sort leaves them — tied responses included.
+//   phase 1  ranges larger than SEL_WARP_MAX: partitioned by the whole CTA, level by level;
+//   phase 2  everything else: a shared work queue of ranges served by the 16 warps independently.
+//            A warp partitions its range, queues the right child and keeps the left; ranges of
+//            <= 16 elements (where std::sort's final insertion sort is the only thing left, i.e. a
+//            stable sort) are finished by a warp-wide rank sort.
+// A partition is the parallel form of __unguarded_partition: the i-th element from the left that
 // does not sort before the pivot (L_i) is swapped with the i-th element from the right that the
 // pivot does not sort before (R_i) while L_i < R_i; with m such swaps the cut is
 // min(L_{m+1}, R_m).  Stopper positions are found by rank (ballot + scan) and scattered into a
-// scratch list; the swaps are independent.
+// scratch list; the swaps are independent.  The depth-limit fallback (heapsort) is replayed by a
+// single lane (never reached on real score lists; kept for exactness).
 // ================================================================================================
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_SMEM_ENTS = 4096;     // candidates kept in shared memory once the active prefix fits
-constexpr int SEL_WARP_MAX = 256;       // ranges up to this size are partitioned by one warp
-constexpr int SEL_SERIAL = 32;          // ranges up to this size are finished by one thread
-constexpr int SEL_QCAP = 256;           // per-level range queue
-constexpr int SEL_SCAP = 1024;          // serial work list
+constexpr int SEL_WARP_MAX = 512;       // ranges up to this size are partitioned by one warp
+constexpr int SEL_QCAP = 512;           // shared work queue (ring)
+constexpr int SEL_STACK = 32;           // per-warp overflow stack
+constexpr int SEL_BIG = 64;             // per-level list of CTA-partitioned ranges
 
 struct SelRange {
     int f, l, d;
 };
 
 struct SelShared {
-    SelRange q[2][SEL_QCAP];
-    SelRange serial[SEL_SCAP];
+    SelRange ring[SEL_QCAP];
+    int ready[SEL_QCAP];
+    SelRange stack[SEL_WARPS][SEL_STACK];
     uint16_t wscratch[SEL_WARPS][2][SEL_WARP_MAX / 2 + 2];
-    int qn[2];
-    int nserial;
+    SelRange big[2][SEL_BIG];
+    int nbig[2];
+    int q_head, q_tail, pending;
     int wtot[SEL_WARPS];
     int bcast[4];
 };
 
-// children of a partition / initial range: route by size
-__device__ __forceinline__ void sel_route(SelShared &S, int nq, yavo_ent *A, int f, int l, int d, int K) {
-    if (f >= K || l - f <= 1) return;
-    const int n = l - f;
-    if (n <= SEL_SERIAL) {
-        const int i = atomicAdd(&S.nserial, 1);
-        if (i < SEL_SCAP) S.serial[i] = {f, l, d};
-        else { atomicSub(&S.nserial, 1); yavo_serial_introsort(A, f, l, d, K); }
-    } else if (d == 0) {
-        // depth limit reached: libstdc++ heapsorts the range; single thread, off the common path
-        yavo_serial_heapsort(A, f, l);
-    } else {
-        const int i = atomicAdd(&S.qn[nq], 1);
-        if (i < SEL_QCAP) S.q[nq][i] = {f, l, d};
-        else { atomicSub(&S.qn[nq], 1); yavo_serial_introsort(A, f, l, d, K); }
+// queue a range for phase 2 (one thread).  Returns false when the ring is full.
+__device__ __forceinline__ bool sel_push(SelShared &S, const SelRange &r) {
+    const int head = *(volatile int *)&S.q_head, tail = *(volatile int *)&S.q_tail;
+    if (tail - head >= SEL_QCAP - 2 * SEL_WARPS) return false;
+    const int idx = atomicAdd(&S.q_tail, 1);
+    S.ring[idx % SEL_QCAP] = r;
+    __threadfence_block();
+    atomicExch(&S.ready[idx % SEL_QCAP], idx + 1);
+    return true;
+}
+
+// warp-collective pop; returns false once no work is left anywhere in the CTA
+__device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
+    const int lane = threadIdx.x & 31;
+    int got = -1;
+    if (lane == 0) {
+        for (;;) {
+            const int h = *(volatile int *)&S.q_head, t = *(volatile int *)&S.q_tail;
+            if (h < t) {
+                if (atomicCAS(&S.q_head, h, h + 1) == h) {
+                    got = h;
+                    break;
+                }
+                continue;
+            }
+            if (*(volatile int *)&S.pending <= 0) break;
+            __nanosleep(64);
+        }
+        if (got >= 0) {
+            while (*(volatile int *)&S.ready[got % SEL_QCAP] != got + 1) {
+            }
+            __threadfence_block();
+        }
     }
+    got = __shfl_sync(0xffffffffu, got, 0);
+    if (got < 0) return false;
+    out = S.ring[got % SEL_QCAP];
+    return true;
 }
 
 // whole-CTA partition of [f,l); returns the cut to every thread.  Lpos/Rpos: global scratch.
@@ -378,7 +408,7 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint
     return cut;
 }
 
-// single-warp partition of [f,l), n <= SEL_WARP_MAX; positions relative to f in 16-bit scratch
+// single-warp partition of [f,l), 16 < n <= SEL_WARP_MAX; positions relative to f in 16-bit scratch
 __device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *Lpos = S.wscratch[warp][0], *Rpos = S.wscratch[warp][1];
@@ -423,6 +453,89 @@ __device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
     return f + cut;
 }
 
+// stable sort of a range of <= 16 elements by one warp (what __final_insertion_sort does to it):
+// rank = elements that sort strictly before + equal elements that come earlier
+__device__ __forceinline__ void sel_warp_leaf(yavo_ent *A, int f, int l) {
+    const int lane = threadIdx.x & 31, n = l - f;
+    const yavo_ent e = (lane < n) ? A[f + lane] : 0ull;
+    const float se = yavo_ent_score(e);
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+        const float sj = __shfl_sync(0xffffffffu, se, j);
+        rank += (sj > se) || (sj == se && j < lane);
+    }
+    __syncwarp();
+    if (lane < n) A[f + rank] = e;
+    __syncwarp();
+}
+
+// phase 2: one warp works a range down to its leaves, handing right children to the queue
+__device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int sp = 0;  // private overflow stack (only used when the ring is full)
+    for (;;) {
+        // cur is counted in S.pending and satisfies cur.f < K, cur.l - cur.f > 1
+        const int n = cur.l - cur.f;
+        bool finished = false;
+        if (n <= YAVO_SORT_THRESHOLD) {
+            sel_warp_leaf(A, cur.f, cur.l);
+            finished = true;
+        } else if (cur.d == 0) {
+            if (lane == 0) yavo_serial_heapsort(A, cur.f, cur.l);  // libstdc++'s depth-limit fallback
+            __syncwarp();
+            finished = true;
+        } else {
+            const int cut = (n <= SEL_WARP_MAX) ? sel_warp_partition(S, A, cur.f, cur.l) : -1;
+            if (cut < 0) {  // cannot happen: phase 1 leaves only ranges <= SEL_WARP_MAX; stay exact anyway
+                if (lane == 0) yavo_serial_introsort(A, cur.f, cur.l, cur.d, K);
+                __syncwarp();
+                finished = true;
+            } else {
+                const SelRange left = {cur.f, cut, cur.d - 1}, right = {cut, cur.l, cur.d - 1};
+                const bool vL = cut - cur.f > 1;               // left starts at cur.f < K
+                const bool vR = cut < K && cur.l - cut > 1;
+                if (vL && vR) {
+                    int pushed = 0;
+                    if (lane == 0) {
+                        atomicAdd(&S.pending, 1);
+                        pushed = sel_push(S, right) ? 1 : 0;
+                    }
+                    pushed = __shfl_sync(0xffffffffu, pushed, 0);
+                    if (!pushed) {
+                        if (sp < SEL_STACK) {
+                            if (lane == 0) S.stack[warp][sp] = right;
+                            sp++;
+                            __syncwarp();
+                        } else {  // both full: finish the child serially (exact, slow, practically unreachable)
+                            if (lane == 0) {
+                                yavo_serial_introsort(A, right.f, right.l, right.d, K);
+                                atomicSub(&S.pending, 1);
+                            }
+                            __syncwarp();
+                        }
+                    }
+                    cur = left;
+                } else if (vL) {
+                    cur = left;
+                } else if (vR) {
+                    cur = right;
+                } else {
+                    finished = true;
+                }
+            }
+        }
+        if (finished) {
+            if (lane == 0) {
+                __threadfence_block();
+                atomicSub(&S.pending, 1);
+            }
+            if (sp == 0) return;
+            sp--;
+            cur = S.stack[warp][sp];
+        }
+    }
+}
+
 // checkBoundry of reference src/BriefDescriptor.cc:128-136 as computeBrief calls it (:97)
 __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
     return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
@@ -442,7 +555,7 @@ select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__r
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int N = ncand[f];
+    const int N = ncand[f];
     if (N > max_cand) {  // candidate buffer overflow: report, never return a silently truncated order
         if (tid == 0) { atomicExch(status, 1); nkp[f] = 0; nbk[f] = 0; }
         return;
@@ -451,67 +564,69 @@ select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__r
     uint32_t *Lpos = scratch_all + (size_t)blockIdx.x * (size_t)(max_cand + 4);
     uint32_t *Rpos = Lpos + (max_cand / 2 + 2);
 
+    for (int i = tid; i < SEL_QCAP; i += SEL_THREADS) S.ready[i] = 0;
+    if (tid == 0) { S.nbig[0] = S.nbig[1] = 0; S.q_head = S.q_tail = 0; S.pending = 0; }
+    __syncthreads();
+
     yavo_ent *A = G;
     bool in_smem = false;
-    if (tid == 0) { S.qn[0] = S.qn[1] = 0; S.nserial = 0; }
-    __syncthreads();
     if (N <= SEL_SMEM_ENTS) {
         for (int i = tid; i < N; i += SEL_THREADS) sbuf[i] = G[i];
         A = sbuf;
         in_smem = true;
-        __syncthreads();
     }
     if (tid == 0 && N > 1) {
-        const int depth = 2 * (31 - __clz(N));
-        sel_route(S, 0, A, 0, N, depth, K);
+        const SelRange r0 = {0, N, 2 * (31 - __clz(N))};
+        if (N > SEL_WARP_MAX) S.big[0][S.nbig[0]++] = r0;
+        else sel_push(S, r0);
     }
     __syncthreads();
 
+    // ---- phase 1: ranges larger than SEL_WARP_MAX, whole CTA, level by level -------------------------
     int cur = 0;
-    while (S.qn[cur] > 0) {
-        const int nq = S.qn[cur];
-        const int nxt = cur ^ 1;
-        // move the active prefix into shared memory as soon as it fits
-        if (!in_smem) {
-            int E = 0;
-            for (int i = 0; i < nq; i++) E = max(E, S.q[cur][i].l);
-            for (int i = 0; i < S.nserial; i++) E = max(E, S.serial[i].l);
-            E = max(E, min(N, K));  // everything that can still move or be output
-            if (E <= SEL_SMEM_ENTS) {
-                for (int i = tid; i < E; i += SEL_THREADS) sbuf[i] = G[i];
-                A = sbuf;
-                in_smem = true;
+    while (S.nbig[cur] > 0) {
+        const int nb = S.nbig[cur], nxt = cur ^ 1;
+        for (int i = 0; i < nb; i++) {
+            const SelRange r = S.big[cur][i];
+            int cut;
+            if (r.d == 0) {  // depth limit: heapsort, nothing below it
+                if (tid == 0) yavo_serial_heapsort(A, r.f, r.l);
                 __syncthreads();
+                continue;
+            }
+            cut = sel_block_partition(S, A, r.f, r.l, Lpos, Rpos);
+            if (tid == 0) {
+                const SelRange ch[2] = {{r.f, cut, r.d - 1}, {cut, r.l, r.d - 1}};
+                for (int c = 0; c < 2; c++) {
+                    if (ch[c].f >= K || ch[c].l - ch[c].f <= 1) continue;
+                    if (ch[c].l - ch[c].f > SEL_WARP_MAX && S.nbig[nxt] < SEL_BIG) S.big[nxt][S.nbig[nxt]++] = ch[c];
+                    else if (ch[c].l - ch[c].f > SEL_WARP_MAX || !sel_push(S, ch[c]))
+                        yavo_serial_introsort(A, ch[c].f, ch[c].l, ch[c].d, K);  // lists full: exact, serial
+                }
             }
         }
-        // (a) large ranges: the whole CTA, one after another
-        for (int i = 0; i < nq; i++) {
-            const SelRange r = S.q[cur][i];
-            if (r.l - r.f <= SEL_WARP_MAX) continue;
-            const int cut = sel_block_partition(S, A, r.f, r.l, Lpos, Rpos);
-            if (tid == 0) sel_route(S, nxt, A, cut, r.l, r.d - 1, K);
-            if (tid == 32) sel_route(S, nxt, A, r.f, cut, r.d - 1, K);
-        }
-        // (b) medium ranges: one warp each
-        for (int i = warp; i < nq; i += SEL_WARPS) {
-            const SelRange r = S.q[cur][i];
-            if (r.l - r.f > SEL_WARP_MAX) continue;
-            const int cut = sel_warp_partition(S, A, r.f, r.l);
-            if (lane == 0) sel_route(S, nxt, A, cut, r.l, r.d - 1, K);
-            if (lane == 1) sel_route(S, nxt, A, r.f, cut, r.d - 1, K);
-        }
         __syncthreads();
-        if (tid == 0) S.qn[cur] = 0;
+        if (tid == 0) S.nbig[cur] = 0;
         cur = nxt;
         __syncthreads();
     }
-    // (c) small ranges: one thread each (introsort tail + the final insertion sort)
-    {
-        const int ns = min(S.nserial, SEL_SCAP);
-        for (int i = tid; i < ns; i += SEL_THREADS) {
-            const SelRange r = S.serial[i];
-            yavo_serial_introsort(A, r.f, r.l, r.d, K);
+    // move the active prefix into shared memory if it fits (phase 2 then never touches global memory)
+    if (!in_smem) {
+        int E = min(N, K);
+        const int qt = S.q_tail;
+        for (int i = 0; i < qt && i < SEL_QCAP; i++) E = max(E, S.ring[i].l);
+        if (E <= SEL_SMEM_ENTS) {
+            for (int i = tid; i < E; i += SEL_THREADS) sbuf[i] = G[i];
+            A = sbuf;
         }
+    }
+    if (tid == 0) S.pending = S.q_tail;
+    __syncthreads();
+
+    // ---- phase 2: warps drain the queue ------------------------------------------------------------------
+    {
+        SelRange t;
+        while (sel_pop(S, t)) sel_warp_work(S, A, t, K);
     }
     __syncthreads();
 
@@ -574,6 +689,9 @@ __device__ __forceinline__ int brief_sample(const uint8_t *S, int pitch, int H, 
 }
 
 // offsets packed one test per word: byte0 = drow1, byte1 = dcol1, byte2 = drow2, byte3 = dcol2 (int8)
+constexpr int BP_WORDS = 5;              // words per staged patch row: 17 columns + alignment phase <= 20 bytes
+constexpr int BP_ROWS = 17;              // rows row-8 .. row+8
+
 __global__ void __launch_bounds__(K4_THREADS)
 brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, int H, int W,
              const uint32_t *__restrict__ offs, const int32_t *__restrict__ rows,
@@ -581,18 +699,20 @@ brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, i
              int kp_stride, uint32_t *__restrict__ desc, uint8_t *__restrict__ valid,
              int *__restrict__ n_oob) {
     __shared__ uint32_t soff[256];
-    __shared__ int2 slin[256];  // the same tests as byte offsets from the keypoint's pixel
+    __shared__ uint32_t spos[256];  // the same tests as byte positions inside a staged 17 x 20 patch (lo16, hi16)
+    __shared__ uint32_t patch[K4_THREADS / 32][BP_ROWS * BP_WORDS];
     for (int i = threadIdx.x; i < 256; i += K4_THREADS) {
         const uint32_t o = offs[i];
         soff[i] = o;
-        slin[i] = make_int2((int)(int8_t)(o & 0xff) * pitch + (int)(int8_t)((o >> 8) & 0xff),
-                            (int)(int8_t)((o >> 16) & 0xff) * pitch + (int)(int8_t)(o >> 24));
+        const int p1 = ((int)(int8_t)(o & 0xff) + 8) * (BP_WORDS * 4) + (int)(int8_t)((o >> 8) & 0xff) + 8;
+        const int p2 = ((int)(int8_t)((o >> 16) & 0xff) + 8) * (BP_WORDS * 4) + (int)(int8_t)(o >> 24) + 8;
+        spos[i] = (uint32_t)p1 | ((uint32_t)p2 << 16);
     }
     __syncthreads();
     const int f = blockIdx.y;
     const int n = n_per_frame ? n_per_frame[f] : n_fixed;
-    const int lane = threadIdx.x & 31;
-    const int kp = blockIdx.x * (K4_THREADS / 32) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int kp = blockIdx.x * (K4_THREADS / 32) + warp;
     if (kp >= n) return;
     const int row = rows[(size_t)f * kp_stride + kp], col = cols[(size_t)f * kp_stride + kp];
     uint32_t *d = desc + ((size_t)f * kp_stride + kp) * 8;
@@ -606,12 +726,25 @@ brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, i
     bool oob = false;
     uint32_t mine = 0;
     if (row + 8 < H && col + 8 < W) {
-        // interior keypoint (warp-uniform): no sample can wrap or leave the buffer, plain linear offsets
-        const uint8_t *base = S + (size_t)row * pitch + col;
+        // interior keypoint (warp-uniform): no sample can wrap or leave the buffer.  Stage the 17 x 17
+        // neighbourhood with aligned word loads (85 words, 3 rounds), then sample bytes from shared memory:
+        // 512 scattered single-byte global loads per keypoint become ~17 cache lines.
+        const int c0 = (col - 8) & ~3, phase = (col - 8) & 3;
+        const int last_w = (col + 8 - c0) >> 2;  // last word of a row that holds a needed byte
+        uint32_t *P = patch[warp];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int idx = lane + 32 * k;
+            const int r = idx / BP_WORDS, w = idx - r * BP_WORDS;
+            if (idx < BP_ROWS * BP_WORDS && w <= last_w)
+                P[idx] = __ldg(reinterpret_cast<const uint32_t *>(S + (size_t)(row - 8 + r) * pitch + c0) + w);
+        }
+        __syncwarp();
+        const uint8_t *Pb = reinterpret_cast<const uint8_t *>(P) + phase;
 #pragma unroll
         for (int w = 0; w < 8; w++) {
-            const int2 lo = slin[32 * w + lane];
-            const unsigned word = __ballot_sync(0xffffffffu, __ldg(base + lo.x) > __ldg(base + lo.y));
+            const uint32_t ps = spos[32 * w + lane];
+            const unsigned word = __ballot_sync(0xffffffffu, Pb[ps & 0xffff] > Pb[ps >> 16]);
             if (lane == w) mine = word;
         }
     } else {
