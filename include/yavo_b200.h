@@ -151,10 +151,10 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match);
 int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols,
                      float *scores, uint8_t *desc, int32_t *match_idx, int32_t *match_dist);
 
-/* frames per pipeline stage of yavo_process_host_batch (default 32) */
+/* frames per pipeline stage of yavo_process_host_batch (default 64) */
 int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames);
-/* frames per kernel sub-batch inside yavo_frontend_batch (0 = automatic: about 32 MB of pixels, so a
- * sub-batch's pixels and blurred planes stay L2-resident between the kernels that touch them) */
+/* frames per set of kernel launches inside yavo_frontend_batch (0 = the whole batch at once, the default) */
+
 int yavo_set_sub_batch(yavo_ctx *ctx, int frames);
 
 /* streaming callers: upload + frontend + fetch of one batch of host frames into slots [0, n), with the

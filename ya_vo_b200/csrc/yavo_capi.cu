@@ -71,8 +71,8 @@ struct yavo_ctx {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_repitched[2] = {nullptr, nullptr};
     std::vector<cudaEvent_t> ev_done;
-    int pipeline_chunk = 32;
-    int sub_batch = 0;  // frames per kernel sub-batch of yavo_frontend_batch (0 = about 32 MB of pixels)
+    int pipeline_chunk = 64;
+    int sub_batch = 0;  // frames per kernel sub-batch of yavo_frontend_batch (0 = the whole batch in one set of launches)
     // optional per-kernel timing (CUDA events on the context's stream around every launch)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -755,10 +755,10 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match) {
     if (int r = check_uploaded(ctx, slot0, n)) return r;
     if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
     CK(cudaSetDevice(ctx->device));
-    // sub-batches sized so that a sub-batch's pixels and blurred planes are still in the 126 MB L2 when the
-    // scoring and BRIEF kernels come back for them (about 32 MB of pitched pixels per sub-batch)
-    const int sub = ctx->sub_batch > 0 ? std::min(ctx->sub_batch, n)
-                                       : std::max(1, (int)std::min<size_t>((size_t)n, (32u << 20) / ctx->frame_stride));
+    // One set of launches for the whole batch by default: measured on B200 (profiles/), L2-sized sub-batches
+    // lose more to the latency-bound select kernel (one CTA per frame, wants hundreds in flight) than the
+    // scoring / BRIEF kernels gain from L2-resident planes.  sub_batch > 0 overrides.
+    const int sub = ctx->sub_batch > 0 ? std::min(ctx->sub_batch, n) : n;
     for (int s0 = 0; s0 < n; s0 += sub)
         if (int r = frontend_range(ctx, slot0 + s0, std::min(sub, n - s0), do_match != 0, s0 > 0)) return r;
     return 0;
