@@ -105,6 +105,14 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def workload_config(batch, kind):
+    """Shared by both arms so the driver compares like with like."""
+    return {"workload": "configs[1] batched (configs[2] shape): consecutive 1241x376 8-bit frames, FAST+BRIEF on each + "
+                        "brute-force Hamming match of frame f-1 -> f",
+            "frames_per_step_per_gpu": batch, "frame": [H, W], "max_keypoints": MAX_KP,
+            "input": "%s seed 1000+f" % kind}
+
+
 def cpu_baseline(sample_frames, offsets, cores):
     """The oracle (kind 'port') on a bounded sample of the same workload, all requested host threads."""
     from oracle import pyoracle as po
@@ -125,7 +133,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     offsets = synth.brief_offsets()
     n = max(8, min(args.batch, 2 * cores))  # bounded sample per step
-    frames = make_frames(n, 1000)
+    frames = make_frames(n, 1000, args.kind)
     from oracle import pyoracle as po
     po.build()
     for _ in range(args.warmup):
@@ -140,10 +148,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]/[2]: consecutive 1241x376 frames, FAST+BRIEF on each + Hamming match f-1->f",
-                   "frames_per_step_per_gpu": args.batch, "frame": [H, W], "max_keypoints": MAX_KP,
-                   "input": "clip(normal(128,30)) seed 1000+f", "note": "literal reference cannot be built here "
-                   "(OpenCV C++ absent); this is the CPU oracle port with identical outputs"},
+        "config": dict(workload_config(args.batch, args.kind), note="literal reference cannot be built here (OpenCV C++ "
+                       "absent); this is the CPU oracle port with identical outputs, all host threads"),
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -177,6 +183,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -298,11 +305,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]/[2] batched as configs[2]: consecutive 1241x376 frames, FAST+BRIEF on each + "
-                               "Hamming match f-1->f", "frames_per_step_per_gpu": B, "frame": [H, W],
-                   "max_keypoints": MAX_KP, "input": "%s seed 1000+f" % args.kind, "mean_keypoints": n_kp_mean,
+        "config": dict(workload_config(B, args.kind), **{"mean_keypoints": n_kp_mean,
                    "l2": "inputs larger than L2 (%d frames x %.2f MB pitched = %.0f MB > 126 MB)" % (B, 1280 * H / 1e6, B * 1280 * H / 1e6),
-                   "parallelism": "frame-sharded, %d rank(s), no collective on the data path" % world},
+                   "parallelism": "frame-sharded, %d rank(s), no collective on the data path" % world}),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches),
