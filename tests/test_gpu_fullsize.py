@@ -1,0 +1,130 @@
+"""GPU: BASELINE.json configs 3-5 at (or near) full size — exact against the oracle where the oracle finishes in
+seconds, size-independent properties beyond that."""
+import numpy as np
+import pytest
+
+from ya_vo_b200 import sharding, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def hamming_rows(a, b):
+    return np.unpackbits(np.bitwise_xor(a, b), axis=1).sum(axis=1)
+
+
+def test_4k_frame_20k_keypoints(cuda_lib, oracle, offsets):
+    """config 4: 3840x2160 uniform noise, cap raised to 20,000 (through the C ABI's max_kp)."""
+    img = synth.synth_frame("U", 3, 2160, 3840)
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=2160, max_cols=3840, max_kp=20000) as ctx:
+        ctx.set_brief_offsets(offsets)
+        ctx.upload(0, img)
+        assert np.array_equal(ctx.blurred(0), oracle.gaussian_blur(img))
+        r, c, s = ctx.fast_candidates(0)
+        er, ec, es = oracle.fast_candidates(img)
+        assert r.size == er.size > 300000
+        assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
+        kr, kc, ks, nc = ctx.fast_detect(0, 20000)
+        okr, okc, oks, onc = oracle.fast_detect(img, 20000)
+        assert nc == onc and kr.size == 20000
+        assert np.array_equal(kr, okr) and np.array_equal(kc, okc) and np.array_equal(ks.view(np.uint32), oks.view(np.uint32))
+        d, v, oob = ctx.brief_describe(0, kr, kc)
+        od, ov, ooob = oracle.brief(img, offsets, okr, okc)
+        assert np.array_equal(v, ov) and np.array_equal(d, od) and oob == ooob
+
+
+def test_candidate_overflow_is_reported(cuda_lib):
+    img = synth.synth_frame("U", 0)
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=376, max_cols=1241, max_kp=2000, max_cand=1000) as ctx:
+        ctx.upload(0, img)
+        with pytest.raises(cuda_lib.YavoError):
+            ctx.fast_detect(0)
+
+
+@pytest.mark.parametrize("n1,n2", [(1024, 65536), (16384, 16384), (65536, 1000)])
+def test_matcher_sweep_exact(cuda_lib, oracle, n1, n2):
+    """config 5 corners that the oracle still finishes in seconds."""
+    d1 = synth.synth_descriptors(n1, n1 * 131 + n2)
+    d2 = synth.planted_descriptors(d1, n2, 9)
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=64, max_cols=128, max_kp=16) as ctx:
+        idx, dist, sec, rev = ctx.match(d1, d2, extensions=True)
+    eidx, edist, esec, erev = oracle.match(d1, d2, extensions=True)
+    assert np.array_equal(idx, eidx) and np.array_equal(dist, edist)
+    assert np.array_equal(sec, esec) and np.array_equal(rev, erev)
+
+
+def test_matcher_64k_x_64k_properties(cuda_lib):
+    """config 5 at 64k x 64k (4.3 G pairs): properties instead of the full oracle."""
+    n = 65536
+    d1 = synth.synth_descriptors(n, 1)
+    rng = np.random.default_rng(2)
+    # train set: every query planted once with exactly 6 bits flipped, at a permuted position
+    d2 = d1.copy()
+    for k in range(6):
+        bits = rng.integers(0, 256, n)
+        d2[np.arange(n), bits // 8] ^= (1 << (bits % 8)).astype(np.uint8)
+    perm = rng.permutation(n)
+    d2p = np.empty_like(d2)
+    d2p[perm] = d2
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=64, max_cols=128, max_kp=16) as ctx:
+        idx, dist, sec, rev = ctx.match(d1, d2p, extensions=True)
+    assert idx.min() >= 0 and idx.max() < n
+    # the reported distance is the distance to the reported index
+    assert np.array_equal(dist, hamming_rows(d1, d2p[idx]))
+    # the planted twin is at most 6 bits away, random others ~128: the twin must be found
+    assert dist.max() <= 6 and np.array_equal(idx, perm)
+    assert np.all(sec >= dist) and sec.min() > 60
+    # cross-check direction agrees (each train descriptor's best query is its source)
+    assert np.array_equal(rev[perm], np.arange(n))
+    # minimality, brute force on a sample of queries
+    for i in rng.integers(0, n, 24):
+        full = hamming_rows(np.broadcast_to(d1[i], d2p.shape), d2p)
+        assert full.min() == dist[i] and int(full.argmin()) == idx[i]
+
+
+def test_sequence_batches_across_seams(cuda_lib, oracle, offsets):
+    """config 3 in miniature: a 13-frame sequence through process_shard in batches of 5 (seams re-use one frame),
+    as one rank and as two 'ranks' run one after the other; every frame and every consecutive pair once."""
+    F = 13
+    frames = synth.synth_batch(F, "G30", 1000)
+    frames[5] = synth.shifted_pair(frames[4], 5)
+    exp = oracle.pipeline(frames, offsets, 2000, True, nthreads=8)
+    with cuda_lib.Context(device=0, n_slots=8, max_rows=376, max_cols=1241, max_kp=2000) as ctx:
+        ctx.set_brief_offsets(offsets)
+        parts = [sharding.process_shard(ctx, lambda a, b: frames[a:b], F, r, 2, batch=5) for r in range(2)]
+        one = sharding.process_shard(ctx, lambda a, b: frames[a:b], F, 0, 1, batch=5)
+    two = {k: np.concatenate([p[k] for p in parts], axis=0) for k in one}
+    for res in (one, two):
+        assert np.array_equal(res["frame"], np.arange(F)) and np.array_equal(res["n_kp"], exp["n_kp"])
+        for f in range(F):
+            k = exp["n_kp"][f]
+            assert np.array_equal(res["rows"][f, :k], exp["rows"][f, :k])
+            assert np.array_equal(res["desc"][f, :k], exp["desc"][f, :k])
+            if f > 0:
+                kq = exp["n_kp"][f - 1]
+                assert np.array_equal(res["match_idx"][f, :kq], exp["match_idx"][f, :kq])
+                assert np.array_equal(res["match_dist"][f, :kq], exp["match_dist"][f, :kq])
+
+
+def test_pipelined_and_resident_paths_agree(cuda_lib, offsets):
+    """pinned host batch (3-stream pipeline) == pageable host batch == device-resident batch."""
+    import torch
+    frames = synth.synth_batch(40, "G30", 2000)
+    pinned = torch.empty(frames.shape, dtype=torch.uint8).pin_memory()
+    pinned.numpy()[:] = frames
+    with cuda_lib.Context(device=0, n_slots=40, max_rows=376, max_cols=1241, max_kp=2000) as ctx:
+        ctx.set_brief_offsets(offsets)
+        ctx.set_pipeline_chunk(7)
+        a = ctx.process_host_batch(pinned.numpy(), True)
+        a = {k: v.copy() for k, v in a.items()}
+        b = ctx.process_host_batch(frames, True)
+        b = {k: v.copy() for k, v in b.items()}
+        ctx.upload_batch(0, frames)
+        ctx.set_sub_batch(9)
+        ctx.frontend_batch(0, 40, True)
+        c = ctx.fetch_batch(0, 40)
+    for k in ("n_kp", "rows", "cols", "scores", "desc"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], c[k]), k
+    for f in range(1, 40):
+        kq = a["n_kp"][f - 1]
+        for k in ("match_idx", "match_dist"):
+            assert np.array_equal(a[k][f, :kq], b[k][f, :kq]) and np.array_equal(a[k][f, :kq], c[k][f, :kq]), (k, f)
