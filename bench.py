@@ -132,7 +132,7 @@ def run_reference(args):
     from ya_vo_b200 import synth
     cores = os.cpu_count() or 1
     offsets = synth.brief_offsets()
-    n = max(8, min(args.batch, 2 * cores))  # bounded sample per step
+    n = max(8, min(args.batch, 8 * cores))  # bounded sample per step (~0.5 s wall per step on the box's cores)
     frames = make_frames(n, 1000, args.kind)
     from oracle import pyoracle as po
     po.build()
@@ -322,7 +322,7 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        ns = max(8, min(B, 2 * cores))
+        ns = max(8, min(B, 16 * cores))  # ~15-30 s of CPU work (about 65 ms per frame and thread)
         v, dt = cpu_baseline(frames[:ns], offsets, cores)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "first %d frames of the step (%.1f s wall, %d threads), oracle port" % (ns, dt, cores)}

@@ -775,11 +775,12 @@ brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, i
 // tracked only when the caller asks for it (SECOND).  Chunk partials are combined by a small
 // reduce kernel (deterministic, no atomics).
 //
-// Pipe balance: the POPC (XU) pipe issues 16 lanes/clk/SM, the integer ALU 64.  A plain
-// 8 x (XOR, POPC) per pair is XU-bound at 2 pairs/clk/SM (measured 1.75, ncu: XU 91 %).  Three
-// carry-save adders (2 LOP3 each) first compress the eight XOR words to two weight-1 and three
-// weight-2 words, so a pair costs 5 POPC + 14 LOP3 instead of 8 POPC + 8 LOP3 — both pipes end up
-// about equally loaded (5/16 vs ~18/64 clk) and the bound moves to ~3.2 pairs/clk/SM.
+// Pipe balance: the POPC (XU) pipe issues 16 lanes/clk/SM, the integer ALU 64, the FMA pipe 64.  A plain
+// 8 x (XOR, POPC) per pair is XU-bound at 2 pairs/clk/SM (measured 1.75, ncu: XU 91 %).  Carry-save
+// adders (2 LOP3 each) first compress the eight XOR words: with three CSAs a pair costs 5 POPC + 14 LOP3
+// (measured 2.81 pairs/clk/SM, XU 93 %, ALU 79 %); with four CSAs 4 POPC + 16 LOP3, and with the
+// popcount sums and the key built by IMADs on the otherwise idle FMA pipe the ALU (17/64 clk) and XU
+// (4/16 clk) are balanced at a bound of ~3.8 pairs/clk/SM.
 // ================================================================================================
 constexpr int MQ = 128;        // queries per CTA == threads
 constexpr int MT = 128;        // train descriptors per shared-memory tile
@@ -791,14 +792,24 @@ __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t
     carry = (a & b) | (c & (a ^ b));  // LOP3 0xE8
 }
 
+// a * b + c on the FMA pipe (IMAD): keeps the additions off the integer ALU, which the LOP3s saturate
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// 256-bit Hamming distance: 8 XOR, four carry-save adders (8 LOP3) leave two weight-1 words, one weight-2
+// and one weight-4 word -> 4 POPC, summed with IMADs.  Per pair: ALU 8+8 (+1 min), XU 4, FMA 4.
 __device__ __forceinline__ uint32_t hamming256(const uint4 &a0, const uint4 &a1, const uint4 &b0, const uint4 &b1) {
     const uint32_t x0 = a0.x ^ b0.x, x1 = a0.y ^ b0.y, x2 = a0.z ^ b0.z, x3 = a0.w ^ b0.w;
     const uint32_t x4 = a1.x ^ b1.x, x5 = a1.y ^ b1.y, x6 = a1.z ^ b1.z, x7 = a1.w ^ b1.w;
-    uint32_t s1, c1, s2, c2, s3, c3;
+    uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
     csa(x0, x1, x2, s1, c1);
     csa(x3, x4, x5, s2, c2);
     csa(s1, s2, x6, s3, c3);
-    return (__popc(s3) + __popc(x7)) + 2u * (__popc(c1) + __popc(c2) + __popc(c3));
+    csa(c1, c2, c3, s4, c4);
+    return imad(__popc(c4), 4u, imad(__popc(s4), 2u, imad(__popc(s3), 1u, __popc(x7))));
 }
 
 template <bool SECOND>
@@ -834,7 +845,7 @@ match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict_
 #pragma unroll 4
         for (int j = 0; j < nt_tile; j++) {
             const uint32_t d = hamming256(a0, a1, st[j][0], st[j][1]);
-            const uint32_t key = (d << 22) + (uint32_t)(t0 + j);
+            const uint32_t key = imad(d, 1u << 22, (uint32_t)(t0 + j));
             if (SECOND) {
                 // ascending j and strict '<' == min over key; sec = second smallest distance
                 if (key < best) {
