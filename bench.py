@@ -281,7 +281,7 @@ def main():
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("detect_describe_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("detect_describe_dram_bytes_per_frame") * B  # per step, like `achieved`
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "detect_blur+compact_score+select_topk+brief (device time of their launches in one step)",
