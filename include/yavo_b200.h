@@ -162,6 +162,22 @@ int yavo_set_sub_batch(yavo_ctx *ctx, int frames);
  * into stages and the H2D copy of stage c+1, the kernels of stage c and the D2H copy of stage c-1 run on
  * three streams; pageable memory goes through the staging buffer without overlap.  Returns after all
  * results are in the host arrays. */
+/* Asynchronous form for a continuous stream of batches (the caller side of LoopHandler::getNextFrame /
+ * insertFrameFeatures, src/LoopHandler.cc:468-485,917-927): queues the H2D copies, kernels and D2H copies of one
+ * batch of PINNED host frames and returns at once.  Further submits may follow before yavo_wait — the next
+ * batch's pixels cross PCIe while this batch is in the kernels — provided each in-flight batch has its own
+ * output arrays.  Input and output arrays must stay valid and untouched until the batch has been waited for;
+ * no other call on the context is allowed in between.  Returns a ticket (0..15, reused round-robin) or a
+ * negative yavo_status. */
+int yavo_submit_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
+                           int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores, uint8_t *desc,
+                           int32_t *match_idx, int32_t *match_dist);
+/* blocks until the batch with this ticket has its results in its host arrays (later batches keep running) */
+int yavo_wait_batch(yavo_ctx *ctx, int ticket);
+/* blocks until every submitted batch has finished and its results are in the host arrays; reports a FAST
+ * candidate-list overflow of any of them */
+int yavo_wait(yavo_ctx *ctx);
+
 int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
                             int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores,
                             uint8_t *desc, int32_t *match_idx, int32_t *match_dist);

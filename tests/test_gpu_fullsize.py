@@ -128,3 +128,36 @@ def test_pipelined_and_resident_paths_agree(cuda_lib, offsets):
         kq = a["n_kp"][f - 1]
         for k in ("match_idx", "match_dist"):
             assert np.array_equal(a[k][f, :kq], b[k][f, :kq]) and np.array_equal(a[k][f, :kq], c[k][f, :kq]), (k, f)
+
+
+def test_async_submit_two_batches_in_flight(cuda_lib, offsets):
+    """yavo_submit_host_batch / yavo_wait_batch / yavo_wait: consecutive batches overlap and still give the
+    results of the synchronous path."""
+    import torch
+    fa = synth.synth_batch(24, "G30", 3000)
+    fb = synth.synth_batch(24, "B4", 4000)
+    pa = torch.empty(fa.shape, dtype=torch.uint8).pin_memory()
+    pb = torch.empty(fb.shape, dtype=torch.uint8).pin_memory()
+    pa.numpy()[:] = fa
+    pb.numpy()[:] = fb
+    with cuda_lib.Context(device=0, n_slots=24, max_rows=376, max_cols=1241, max_kp=2000) as ctx:
+        ctx.set_brief_offsets(offsets)
+        ctx.set_pipeline_chunk(5)
+        ra = {k: v.copy() for k, v in ctx.process_host_batch(pa.numpy(), True).items()}
+        rb = {k: v.copy() for k, v in ctx.process_host_batch(pb.numpy(), True).items()}
+        for rounds in range(2):
+            oa, ta = ctx.submit_host_batch(pa.numpy(), True)
+            ob, tb = ctx.submit_host_batch(pb.numpy(), True)
+            oc, tc = ctx.submit_host_batch(pa.numpy(), True)
+            ctx.wait_batch(ta)
+            assert np.array_equal(oa["n_kp"], ra["n_kp"]) and np.array_equal(oa["desc"], ra["desc"])
+            ctx.wait()
+            for got, exp in ((oa, ra), (ob, rb), (oc, ra)):
+                for k in ("n_kp", "rows", "cols", "scores", "desc"):
+                    assert np.array_equal(got[k], exp[k]), k
+                for f in range(1, 24):
+                    kq = exp["n_kp"][f - 1]
+                    assert np.array_equal(got["match_idx"][f, :kq], exp["match_idx"][f, :kq])
+                    assert np.array_equal(got["match_dist"][f, :kq], exp["match_dist"][f, :kq])
+        with pytest.raises(cuda_lib.YavoError):
+            ctx.submit_host_batch(fa, True)  # pageable memory is refused by the asynchronous entry point

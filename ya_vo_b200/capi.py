@@ -25,7 +25,7 @@ EXPORTS = [
     "yavo_ring_points", "yavo_fast_detect", "yavo_fast_candidates",
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
-    "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
+    "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
 ]
 
 
@@ -245,6 +245,23 @@ class Context:
 
     def set_pipeline_chunk(self, frames):
         self._ck(self._L.yavo_set_pipeline_chunk(self._h, int(frames)))
+
+    def submit_host_batch(self, frames, do_match=True, out=None):
+        """Asynchronous: frames must be pinned host memory; call wait() before reading `out`."""
+        n, H, W = frames.shape
+        out = out or self.alloc_batch_outputs(n)
+        t = self._ck(self._L.yavo_submit_host_batch(self._h, _p(frames), n, H, W, int(do_match), _p(out["n_kp"]),
+                                                    _p(out["rows"]), _p(out["cols"]), _p(out["scores"]), _p(out["desc"]),
+                                                    _p(out["match_idx"]), _p(out["match_dist"])))
+        for i in range(n):
+            self._shape[i] = (H, W)
+        return out, t
+
+    def wait_batch(self, ticket):
+        self._ck(self._L.yavo_wait_batch(self._h, int(ticket)))
+
+    def wait(self):
+        self._ck(self._L.yavo_wait(self._h))
 
     def process_host_batch(self, frames, do_match=True, out=None):
         n, H, W = frames.shape

@@ -70,7 +70,12 @@ struct yavo_ctx {
     // copy/compute overlap of yavo_process_host_batch
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_repitched[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> ev_done;
+    std::vector<cudaEvent_t> ev_done, ev_fetched;
+    std::vector<char> fetched_valid;
+    int fetched_C = 0;
+    cudaEvent_t ev_ticket[16] = {};
+    unsigned long long n_tickets = 0;
+    char raw_used[2] = {0, 0};
     int pipeline_chunk = 64;
     int sub_batch = 0;  // frames per kernel sub-batch of yavo_frontend_batch (0 = the whole batch in one set of launches)
     // optional per-kernel timing (CUDA events on the context's stream around every launch)
@@ -190,6 +195,8 @@ int launch_repitch(yavo_ctx *ctx, const uint8_t *d_src, size_t src_pitch, int sl
 // host pixels (row pitch `stride`) for n frames -> slots
 int upload_host(yavo_ctx *ctx, int slot0, int n, const uint8_t *pixels, int rows, int cols, int stride) {
     const size_t fbytes = (size_t)rows * cols, total = fbytes * n;
+    if (ctx->s_h2d) CK(cudaStreamSynchronize(ctx->s_h2d));  // the pipelined path shares d_raw
+    ctx->raw_used[0] = ctx->raw_used[1] = 0;
     if (int r = ensure_raw(ctx, total)) return r;
     if (stride == cols && is_pinned_host(pixels)) {
         CK(cudaMemcpyAsync(ctx->d_raw, pixels, total, cudaMemcpyHostToDevice, ctx->stream));
@@ -397,6 +404,9 @@ void yavo_destroy(yavo_ctx *c) {
     if (c->h_small) cudaFreeHost(c->h_small);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_fetched) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_ticket)
+        if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_repitched[i]) cudaEventDestroy(c->ev_repitched[i]);
@@ -794,23 +804,19 @@ static int fetch_async(yavo_ctx *ctx, cudaStream_t st, int base, int slot0, int 
     return 0;
 }
 
-int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
-                            int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores, uint8_t *desc,
-                            int32_t *match_idx, int32_t *match_dist) {
+int yavo_submit_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
+                           int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores, uint8_t *desc,
+                           int32_t *match_idx, int32_t *match_dist) {
     if (int r = check_slot(ctx, 0, n)) return r;
     if (n == 0) return 0;
     if (!pixels || rows < 1 || cols < 1 || rows > ctx->max_rows || cols > ctx->max_cols)
         return fail(ctx, YAVO_ERR_INVALID, "bad frame size %dx%d", rows, cols);
     if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
+    if (!is_pinned_host(pixels))
+        return fail(ctx, YAVO_ERR_INVALID, "yavo_submit_host_batch needs pinned host frames (cudaHostAlloc/cudaHostRegister)");
     CK(cudaSetDevice(ctx->device));
-    if (!is_pinned_host(pixels)) {
-        // pageable frames: packed through the pinned staging buffer, no overlap
-        if (int r = upload_host(ctx, 0, n, pixels, rows, cols, cols)) return r;
-        if (int r = frontend_range(ctx, 0, n, do_match != 0, false)) return r;
-        return yavo_fetch_batch(ctx, 0, n, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist);
-    }
-    // pinned frames: three streams.  Chunk c's pixels cross PCIe (s_h2d) while chunk c-1 is in the kernels
-    // (ctx->stream) and chunk c-2's keypoints / descriptors / matches go back (s_d2h).
+    // three streams: chunk c's pixels cross PCIe (s_h2d) while chunk c-1 is in the kernels (ctx->stream) and
+    // chunk c-2's keypoints / descriptors / matches go back (s_d2h); consecutive submits overlap the same way.
     if (!ctx->s_h2d) {
         CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -822,29 +828,94 @@ int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int row
     const int C = std::max(1, std::min(ctx->pipeline_chunk, n));
     const int nchunks = (n + C - 1) / C;
     while ((int)ctx->ev_done.size() < nchunks) {
-        cudaEvent_t e;
+        cudaEvent_t e, g;
         CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&g, cudaEventDisableTiming));
         ctx->ev_done.push_back(e);
+        ctx->ev_fetched.push_back(g);
+        ctx->fetched_valid.push_back(0);
     }
     const size_t fbytes = (size_t)rows * cols;
-    if (int r = ensure_raw(ctx, 2 * (size_t)C * fbytes)) return r;
+    if (2 * (size_t)C * fbytes > ctx->raw_bytes) {
+        // growing the staging buffer: nothing may be in flight
+        if (int r = yavo_wait(ctx)) return r;
+        if (int r = ensure_raw(ctx, 2 * (size_t)C * fbytes)) return r;
+        ctx->raw_used[0] = ctx->raw_used[1] = 0;
+    }
+    // results of an earlier submit still travelling out of the slots this one overwrites: same chunking ->
+    // wait chunk by chunk, otherwise wait for all of them
+    const bool same_shape = ctx->fetched_C == C;
+    if (!same_shape)
+        for (size_t c = 0; c < ctx->fetched_valid.size(); c++)
+            if (ctx->fetched_valid[c]) {
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fetched[c], 0));
+                ctx->fetched_valid[c] = 0;
+            }
+    ctx->fetched_C = C;
     for (int c = 0; c < nchunks; c++) {
         const int buf = c & 1, s0 = c * C, nc = std::min(C, n - s0);
         uint8_t *raw = ctx->d_raw + (size_t)buf * C * fbytes;
-        if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_repitched[buf], 0));
+        if (ctx->raw_used[buf]) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_repitched[buf], 0));
         CK(cudaMemcpyAsync(raw, pixels + (size_t)s0 * fbytes, (size_t)nc * fbytes, cudaMemcpyHostToDevice, ctx->s_h2d));
         CK(cudaEventRecord(ctx->ev_h2d[buf], ctx->s_h2d));
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
+        if (ctx->fetched_valid[c]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_fetched[c], 0));
+        // the match of (slot s0-1, s0) reads the previous chunk's descriptors: in order on ctx->stream
         if (int r = launch_repitch(ctx, raw, cols, s0, nc, rows, cols)) return r;
         CK(cudaEventRecord(ctx->ev_repitched[buf], ctx->stream));
+        ctx->raw_used[buf] = 1;
         if (int r = frontend_range(ctx, s0, nc, do_match != 0, c > 0)) return r;
         CK(cudaEventRecord(ctx->ev_done[c], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[c], 0));
         if (int r = fetch_async(ctx, ctx->s_d2h, 0, s0, nc, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist))
             return r;
+        CK(cudaEventRecord(ctx->ev_fetched[c], ctx->s_d2h));
+        ctx->fetched_valid[c] = 1;
     }
-    CK(cudaStreamSynchronize(ctx->s_d2h));
+    // ticket: an event after the last D2H copy of this batch
+    const int ticket = (int)(ctx->n_tickets++ % 16);
+    if (!ctx->ev_ticket[ticket]) CK(cudaEventCreateWithFlags(&ctx->ev_ticket[ticket], cudaEventDisableTiming | cudaEventBlockingSync));
+    CK(cudaEventRecord(ctx->ev_ticket[ticket], ctx->s_d2h));
+    return ticket;
+}
+
+int yavo_wait_batch(yavo_ctx *ctx, int ticket) {
+    if (!ctx || ticket < 0 || ticket >= 16 || !ctx->ev_ticket[ticket]) return YAVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->ev_ticket[ticket]));
+    return 0;
+}
+
+int yavo_wait(yavo_ctx *ctx) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->s_h2d) CK(cudaStreamSynchronize(ctx->s_h2d));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->s_d2h) CK(cudaStreamSynchronize(ctx->s_d2h));
+    for (size_t c = 0; c < ctx->fetched_valid.size(); c++) ctx->fetched_valid[c] = 0;
     return check_status(ctx);
+}
+
+int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
+                            int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores, uint8_t *desc,
+                            int32_t *match_idx, int32_t *match_dist) {
+    if (int r = check_slot(ctx, 0, n)) return r;
+    if (n == 0) return 0;
+    if (!pixels || rows < 1 || cols < 1 || rows > ctx->max_rows || cols > ctx->max_cols)
+        return fail(ctx, YAVO_ERR_INVALID, "bad frame size %dx%d", rows, cols);
+    if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
+    CK(cudaSetDevice(ctx->device));
+    if (!is_pinned_host(pixels)) {
+        // pageable frames: packed through the pinned staging buffer, no overlap
+        if (int r = yavo_wait(ctx)) return r;
+        if (int r = upload_host(ctx, 0, n, pixels, rows, cols, cols)) return r;
+        if (int r = frontend_range(ctx, 0, n, do_match != 0, false)) return r;
+        return yavo_fetch_batch(ctx, 0, n, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist);
+    }
+    const int t = yavo_submit_host_batch(ctx, pixels, n, rows, cols, do_match, n_kp, out_rows, out_cols, scores, desc,
+                                         match_idx, match_dist);
+    if (t < 0) return t;
+    return yavo_wait(ctx);
 }
 
 int yavo_set_sub_batch(yavo_ctx *ctx, int frames) {
