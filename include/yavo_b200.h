@@ -151,7 +151,8 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match);
 int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols,
                      float *scores, uint8_t *desc, int32_t *match_idx, int32_t *match_dist);
 
-/* frames per pipeline stage of yavo_process_host_batch (default 64) */
+/* frames per copy/compute pipeline stage of the host-batch entry points (0 = automatic, the default:
+ * a quarter of the batch, clamped to 16..128 frames) */
 int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames);
 /* frames per set of kernel launches inside yavo_frontend_batch (0 = the whole batch at once, the default) */
 
