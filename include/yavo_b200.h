@@ -63,7 +63,8 @@ int yavo_sync(yavo_ctx *ctx);
 void *yavo_get_stream(yavo_ctx *ctx);
 /* measurement: when on, every kernel launch is bracketed by a CUDA event pair on the context's stream.
  * yavo_profile_collect synchronises and returns, per kernel class
- * {0 repitch, 1 detect_blur, 2 compact_score, 3 select_topk, 4 brief, 5 match_partial, 6 match_reduce},
+ * {0 repitch, 1 detect_blur, 2 compact_score, 3 select_topk, 4 brief, 5 match_partial, 6 match_reduce,
+ *  7 filter_pairs},
  * the summed device time in ms and the number of launches since the last collect / set_profiling. */
 int yavo_set_profiling(yavo_ctx *ctx, int on);
 int yavo_profile_collect(yavo_ctx *ctx, double *ms_per_class, int *launches_per_class, int n_classes);
@@ -150,6 +151,14 @@ int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match);
  *   (row 0 of the batch is unused). */
 int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *rows, int32_t *cols,
                      float *scores, uint8_t *desc, int32_t *match_idx, int32_t *match_dist);
+
+/* Brief::removeOutliers (src/BriefDescriptor.cc:213-231) fused with the conversion of the kept matches to
+ * point pairs that the callers perform (src/LoopHandler.cc:232-237,251-254), on the device, for the matches
+ * yavo_frontend_batch left in slots (slot0, slot0+n).  For every f in [1, n): n_pairs[f] kept matches of the
+ * pair (slot0+f-1, slot0+f), min_dist[f] the smallest distance, pairs[f][j] = {q_row, q_col, t_row, t_col,
+ * dist, q_index, t_index, 0} in match order (arrays are n / n / n x max_kp x 8; entry 0 unused; any may be NULL). */
+int yavo_filter_pairs(yavo_ctx *ctx, int slot0, int n, int threshold, int32_t *n_pairs, int32_t *min_dist,
+                      int32_t *pairs);
 
 /* frames per copy/compute pipeline stage of the host-batch entry points (0 = automatic, the default:
  * a quarter of the batch, clamped to 16..128 frames) */

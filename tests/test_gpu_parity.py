@@ -205,3 +205,32 @@ def test_known_answers_through_mirror(cuda_lib):
     for p in pts[:11]:
         fd.putPixel(img2, p)
     assert fd.checkContiguousPixels(img2.getPixelVal(25, 25), pts, img2) is False
+
+
+def test_filter_pairs_matches_remove_outliers(cuda_lib, oracle, offsets, kitti):
+    """removeOutliers (src/BriefDescriptor.cc:213-231) + the callers' point-pair conversion, fused on the device."""
+    a = synth.synth_frame("G30", 1000)
+    frames = np.stack([a, synth.shifted_pair(a, 1), kitti, synth.shifted_pair(kitti, 2, 0, 2), np.full((376, 1241), 9, np.uint8),
+                       synth.synth_frame("U", 3)])
+    n = frames.shape[0]
+    exp = oracle.pipeline(frames, offsets, 2000, True, nthreads=4)
+    with cuda_lib.Context(device=0, n_slots=n, max_rows=376, max_cols=1241, max_kp=2000) as c:
+        c.set_brief_offsets(offsets)
+        c.upload_batch(0, frames)
+        c.frontend_batch(0, n, True)
+        for thr in (20, 64):
+            n_pairs, min_dist, pairs = c.filter_pairs(0, n, thr)
+            for f in range(1, n):
+                kq, kt = exp["n_kp"][f - 1], exp["n_kp"][f]
+                d = exp["match_dist"][f, :kq]
+                if kq == 0 or kt == 0:
+                    assert n_pairs[f] == 0
+                    continue
+                keep = oracle.remove_outliers(d, thr)
+                assert n_pairs[f] == keep.sum() and min_dist[f] == d.min()
+                qi = np.nonzero(keep)[0]
+                ti = exp["match_idx"][f, :kq][keep]
+                got = pairs[f, :n_pairs[f]]
+                assert np.array_equal(got[:, 5], qi) and np.array_equal(got[:, 6], ti) and np.array_equal(got[:, 4], d[keep])
+                assert np.array_equal(got[:, 0], exp["rows"][f - 1, qi]) and np.array_equal(got[:, 1], exp["cols"][f - 1, qi])
+                assert np.array_equal(got[:, 2], exp["rows"][f, ti]) and np.array_equal(got[:, 3], exp["cols"][f, ti])

@@ -25,7 +25,7 @@ EXPORTS = [
     "yavo_ring_points", "yavo_fast_detect", "yavo_fast_candidates",
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
-    "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
+    "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
 ]
 
 
@@ -125,7 +125,8 @@ class Context:
         """cudaStream_t of the context as an integer (wrap with torch.cuda.ExternalStream to record events)."""
         return int(self._L.yavo_get_stream(self._h) or 0)
 
-    KERNEL_CLASSES = ("repitch", "detect_blur", "compact_score", "select_topk", "brief", "match_partial", "match_reduce")
+    KERNEL_CLASSES = ("repitch", "detect_blur", "compact_score", "select_topk", "brief", "match_partial", "match_reduce",
+                      "filter_pairs")
 
     def set_profiling(self, on):
         self._ck(self._L.yavo_set_profiling(self._h, int(bool(on))))
@@ -239,6 +240,15 @@ class Context:
                                           _p(out["scores"]), _p(out["desc"]), _p(out["match_idx"]),
                                           _p(out["match_dist"])))
         return out
+
+    def filter_pairs(self, slot0, n, threshold=20):
+        """removeOutliers + point pairs on the device for the matches of the last frontend_batch."""
+        n_pairs = np.zeros(n, np.int32)
+        min_dist = np.zeros(n, np.int32)
+        pairs = np.zeros((n, self.max_kp, 8), np.int32)
+        self._ck(self._L.yavo_filter_pairs(self._h, int(slot0), int(n), int(threshold), _p(n_pairs), _p(min_dist),
+                                           _p(pairs)))
+        return n_pairs, min_dist, pairs
 
     def set_sub_batch(self, frames):
         self._ck(self._L.yavo_set_sub_batch(self._h, int(frames)))

@@ -45,6 +45,8 @@ struct yavo_ctx {
     int *d_nbk = nullptr;
     uint32_t *d_desc = nullptr;  // per slot max_kp x 8 words (compacted order)
     int32_t *d_midx = nullptr, *d_mdist = nullptr;
+    int32_t *d_pairs = nullptr;  // per slot max_kp x 8 ints: filtered point pairs of (slot-1, slot)
+    int *d_npairs = nullptr, *d_minDist = nullptr;
     int *d_status = nullptr, *d_noob = nullptr;
     uint32_t *d_offs = nullptr;
     bool offs_set = false;
@@ -86,7 +88,7 @@ struct yavo_ctx {
     std::string err;
 };
 
-enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_COUNT };
+enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_COUNT };
 
 namespace {
 
@@ -374,6 +376,10 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_desc, S * max_kp * 8));
     CKC(dalloc(&c->d_midx, S * max_kp));
     CKC(dalloc(&c->d_mdist, S * max_kp));
+    CKC(dalloc(&c->d_pairs, S * max_kp * 8));
+    CKC(dalloc(&c->d_npairs, S));
+    CKC(dalloc(&c->d_minDist, S));
+    CKC(cudaMemset(c->d_npairs, 0, S * sizeof(int)));
     CKC(dalloc(&c->d_status, 1));
     CKC(dalloc(&c->d_noob, 1));
     CKC(dalloc(&c->d_offs, 256));
@@ -397,7 +403,8 @@ void yavo_destroy(yavo_ctx *c) {
                     c->d_kp_row, c->d_kp_col,  c->d_kp_score, c->d_nkp,     c->d_bk_row,   c->d_bk_col, c->d_bk_score,
                     c->d_bk_id,  c->d_nbk,     c->d_desc,    c->d_midx,     c->d_mdist,    c->d_status, c->d_noob,
                     c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
-                    c->d_mo_idx, c->d_mo_dist, c->d_mo_sec,  c->d_part_key, c->d_part_sec, c->d_raw};
+                    c->d_mo_idx, c->d_mo_dist, c->d_mo_sec,  c->d_part_key, c->d_part_sec, c->d_raw,
+                    c->d_pairs,  c->d_npairs,  c->d_minDist};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -919,6 +926,24 @@ int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int row
                                          match_idx, match_dist);
     if (t < 0) return t;
     return yavo_wait(ctx);
+}
+
+int yavo_filter_pairs(yavo_ctx *ctx, int slot0, int n, int threshold, int32_t *n_pairs, int32_t *min_dist,
+                      int32_t *pairs) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (n < 2) return 0;
+    CK(cudaSetDevice(ctx->device));
+    const size_t o = (size_t)slot0 * ctx->max_kp;
+    PROF(KC_FILTER, filter_pairs_kernel<<<n - 1, K6_THREADS, 0, ctx->stream>>>(
+        ctx->d_midx + o, ctx->d_mdist + o, ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_nbk + slot0, ctx->max_kp,
+        threshold, ctx->d_pairs + o * 8, ctx->d_npairs + slot0, ctx->d_minDist + slot0));
+    CK_LAUNCH();
+    if (n_pairs) CK(cudaMemcpyAsync(n_pairs, ctx->d_npairs + slot0, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (min_dist) CK(cudaMemcpyAsync(min_dist, ctx->d_minDist + slot0, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (pairs)
+        CK(cudaMemcpyAsync(pairs, ctx->d_pairs + o * 8, 32 * (size_t)n * ctx->max_kp, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
 }
 
 int yavo_set_sub_batch(yavo_ctx *ctx, int frames) {

@@ -903,4 +903,73 @@ __global__ void match_reduce_kernel(const uint32_t *__restrict__ part_key, const
     }
 }
 
+// ================================================================================================
+// K6  outlier filter + point pairs  (reference src/BriefDescriptor.cc:213-231 and the conversion of the
+// kept matches to point pairs in src/LoopHandler.cc:232-237,251-254)
+// One CTA per frame pair (f-1, f): min-reduce of the match distances, keep distance < max(2*min, threshold)
+// in order, and write the kept matches as compact point pairs — what cv::findEssentialMat consumes — so a
+// caller that only needs the filtered correspondences never downloads descriptors or the full match list.
+// out_pairs rows: {q_row, q_col, t_row, t_col, dist, q_index, t_index, 0}
+// ================================================================================================
+constexpr int K6_THREADS = 256;
+
+__global__ void __launch_bounds__(K6_THREADS)
+filter_pairs_kernel(const int32_t *__restrict__ midx, const int32_t *__restrict__ mdist,
+                    const int32_t *__restrict__ bk_row, const int32_t *__restrict__ bk_col,
+                    const int *__restrict__ nbk, int kp_stride, int threshold, int32_t *__restrict__ out_pairs,
+                    int *__restrict__ out_n, int *__restrict__ out_min) {
+    __shared__ int red[K6_THREADS / 32];
+    __shared__ int s_min;
+    const int p = blockIdx.x;  // pair index: queries = slot p, train = slot p+1, matches stored at slot p+1
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nq = nbk[p], nt = nbk[p + 1];
+    const int32_t *mi = midx + (size_t)(p + 1) * kp_stride, *md = mdist + (size_t)(p + 1) * kp_stride;
+    int mn = 0x7fffffff;
+    for (int i = tid; i < nq; i += K6_THREADS) mn = min(mn, md[i]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    if (lane == 0) red[warp] = mn;
+    __syncthreads();
+    if (tid == 0) {
+        int m = 0x7fffffff;
+        for (int w = 0; w < K6_THREADS / 32; w++) m = min(m, red[w]);
+        s_min = m;
+    }
+    __syncthreads();
+    const long long lim = max(2LL * s_min, (long long)threshold);
+    int run = 0;
+    for (int base = 0; base < nq; base += K6_THREADS) {
+        const int i = base + tid;
+        const bool keep = i < nq && nt > 0 && (long long)md[i] < lim;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        __syncthreads();
+        if (lane == 0) red[warp] = __popc(b);
+        __syncthreads();
+        int pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < K6_THREADS / 32; w++) {
+            if (w < warp) pre += red[w];
+            tot += red[w];
+        }
+        if (keep) {
+            const int j = run + pre + __popc(b & ((1u << lane) - 1u));
+            const int t = mi[i];
+            int32_t *o = out_pairs + ((size_t)(p + 1) * kp_stride + j) * 8;
+            o[0] = bk_row[(size_t)p * kp_stride + i];
+            o[1] = bk_col[(size_t)p * kp_stride + i];
+            o[2] = bk_row[(size_t)(p + 1) * kp_stride + t];
+            o[3] = bk_col[(size_t)(p + 1) * kp_stride + t];
+            o[4] = md[i];
+            o[5] = i;
+            o[6] = t;
+            o[7] = 0;
+        }
+        run += tot;
+    }
+    if (tid == 0) {
+        out_n[p + 1] = run;
+        out_min[p + 1] = s_min;
+    }
+}
+
 }  // namespace yavo
