@@ -341,8 +341,10 @@ def main():
         cores = os.cpu_count() or 1
         ns = max(8, min(B, 16 * cores))  # ~15-30 s of CPU work (about 65 ms per frame and thread)
         v, dt = cpu_baseline(frames[:ns], offsets, cores)
+        v1, dt1 = cpu_baseline(frames[:8], offsets, 1)  # the reference itself is single-threaded
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "first %d frames of the step (%.1f s wall, %d threads), oracle port" % (ns, dt, cores)}
+                                "sample": "first %d frames of the step (%.1f s wall, %d threads), oracle port" % (ns, dt, cores),
+                                "single_thread_value": v1, "single_thread_sample": "first 8 frames, %.1f s" % dt1}
     elif rank == 0:
         line["cpu_baseline"] = None
     ctx.close()
