@@ -655,8 +655,12 @@ static int match_device(yavo_ctx *ctx, const uint32_t *dq, int n1, const uint32_
     const int chunk = std::max(1, (std::max(n2, 1) + chunks - 1) / chunks);
     if (int r = ensure_partials(ctx, (size_t)n1 * chunks)) return r;
     dim3 grid((n1 + MQ - 1) / MQ, chunks, 1);
-    PROF(KC_MATCH, match_partial_kernel<true><<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk, chunks, n1,
-                                                       ctx->d_part_key, ctx->d_part_sec));
+    if (o_sec)  // second-best tracking only when the caller asked for it (ratio-test extension)
+        PROF(KC_MATCH, match_partial_kernel<true><<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk,
+                                                                                 chunks, n1, ctx->d_part_key, ctx->d_part_sec));
+    else
+        PROF(KC_MATCH, match_partial_kernel<false><<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk,
+                                                                                  chunks, n1, ctx->d_part_key, ctx->d_part_sec));
     CK_LAUNCH();
     PROF(KC_MATCH_REDUCE, match_reduce_kernel<<<dim3((n1 + 127) / 128, 1), 128, 0, ctx->stream>>>(
         ctx->d_part_key, ctx->d_part_sec, nullptr, n1, 0, nullptr, n2, 0, chunk, chunks, n1, o_idx, o_dist, o_sec));
@@ -700,7 +704,9 @@ int yavo_match(yavo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int 
     if (n1 > 0) CK(cudaMemcpyAsync(ctx->d_mq, d1, 32 * (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
     if (n2 > 0) CK(cudaMemcpyAsync(ctx->d_mt, d2, 32 * (size_t)n2, cudaMemcpyHostToDevice, ctx->stream));
     if (n1 > 0) {
-        if (int r = match_device(ctx, ctx->d_mq, n1, ctx->d_mt, n2, ctx->d_mo_idx, ctx->d_mo_dist, ctx->d_mo_sec)) return r;
+        if (int r = match_device(ctx, ctx->d_mq, n1, ctx->d_mt, n2, ctx->d_mo_idx, ctx->d_mo_dist,
+                                 out_second ? ctx->d_mo_sec : nullptr))
+            return r;
         CK(cudaMemcpyAsync(out_idx, ctx->d_mo_idx, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(out_dist, ctx->d_mo_dist, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
         if (out_second) CK(cudaMemcpyAsync(out_second, ctx->d_mo_sec, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
@@ -708,7 +714,7 @@ int yavo_match(yavo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int 
     }
     if (out_rev_idx && n2 > 0) {
         // cross-check extension: the same kernel with the roles swapped
-        if (int r = match_device(ctx, ctx->d_mt, n2, ctx->d_mq, n1, ctx->d_mo_idx, ctx->d_mo_dist, ctx->d_mo_sec)) return r;
+        if (int r = match_device(ctx, ctx->d_mt, n2, ctx->d_mq, n1, ctx->d_mo_idx, ctx->d_mo_dist, nullptr)) return r;
         CK(cudaMemcpyAsync(out_rev_idx, ctx->d_mo_idx, 4 * (size_t)n2, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }

@@ -345,6 +345,9 @@ __device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
 }
 
 // whole-CTA partition of [f,l); returns the cut to every thread.  Lpos/Rpos: global scratch.
+// Each thread classifies SEL_ITEMS consecutive positions per pass (one block-wide scan per 4096 elements).
+constexpr int SEL_ITEMS = 8;
+
 __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint32_t *Lpos, uint32_t *Rpos) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = l - f;
@@ -353,42 +356,81 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint
     const yavo_ent piv = A[f];
     const int cap = n / 2 + 1;
     int runL = 0, runR = 0;
-    for (int base = 0; base < n - 1; base += SEL_THREADS) {
-        const int i = base + tid;
-        const bool in = i < n - 1;
-        const int pL = f + 1 + i, pR = l - 1 - i;
-        const bool sL = in && !yavo_before(A[pL], piv);
-        const bool sR = in && !yavo_before(piv, A[pR]);
-        const unsigned bL = __ballot_sync(0xffffffffu, sL), bR = __ballot_sync(0xffffffffu, sR);
-        if (lane == 0) S.wtot[warp] = __popc(bL) | (__popc(bR) << 16);
+    for (int base = 0; base < n - 1; base += SEL_THREADS * SEL_ITEMS) {
+        const int i0 = base + tid * SEL_ITEMS;
+        unsigned fL = 0, fR = 0;
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; e++) {
+            const int i = i0 + e;
+            if (i < n - 1) {
+                fL |= (unsigned)(!yavo_before(A[f + 1 + i], piv)) << e;
+                fR |= (unsigned)(!yavo_before(piv, A[l - 1 - i])) << e;
+            }
+        }
+        const int packed = __popc(fL) | (__popc(fR) << 16);
+        int incl = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) S.wtot[warp] = incl;
         __syncthreads();
-        int preL = 0, preR = 0, totL = 0, totR = 0;
+        int pre = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < SEL_WARPS; w++) {
             const int t = S.wtot[w];
-            if (w < warp) { preL += t & 0xffff; preR += t >> 16; }
-            totL += t & 0xffff;
-            totR += t >> 16;
+            if (w < warp) pre += t;
+            tot += t;
         }
-        const unsigned lt = (1u << lane) - 1u;
-        const int rL = runL + preL + __popc(bL & lt), rR = runR + preR + __popc(bR & lt);
-        if (sL && rL < cap) Lpos[rL] = pL;
-        if (sR && rR < cap) Rpos[rR] = pR;
-        runL += totL;
-        runR += totR;
+        const int excl = pre + incl - packed;
+        int rL = runL + (excl & 0xffff), rR = runR + (excl >> 16);
+#pragma unroll
+        for (int e = 0; e < SEL_ITEMS; e++) {
+            if ((fL >> e) & 1u) {
+                if (rL < cap) Lpos[rL] = f + 1 + i0 + e;
+                rL++;
+            }
+            if ((fR >> e) & 1u) {
+                if (rR < cap) Rpos[rR] = l - 1 - (i0 + e);
+                rR++;
+            }
+        }
+        runL += tot & 0xffff;
+        runR += tot >> 16;
         __syncthreads();
     }
     const int nL = min(runL, cap), nR = min(runR, cap);
     const int npairs = min(nL, nR);
     int cnt = 0;
-    for (int i = tid; i < npairs; i += SEL_THREADS) {
-        const uint32_t a = Lpos[i], b = Rpos[i];
-        if (a < b) {
-            const yavo_ent t = A[a];
-            A[a] = A[b];
-            A[b] = t;
-            cnt++;
+    for (int i = tid; i < npairs; i += SEL_THREADS * 4) {
+        // four independent swaps per thread in flight (the pairs are disjoint)
+        uint32_t a[4], b[4];
+        yavo_ent va[4], vb[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int k = i + u * SEL_THREADS;
+            ok[u] = false;
+            if (k < npairs) {
+                a[u] = Lpos[k];
+                b[u] = Rpos[k];
+                ok[u] = a[u] < b[u];
+            }
         }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) {
+                va[u] = A[a[u]];
+                vb[u] = A[b[u]];
+            }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (ok[u]) {
+                A[a[u]] = vb[u];
+                A[b[u]] = va[u];
+                cnt++;
+            }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
@@ -541,7 +583,7 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
     return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
+__global__ void __launch_bounds__(SEL_THREADS, 3)
 select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
                    uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
                    int32_t *__restrict__ kp_row, int32_t *__restrict__ kp_col, float *__restrict__ kp_score,
