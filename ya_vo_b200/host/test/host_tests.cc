@@ -9,6 +9,7 @@
 //   host_tests pipeline <frameA.bin> <frameB.bin> <H> <W> <offsets.bin> <out.bin>
 //       tests/BriefDescriptorTest.cc:9-64 call order: FAST x2, BRIEF x2, match, removeOutliers(…,20),
 //       drawMatches; results are dumped for the pytest side to compare with the oracle.  Needs a GPU.
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -126,12 +127,29 @@ static int pipeline(char **a) {
     cv::Mat testImage1(H, W, CV_8UC1, A.data()), testImage2(H, W, CV_8UC1, B.data());
     Image testObj1(testImage1), testObj2(testImage2);
     FastDetector fd(12, 50);
+    {   // warm-up on a throw-away copy (context creation, first launches), then the reference's timing printouts
+        Image warm(testImage2);
+        auto w = fd.getFastFeatures(warm);
+        brief.computeBrief(w, warm);
+    }
+    auto start = std::chrono::high_resolution_clock::now();
     auto features1 = fd.getFastFeatures(testObj1);
+    auto stop = std::chrono::high_resolution_clock::now();
+    std::cout << "Time taken for FAST feature detection: "
+              << std::chrono::duration_cast<std::chrono::microseconds>(stop - start).count() << " us" << std::endl;
     std::vector<float> scores1 = fd.lastScores();
     auto features2 = fd.getFastFeatures(testObj2);
+    start = std::chrono::high_resolution_clock::now();
     brief.computeBrief(features1, testObj1);
+    stop = std::chrono::high_resolution_clock::now();
+    std::cout << "Time taken for BRIEF descriptor computation: "
+              << std::chrono::duration_cast<std::chrono::microseconds>(stop - start).count() << " us" << std::endl;
     brief.computeBrief(features2, testObj2);
+    start = std::chrono::high_resolution_clock::now();
     std::vector<Matches> matches = brief.matchFeatures(testObj1, testObj2);
+    stop = std::chrono::high_resolution_clock::now();
+    std::cout << "Time taken for matchFeatures: "
+              << std::chrono::duration_cast<std::chrono::microseconds>(stop - start).count() << " us" << std::endl;
     std::vector<Matches> filterMatches;
     brief.removeOutliers(matches, filterMatches, 20.0);
     cv::Mat sideBySide = brief.drawMatches(testObj1, testObj2, filterMatches);
