@@ -282,7 +282,7 @@ compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, in
 // ================================================================================================
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
-constexpr int SEL_SMEM_ENTS = 4096;     // candidates kept in shared memory once the active prefix fits
+constexpr int SEL_SMEM_ENTS = 8192;     // candidates kept in shared memory once the active prefix fits
 constexpr int SEL_WARP_MAX = 512;       // ranges up to this size are partitioned by one warp
 constexpr int SEL_QCAP = 512;           // shared work queue (ring)
 constexpr int SEL_STACK = 32;           // per-warp overflow stack
@@ -297,6 +297,7 @@ struct SelShared {
     int ready[SEL_QCAP];
     SelRange stack[SEL_WARPS][SEL_STACK];
     uint16_t wscratch[SEL_WARPS][2][SEL_WARP_MAX / 2 + 2];
+    uint16_t bscratch[2][SEL_SMEM_ENTS / 2 + 2];  // CTA-partition stopper lists while the data is in smem
     SelRange big[2][SEL_BIG];
     int nbig[2];
     int q_head, q_tail, pending;
@@ -348,7 +349,8 @@ __device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
 // Each thread classifies SEL_ITEMS consecutive positions per pass (one block-wide scan per 4096 elements).
 constexpr int SEL_ITEMS = 8;
 
-__device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint32_t *Lpos, uint32_t *Rpos) {
+template <typename PosT>
+__device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, PosT *Lpos, PosT *Rpos) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = l - f;
     if (tid == 0) yavo_median_to_first(A, f, l);
@@ -388,11 +390,11 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint
 #pragma unroll
         for (int e = 0; e < SEL_ITEMS; e++) {
             if ((fL >> e) & 1u) {
-                if (rL < cap) Lpos[rL] = f + 1 + i0 + e;
+                if (rL < cap) Lpos[rL] = (PosT)(1 + i0 + e);  // positions relative to f
                 rL++;
             }
             if ((fR >> e) & 1u) {
-                if (rR < cap) Rpos[rR] = l - 1 - (i0 + e);
+                if (rR < cap) Rpos[rR] = (PosT)(n - 1 - (i0 + e));
                 rR++;
             }
         }
@@ -413,9 +415,11 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint
             const int k = i + u * SEL_THREADS;
             ok[u] = false;
             if (k < npairs) {
-                a[u] = Lpos[k];
-                b[u] = Rpos[k];
+                a[u] = (uint32_t)Lpos[k];
+                b[u] = (uint32_t)Rpos[k];
                 ok[u] = a[u] < b[u];
+                a[u] += f;
+                b[u] += f;
             }
         }
 #pragma unroll
@@ -440,9 +444,9 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, uint
         int m = 0;
         for (int w = 0; w < SEL_WARPS; w++) m += S.wtot[w];
         uint32_t cut = 0xffffffffu;
-        if (m < nL) cut = Lpos[m];
-        if (m >= 1) cut = min(cut, Rpos[m - 1]);
-        S.bcast[0] = (int)cut;
+        if (m < nL) cut = (uint32_t)Lpos[m];
+        if (m >= 1) cut = min(cut, (uint32_t)Rpos[m - 1]);
+        S.bcast[0] = f + (int)cut;
     }
     __syncthreads();
     const int cut = S.bcast[0];
@@ -583,7 +587,7 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
     return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS, 3)
+__global__ void __launch_bounds__(SEL_THREADS, 2)
 select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
                    uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
                    int32_t *__restrict__ kp_row, int32_t *__restrict__ kp_col, float *__restrict__ kp_score,
@@ -628,6 +632,18 @@ select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__r
     int cur = 0;
     while (S.nbig[cur] > 0) {
         const int nb = S.nbig[cur], nxt = cur ^ 1;
+        if (!in_smem) {  // move the active prefix into shared memory as soon as it fits
+            int E = min(N, K);
+            for (int i = 0; i < nb; i++) E = max(E, S.big[cur][i].l);
+            const int qt = S.q_tail;
+            for (int i = 0; i < qt; i++) E = max(E, S.ring[i].l);
+            if (E <= SEL_SMEM_ENTS) {
+                for (int i = tid; i < E; i += SEL_THREADS) sbuf[i] = G[i];
+                A = sbuf;
+                in_smem = true;
+                __syncthreads();
+            }
+        }
         for (int i = 0; i < nb; i++) {
             const SelRange r = S.big[cur][i];
             int cut;
@@ -636,7 +652,8 @@ select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__r
                 __syncthreads();
                 continue;
             }
-            cut = sel_block_partition(S, A, r.f, r.l, Lpos, Rpos);
+            cut = in_smem ? sel_block_partition<uint16_t>(S, A, r.f, r.l, S.bscratch[0], S.bscratch[1])
+                          : sel_block_partition<uint32_t>(S, A, r.f, r.l, Lpos, Rpos);
             if (tid == 0) {
                 const SelRange ch[2] = {{r.f, cut, r.d - 1}, {cut, r.l, r.d - 1}};
                 for (int c = 0; c < 2; c++) {
@@ -660,6 +677,7 @@ select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__r
         if (E <= SEL_SMEM_ENTS) {
             for (int i = tid; i < E; i += SEL_THREADS) sbuf[i] = G[i];
             A = sbuf;
+            in_smem = true;
         }
     }
     if (tid == 0) S.pending = S.q_tail;
