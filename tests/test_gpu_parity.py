@@ -234,3 +234,47 @@ def test_filter_pairs_matches_remove_outliers(cuda_lib, oracle, offsets, kitti):
                 assert np.array_equal(got[:, 5], qi) and np.array_equal(got[:, 6], ti) and np.array_equal(got[:, 4], d[keep])
                 assert np.array_equal(got[:, 0], exp["rows"][f - 1, qi]) and np.array_equal(got[:, 1], exp["cols"][f - 1, qi])
                 assert np.array_equal(got[:, 2], exp["rows"][f, ti]) and np.array_equal(got[:, 3], exp["cols"][f, ti])
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (2, 3), (3, 9), (4, 4), (8, 8), (9, 130), (130, 9), (17, 257)])
+def test_tiny_and_odd_frames(cuda_lib, oracle, offsets, H, W):
+    """frames smaller than the blur kernel / the FAST border: reflected borders, empty interiors."""
+    img = synth.synth_frame("U", 900 + H * 7 + W, H, W)
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=H, max_cols=W, max_kp=64) as c:
+        c.set_brief_offsets(offsets)
+        c.upload(0, img)
+        assert np.array_equal(c.download(0), img)
+        assert np.array_equal(c.blurred(0), oracle.gaussian_blur(img))
+        r, cc, s, nc = c.fast_detect(0)
+        er, ec, es, enc = oracle.fast_detect(img, 64)
+        assert nc == enc and np.array_equal(r, er) and np.array_equal(cc, ec)
+        rows = np.array([0, H // 2, H - 1, 8], np.int32)
+        cols = np.array([0, W // 2, W - 1, 8], np.int32)
+        d, v, oob = c.brief_describe(0, rows, cols)
+        ed, ev, eoob = oracle.brief(img, offsets, rows, cols)
+        assert np.array_equal(v, ev) and np.array_equal(d, ed) and oob == eoob
+
+
+def test_argument_errors_are_reported(cuda_lib, offsets):
+    with cuda_lib.Context(device=0, n_slots=2, max_rows=64, max_cols=64, max_kp=100) as c:
+        with pytest.raises(cuda_lib.YavoError):
+            c.fast_detect(0)  # nothing uploaded
+        with pytest.raises(cuda_lib.YavoError):
+            c.upload(5, np.zeros((8, 8), np.uint8))  # slot out of range
+        with pytest.raises(cuda_lib.YavoError):
+            c.upload(0, np.zeros((65, 8), np.uint8))  # larger than the context
+        c.upload(0, synth.synth_frame("U", 1, 64, 64))
+        with pytest.raises(cuda_lib.YavoError):
+            c.brief_describe(0, [10], [10])  # offsets not set
+        with pytest.raises(cuda_lib.YavoError):
+            c.set_brief_offsets(np.full((256, 4), 9, np.int32))  # outside [-8, 8]
+        c.set_brief_offsets(offsets)
+        with pytest.raises(cuda_lib.YavoError):
+            c.fast_detect(0, 101)  # more keypoints than the context was created for
+        c.upload(1, synth.synth_frame("U", 2, 32, 64))
+        with pytest.raises(cuda_lib.YavoError):
+            c.frontend_batch(0, 2, True)  # slots of different sizes in one batch
+        d, v, _ = c.brief_describe(0, [], [])
+        assert d.shape == (0, 32)
+    with pytest.raises(cuda_lib.YavoError):
+        cuda_lib.Context(device=99)
