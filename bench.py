@@ -113,6 +113,27 @@ def workload_config(batch, kind):
             "input": "%s seed 1000+f" % kind}
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pins this rank to the CPUs NVML reports as local to its GPU, so the pinned frame / result buffers it
+    allocates afterwards live on that socket (matters for the host-fed e2e leg at 4-8 GPUs)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1 and 64 * w + b < ncpu]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return len(allowed)
+    except Exception:
+        pass
+    return None
+
+
 def cpu_baseline(sample_frames, offsets, cores):
     """The oracle (kind 'port') on a bounded sample of the same workload, all requested host threads."""
     from oracle import pyoracle as po
@@ -184,6 +205,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
     os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    numa = bind_to_gpu_numa_node(local)  # pinned buffers are first-touched on the GPU's own socket
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -324,7 +346,8 @@ def main():
         "dtype": "u8", "data": "synthetic",
         "config": dict(workload_config(B, args.kind), **{"mean_keypoints": n_kp_mean,
                    "l2": "inputs larger than L2 (%d frames x %.2f MB pitched = %.0f MB > 126 MB)" % (B, 1280 * H / 1e6, B * 1280 * H / 1e6),
-                   "parallelism": "frame-sharded, %d rank(s), no collective on the data path" % world}),
+                   "parallelism": "frame-sharded, %d rank(s), no collective on the data path" % world,
+                   "cpus_bound_per_rank": numa}),
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_s / args.steps},
         "gpu_launches": int(launches),
@@ -338,7 +361,11 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU baseline may use every host core
+        except Exception:
+            pass
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         ns = max(8, min(B, 16 * cores))  # ~15-30 s of CPU work (about 65 ms per frame and thread)
         v, dt = cpu_baseline(frames[:ns], offsets, cores)
         v1, dt1 = cpu_baseline(frames[:8], offsets, 1)  # the reference itself is single-threaded
