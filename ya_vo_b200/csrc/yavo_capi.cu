@@ -233,7 +233,7 @@ int check_uploaded(yavo_ctx *ctx, int slot0, int n) {
 }
 
 // K1 (+K2) over slots [slot0, slot0+n)
-int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
+int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur, bool score = false) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t fs = ctx->frame_stride;
     const uint8_t *frames = ctx->d_frames + fs * slot0;
@@ -256,9 +256,15 @@ int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
         for (int s = slot0; s < slot0 + n; s++) ctx->slot_blur_valid[s] = 1;
     if (do_fast) {
         dim3 g2((H + K2_ROWS - 1) / K2_ROWS, n);
-        PROF(KC_COMPACT, compact_score_kernel<<<g2, K2_THREADS, 0, ctx->stream>>>(
-            frames, fs, ctx->pitch, H, W, mask, ctx->mask_words, rowcnt, ctx->rows_alloc,
-            ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0));
+        // the candidate list in scan order; scores are filled in by the select kernel unless asked for here
+        if (score)
+            PROF(KC_COMPACT, compact_score_kernel<true><<<g2, K2_THREADS, 0, ctx->stream>>>(
+                frames, fs, ctx->pitch, H, W, mask, ctx->mask_words, rowcnt, ctx->rows_alloc,
+                ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0));
+        else
+            PROF(KC_COMPACT, compact_score_kernel<false><<<g2, K2_THREADS, 0, ctx->stream>>>(
+                frames, fs, ctx->pitch, H, W, mask, ctx->mask_words, rowcnt, ctx->rows_alloc,
+                ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0));
         CK_LAUNCH();
     }
     return 0;
@@ -269,7 +275,7 @@ int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t o = (size_t)slot0 * ctx->max_kp;
     PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->stream>>>(
-        ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
+        ctx->d_frames + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
         ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp, ctx->d_kp_row + o,
         ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
         ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->d_status));
@@ -516,7 +522,7 @@ int yavo_fast_candidates(yavo_ctx *ctx, int slot, int cap, int32_t *out_rows, in
     if (int r = check_slot(ctx, slot)) return r;
     if (int r = check_uploaded(ctx, slot, 1)) return r;
     CK(cudaSetDevice(ctx->device));
-    if (int r = launch_detect(ctx, slot, 1, true, true)) return r;
+    if (int r = launch_detect(ctx, slot, 1, true, true, /*score=*/true)) return r;
     CK(cudaMemcpyAsync(ctx->h_small, ctx->d_ncand + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int n = ctx->h_small[0];

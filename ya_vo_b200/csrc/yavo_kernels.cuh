@@ -197,6 +197,7 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
 constexpr int K2_THREADS = 256;
 constexpr int K2_ROWS = K2_THREADS / 32;
 
+template <bool SCORE>
 __global__ void __launch_bounds__(K2_THREADS)
 compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
                      const uint32_t *__restrict__ mask, int mask_words, const int *__restrict__ rowcnt,
@@ -251,12 +252,15 @@ compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, in
             m &= m - 1;
             const int col = wi * 32 + b;
             if (p < max_cand) {
-                int a, bb, cc;
-                yavo_structure_tensor(
-                    [&](int r, int cidx) { return (int)__ldg(img + (size_t)r * pitch + cidx); }, row, col, &a,
-                    &bb, &cc);
-                cand[(size_t)f * max_cand + p] =
-                    yavo_make_ent(yavo_harris_from_tensor(a, bb, cc), ((uint32_t)row << 16) | (uint32_t)col);
+                float score = 0.f;  // !SCORE: positions only, the select kernel scores while it loads
+                if (SCORE) {
+                    int a, bb, cc;
+                    yavo_structure_tensor(
+                        [&](int r, int cidx) { return (int)__ldg(img + (size_t)r * pitch + cidx); }, row, col, &a,
+                        &bb, &cc);
+                    score = yavo_harris_from_tensor(a, bb, cc);
+                }
+                cand[(size_t)f * max_cand + p] = yavo_make_ent(score, ((uint32_t)row << 16) | (uint32_t)col);
             }
             p++;
         }
@@ -588,7 +592,8 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
 }
 
 __global__ void __launch_bounds__(SEL_THREADS, 2)
-select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
+select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch,
+                   yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
                    uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
                    int32_t *__restrict__ kp_row, int32_t *__restrict__ kp_col, float *__restrict__ kp_score,
                    int *__restrict__ nkp,
@@ -614,12 +619,22 @@ select_topk_kernel(yavo_ent *__restrict__ cand_all, int max_cand, const int *__r
     if (tid == 0) { S.nbig[0] = S.nbig[1] = 0; S.q_head = S.q_tail = 0; S.pending = 0; }
     __syncthreads();
 
-    yavo_ent *A = G;
-    bool in_smem = false;
-    if (N <= SEL_SMEM_ENTS) {
-        for (int i = tid; i < N; i += SEL_THREADS) sbuf[i] = G[i];
-        A = sbuf;
-        in_smem = true;
+    // load the candidate list (positions in scan order) and score it on the way in: Harris response from
+    // the 5x5 pixel window (reference src/FastDetector.cc:244-273); this kernel is latency-bound, so the
+    // arithmetic rides in otherwise idle issue slots
+    const bool in_smem_at_start = N <= SEL_SMEM_ENTS;
+    yavo_ent *A = in_smem_at_start ? sbuf : G;
+    bool in_smem = in_smem_at_start;
+    {
+        const uint8_t *img = frames + (size_t)f * frame_stride;
+        for (int i = tid; i < N; i += SEL_THREADS) {
+            const uint32_t rc = (uint32_t)G[i];
+            const int row = (int)(rc >> 16), col = (int)(rc & 0xffffu);
+            int a, bb, cc;
+            yavo_structure_tensor([&](int r, int cidx) { return (int)__ldg(img + (size_t)r * pitch + cidx); }, row, col,
+                                  &a, &bb, &cc);
+            A[i] = yavo_make_ent(yavo_harris_from_tensor(a, bb, cc), rc);
+        }
     }
     if (tid == 0 && N > 1) {
         const SelRange r0 = {0, N, 2 * (31 - __clz(N))};
