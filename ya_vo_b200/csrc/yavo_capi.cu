@@ -271,12 +271,17 @@ int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur, b
 }
 
 // K3 over slots [slot0, slot0+n)
+// K2 scores the candidates itself when only a few frames are in flight (its grid covers every row of every
+// frame); with many frames the select kernel scores while loading, in issue slots it would otherwise idle in
+inline bool score_in_k2(int n) { return n < 16; }
+
 int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t o = (size_t)slot0 * ctx->max_kp;
     PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->stream>>>(
         ctx->d_frames + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
-        ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp, ctx->d_kp_row + o,
+        ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp, score_in_k2(n) ? 0 : 1,
+        ctx->d_kp_row + o,
         ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
         ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->d_status));
     CK_LAUNCH();
@@ -553,7 +558,7 @@ int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int
     if (max_kp > ctx->max_kp)
         return fail(ctx, YAVO_ERR_CAPACITY, "max_kp %d exceeds the context's %d", max_kp, ctx->max_kp);
     CK(cudaSetDevice(ctx->device));
-    if (int r = launch_detect(ctx, slot, 1, true, true)) return r;
+    if (int r = launch_detect(ctx, slot, 1, true, true, score_in_k2(1))) return r;
     if (int r = launch_select(ctx, slot, 1, max_kp)) return r;
     CK(cudaMemcpyAsync(ctx->h_small + 1, ctx->d_ncand + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_small + 2, ctx->d_nkp + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -746,7 +751,7 @@ int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *kee
 // link_prev also matches (slot0-1, slot0), whose query descriptors an earlier call left in place.
 static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool link_prev) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
-    if (int r = launch_detect(ctx, slot0, n, true, true)) return r;
+    if (int r = launch_detect(ctx, slot0, n, true, true, score_in_k2(n))) return r;
     if (int r = launch_select(ctx, slot0, n, ctx->max_kp)) return r;
     const size_t o = (size_t)slot0 * ctx->max_kp;
     {

@@ -594,7 +594,7 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
 __global__ void __launch_bounds__(SEL_THREADS, 2)
 select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch,
                    yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
-                   uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
+                   uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride, int score_on_load,
                    int32_t *__restrict__ kp_row, int32_t *__restrict__ kp_col, float *__restrict__ kp_score,
                    int *__restrict__ nkp,
                    // compacted (checkBoundry-admitted) list that BRIEF / the matcher consume
@@ -625,7 +625,10 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     const bool in_smem_at_start = N <= SEL_SMEM_ENTS;
     yavo_ent *A = in_smem_at_start ? sbuf : G;
     bool in_smem = in_smem_at_start;
-    {
+    if (!score_on_load) {  // the list arrives scored (few frames in flight: K2 spreads the scoring over more SMs)
+        if (in_smem)
+            for (int i = tid; i < N; i += SEL_THREADS) sbuf[i] = G[i];
+    } else {
         const uint8_t *img = frames + (size_t)f * frame_stride;
         for (int i = tid; i < N; i += SEL_THREADS) {
             const uint32_t rc = (uint32_t)G[i];
