@@ -328,6 +328,19 @@ def main():
                 "peak_kind": peak_kind, "traffic": traffic, "ms_per_step": dd_ms,
                 "algorithmic_bytes_per_step": B * b_frame,
                 "note": "ALU-issue bound, not HBM bound: ~1 byte/pixel compulsory traffic vs tens of integer ops/pixel"}
+    # issue-slot roofline of the detect kernel: its instruction count per frame (ncu, profiles/traffic.json) against
+    # 4 warp instructions per clock per SM — the limit that actually binds this ALU-heavy kernel
+    roofline_issue = None
+    try:
+        wi = json.load(open(tp))["warp_insts_per_frame_by_kernel"]["detect_blur_kernel<1, 1>"]
+        clk = (clocks.get("sm_mhz") or sm_max) * 1e6
+        peak_issue = 148 * 4 * clk
+        ach = wi * B / (ms_step["detect_blur"] * 1e-3)
+        roofline_issue = {"bound": "issue", "kernel": "detect_blur", "achieved": ach / 1e9, "peak": peak_issue / 1e9,
+                          "unit": "G warp-inst/s", "frac": ach / peak_issue, "warp_insts_per_frame": wi,
+                          "lane_insts_per_pixel": wi * 32 / (H * W)}
+    except Exception:
+        pass
     pairs = float((outs["n_kp"][:-1].astype(np.float64) * outs["n_kp"][1:].astype(np.float64)).sum())
     m_ms = prof["match_partial"][0] / steps  # all match launches of one step
     gpairs = pairs / (m_ms * 1e-3) / 1e9 if m_ms > 0 else 0.0
@@ -354,6 +367,7 @@ def main():
         "clocks": clocks,
         "roofline": roofline,
         "roofline_popc": roofline_popc,
+        "roofline_issue": roofline_issue,
         "kernel_ms_per_launch": ms,
         "kernel_ms_per_step": ms_step,
         "kernel_launches_per_step": {k: v[1] / steps for k, v in prof.items()},
