@@ -32,10 +32,10 @@ __global__ void repitch_kernel(const uint8_t *__restrict__ src, size_t src_pitch
 
 // ================================================================================================
 // K1  detect + blur
-// One CTA per 128x32 pixel tile of one frame.  The tile plus a 4-pixel halo is staged in shared
-// memory as aligned 32-bit words (frame rows are stored with a pitch that is a multiple of 128 so
-// every tile row starts word-aligned and is read with coalesced 4-byte loads).  Two products come
-// out of the single read of the pixels:
+// One CTA per 128x32 pixel tile of one frame.  The tile plus its halo is staged in shared memory by
+// bulk asynchronous copies (cp.async.bulk, one 160-byte row each, completion on an mbarrier); frame
+// rows are stored with a pitch that is a multiple of 128 so every staged row is 16-byte aligned.
+// Two products come out of the single read of the pixels:
 //   * the FAST segment-test bitmask (1 bit per pixel, one word per 32 pixels) and per-row corner
 //     counts (reference src/FastDetector.cc:298-320); 4 pixels per thread with byte-SIMD
 //   * the 9x9 sigma-2.5 fixed-point Gaussian of the tile (reference src/BriefDescriptor.cc:90),
@@ -44,9 +44,42 @@ __global__ void repitch_kernel(const uint8_t *__restrict__ src, size_t src_pitch
 constexpr int TW = 128;            // tile width  (pixels)
 constexpr int TH = 32;             // tile height (pixels)
 constexpr int HALO = 4;
-constexpr int SW = (TW + 2 * HALO) / 4;  // 34 words per staged row
+constexpr int SW = (TW + 2 * HALO) / 4;  // 34 words per staged row that the kernels read
+constexpr int SLEAD = 16;                // staged rows start 16 bytes left of the tile (16-byte aligned for bulk copies)
+constexpr int SROW = SLEAD + TW + 16;    // 160 bytes staged per row
+constexpr int SROW_W = SROW / 4;         // 40 words
+constexpr int SPX = SLEAD / 4;           // word index of the tile's first pixel inside a staged row
 constexpr int SH = TH + 2 * HALO;        // 40 staged rows
 constexpr int K1_THREADS = 256;
+
+// ---- bulk asynchronous copy (TMA engine, cp.async.bulk -> SASS UBLKCP) with an mbarrier for completion ----
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 __device__ __forceinline__ int reflect101(int p, int n) {
     if (n == 1) return 0;
@@ -59,7 +92,8 @@ __global__ void __launch_bounds__(K1_THREADS)
 detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
                    uint8_t *__restrict__ blur, uint32_t *__restrict__ mask, int mask_words,
                    int *__restrict__ rowcnt, int rows_alloc) {
-    __shared__ uint32_t tile[SH][SW + 1];          // +1 word: rows land on different banks
+    __shared__ __align__(128) uint32_t tile[SH][SROW_W];  // staged rows: cols x0-16 .. x0+143
+    __shared__ __align__(8) uint64_t tile_bar;
     __shared__ uint4 hpair[SH / 2][TW / 4];        // [row pair][quad] -> 4 x (h[even] | h[odd] << 16)
 
     const int f = blockIdx.z;
@@ -67,20 +101,26 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     const uint8_t *img = frames + (size_t)f * frame_stride;
     const int tid = threadIdx.x;
 
-    // ---- stage tile rows y0-4 .. y0+35 (reflected into the image), cols x0-4 .. x0+131 ----------
-    // one warp per staged row: lane l loads word l (128 contiguous bytes), lanes 0/1 the two tail words
-    const int pitch_w = pitch >> 2;
-    const int wbase = (x0 - HALO) >> 2;  // may be -1 for the first tile column
+    // ---- stage tile rows y0-4 .. y0+35 (reflected into the image), cols x0-16 .. x0+143 -------------
+    // One bulk asynchronous copy (TMA engine) per staged row, issued by the lanes of warp 0 and tracked by an
+    // mbarrier: no per-thread address arithmetic or register staging.  Source and destination are 16-byte
+    // aligned because the frame pitch and the tile origin are multiples of 128.
     {
-        const int ln = tid & 31;
-        const int gw0 = max(wbase + ln, 0);                          // only word -1 can be negative
-        const int gw1 = min(wbase + 32 + ln, pitch_w - 1);           // tail words 32, 33
-        for (int tr = tid >> 5; tr < SH; tr += K1_THREADS / 32) {
-            const int gr = reflect101(y0 - HALO + tr, H);
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(img + (size_t)gr * pitch);
-            tile[tr][ln] = __ldg(src + min(gw0, pitch_w - 1));
-            if (ln < SW - 32) tile[tr][32 + ln] = __ldg(src + gw1);
+        const int src_col = max(x0 - SLEAD, 0);
+        const int dst_off = src_col - (x0 - SLEAD);                    // 16 for the first tile column, else 0
+        const uint32_t row_bytes = (uint32_t)min(SROW - dst_off, pitch - src_col);
+        if (tid == 0) mbar_init(&tile_bar, 1);
+        __syncthreads();
+        if (tid < 32) {
+            if (tid == 0) mbar_expect_tx(&tile_bar, row_bytes * SH);
+            __syncwarp();
+            for (int tr = tid; tr < SH; tr += 32) {
+                const int gr = reflect101(y0 - HALO + tr, H);
+                bulk_g2s(reinterpret_cast<uint8_t *>(&tile[tr][0]) + dst_off, img + (size_t)gr * pitch + src_col, row_bytes,
+                         &tile_bar);
+            }
         }
+        mbar_wait(&tile_bar, 0);
     }
     const bool edge_cols = DO_BLUR && (x0 == 0 || x0 + TW + HALO > W);
     if (edge_cols) {
@@ -91,11 +131,11 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
         for (int i = tid; i < SH * 8; i += K1_THREADS) {
             const int tr = i >> 3, j = i & 7;
             const int gc = (j < 4) ? (j - 4) : (W + j - 4);
-            const int tc = gc - (x0 - HALO);
-            if (tc < 0 || tc >= TW + 2 * HALO) continue;
+            const int tc = gc - (x0 - SLEAD);
+            if (tc < 0 || tc >= SROW) continue;
             if (j < 4 && x0 != 0) continue;
             const int gr = reflect101(y0 - HALO + tr, H);
-            tb[tr * (SW + 1) * 4 + tc] = __ldg(img + (size_t)gr * pitch + reflect101(gc, W));
+            tb[tr * SROW + tc] = __ldg(img + (size_t)gr * pitch + reflect101(gc, W));
         }
     }
     __syncthreads();
@@ -106,8 +146,8 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
         // horizontal pass: (SH/2) row pairs x 32 quads; thread -> one quad of one row pair
         for (int i = tid; i < (SH / 2) * (TW / 4); i += K1_THREADS) {
             const int rp = i >> 5, q = i & 31;
-            const uint32_t *ra = &tile[2 * rp][q + 1];
-            const uint32_t *rb = &tile[2 * rp + 1][q + 1];
+            const uint32_t *ra = &tile[2 * rp][q + SPX];
+            const uint32_t *rb = &tile[2 * rp + 1][q + SPX];
             uint32_t ha[4], hb[4];
             yavo_blur_h4(ra[-1], ra[0], ra[1], ha);
             yavo_blur_h4(rb[-1], rb[0], rb[1], hb);
@@ -128,9 +168,9 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
             if (gr >= 4 && gr < H - 4) {  // warp-uniform
                 const int sr = tr + HALO;
                 bool pre;
-                nib = yavo_fast4(&tile[sr - 3][lane + 1], &tile[sr - 2][lane + 1], &tile[sr - 1][lane + 1],
-                                 &tile[sr][lane + 1], &tile[sr + 1][lane + 1], &tile[sr + 2][lane + 1],
-                                 &tile[sr + 3][lane + 1], &pre);
+                nib = yavo_fast4(&tile[sr - 3][lane + SPX], &tile[sr - 2][lane + SPX], &tile[sr - 1][lane + SPX],
+                                 &tile[sr][lane + SPX], &tile[sr + 1][lane + SPX], &tile[sr + 2][lane + SPX],
+                                 &tile[sr + 3][lane + SPX], &pre);
                 nib &= colmask;
             }
             uint32_t v = nib << (4 * (lane & 7));
