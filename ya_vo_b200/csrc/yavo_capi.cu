@@ -48,7 +48,7 @@ struct yavo_ctx {
     int32_t *d_pairs = nullptr;  // per slot max_kp x 8 ints: filtered point pairs of (slot-1, slot)
     int *d_npairs = nullptr, *d_minDist = nullptr;
     int *d_status = nullptr, *d_noob = nullptr;
-    uint32_t *d_offs = nullptr;
+    uint32_t *d_offs = nullptr, *d_spos = nullptr;  // BRIEF tests: packed offsets / positions inside a staged patch
     bool offs_set = false;
     // scratch for the explicit-point / explicit-descriptor entry points
     int32_t *d_pt_row = nullptr, *d_pt_col = nullptr;
@@ -394,6 +394,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_status, 1));
     CKC(dalloc(&c->d_noob, 1));
     CKC(dalloc(&c->d_offs, 256));
+    CKC(dalloc(&c->d_spos, 256));
     CKC(cudaMemset(c->d_frames, 0, S * c->frame_stride));
     CKC(cudaMemset(c->d_status, 0, sizeof(int)));
     CKC(cudaMemset(c->d_nbk, 0, S * sizeof(int)));
@@ -415,7 +416,7 @@ void yavo_destroy(yavo_ctx *c) {
                     c->d_bk_id,  c->d_nbk,     c->d_desc,    c->d_midx,     c->d_mdist,    c->d_status, c->d_noob,
                     c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
                     c->d_mo_idx, c->d_mo_dist, c->d_mo_sec,  c->d_part_key, c->d_part_sec, c->d_raw,
-                    c->d_pairs,  c->d_npairs,  c->d_minDist};
+                    c->d_pairs,  c->d_npairs,  c->d_minDist, c->d_spos};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -581,7 +582,7 @@ int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int
 
 int yavo_set_brief_offsets(yavo_ctx *ctx, const int32_t *offsets) {
     if (!ctx || !offsets) return YAVO_ERR_INVALID;
-    uint32_t packed[256];
+    uint32_t packed[256], spos[256];
     for (int j = 0; j < 256; j++) {
         uint32_t w = 0;
         for (int k = 0; k < 4; k++) {
@@ -590,9 +591,14 @@ int yavo_set_brief_offsets(yavo_ctx *ctx, const int32_t *offsets) {
             w |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
         }
         packed[j] = w;
+        // the same test as byte positions inside the 17 x 20-byte patch the kernel stages per keypoint
+        const int p1 = (offsets[4 * j + 0] + 8) * (BP_WORDS * 4) + offsets[4 * j + 1] + 8;
+        const int p2 = (offsets[4 * j + 2] + 8) * (BP_WORDS * 4) + offsets[4 * j + 3] + 8;
+        spos[j] = (uint32_t)p1 | ((uint32_t)p2 << 16);
     }
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->d_offs, packed, sizeof packed, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_spos, spos, sizeof spos, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->offs_set = true;
     return 0;
@@ -647,9 +653,10 @@ int yavo_brief_describe(yavo_ctx *ctx, int slot, const int32_t *rows, const int3
     CK(cudaMemcpyAsync(ctx->d_pt_row, rows, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_pt_col, cols, 4 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_noob, 0, sizeof(int), ctx->stream));
-    dim3 grid((n + K4_THREADS / 32 - 1) / (K4_THREADS / 32), 1);
+    const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
+    dim3 grid((n + kp_per_block - 1) / kp_per_block, 1);
     PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(ctx->d_blur + ctx->frame_stride * slot, ctx->frame_stride,
-                                                       ctx->pitch, H, W, ctx->d_offs, ctx->d_pt_row, ctx->d_pt_col,
+                                                       ctx->pitch, H, W, ctx->d_offs, ctx->d_spos, ctx->d_pt_row, ctx->d_pt_col,
                                                        nullptr, n, n, ctx->d_pt_desc, ctx->d_pt_valid, ctx->d_noob));
     CK_LAUNCH();
     CK(cudaMemcpyAsync(out_desc, ctx->d_pt_desc, 32 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -755,9 +762,10 @@ static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool l
     if (int r = launch_select(ctx, slot0, n, ctx->max_kp)) return r;
     const size_t o = (size_t)slot0 * ctx->max_kp;
     {
-        dim3 grid((ctx->max_kp + K4_THREADS / 32 - 1) / (K4_THREADS / 32), n);
+        const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
+        dim3 grid((ctx->max_kp + kp_per_block - 1) / kp_per_block, n);
         PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(
-            ctx->d_blur + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, H, W, ctx->d_offs,
+            ctx->d_blur + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, H, W, ctx->d_offs, ctx->d_spos,
             ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_nbk + slot0, 0, ctx->max_kp, ctx->d_desc + o * 8, nullptr,
             nullptr));
         CK_LAUNCH();

@@ -806,81 +806,86 @@ __device__ __forceinline__ int brief_sample(const uint8_t *S, int pitch, int H, 
     return (int)__ldg(S + (size_t)r * pitch + c);
 }
 
-// offsets packed one test per word: byte0 = drow1, byte1 = dcol1, byte2 = drow2, byte3 = dcol2 (int8)
+// offsets packed one test per word: byte0 = drow1, byte1 = dcol1, byte2 = drow2, byte3 = dcol2 (int8);
+// spos: the same tests as byte positions inside a staged 17 x 20 patch (lo16 = first sample, hi16 = second),
+// both tables prepared by the host when the offset table is set.
 constexpr int BP_WORDS = 5;              // words per staged patch row: 17 columns + alignment phase <= 20 bytes
 constexpr int BP_ROWS = 17;              // rows row-8 .. row+8
+constexpr int BP_KPW = 4;                // keypoints per warp (amortises the per-warp set-up)
 
 __global__ void __launch_bounds__(K4_THREADS)
 brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, int H, int W,
-             const uint32_t *__restrict__ offs, const int32_t *__restrict__ rows,
+             const uint32_t *__restrict__ offs, const uint32_t *__restrict__ spos, const int32_t *__restrict__ rows,
              const int32_t *__restrict__ cols, const int *__restrict__ n_per_frame, int n_fixed,
              int kp_stride, uint32_t *__restrict__ desc, uint8_t *__restrict__ valid,
              int *__restrict__ n_oob) {
-    __shared__ uint32_t soff[256];
-    __shared__ uint32_t spos[256];  // the same tests as byte positions inside a staged 17 x 20 patch (lo16, hi16)
     __shared__ uint32_t patch[K4_THREADS / 32][BP_ROWS * BP_WORDS];
-    for (int i = threadIdx.x; i < 256; i += K4_THREADS) {
-        const uint32_t o = offs[i];
-        soff[i] = o;
-        const int p1 = ((int)(int8_t)(o & 0xff) + 8) * (BP_WORDS * 4) + (int)(int8_t)((o >> 8) & 0xff) + 8;
-        const int p2 = ((int)(int8_t)((o >> 16) & 0xff) + 8) * (BP_WORDS * 4) + (int)(int8_t)(o >> 24) + 8;
-        spos[i] = (uint32_t)p1 | ((uint32_t)p2 << 16);
-    }
-    __syncthreads();
     const int f = blockIdx.y;
     const int n = n_per_frame ? n_per_frame[f] : n_fixed;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int kp = blockIdx.x * (K4_THREADS / 32) + warp;
-    if (kp >= n) return;
-    const int row = rows[(size_t)f * kp_stride + kp], col = cols[(size_t)f * kp_stride + kp];
-    uint32_t *d = desc + ((size_t)f * kp_stride + kp) * 8;
-    const bool ok = brief_admits(row, col, H, W);
-    if (valid && lane == 0) valid[(size_t)f * kp_stride + kp] = ok ? 1 : 0;
-    if (!ok) {
-        if (lane < 8) d[lane] = 0u;
-        return;
+    const int kp0 = (blockIdx.x * (K4_THREADS / 32) + warp) * BP_KPW;
+    if (kp0 >= n) return;
+    // this lane's eight tests (j = 32 w + lane), the same for every keypoint
+    uint32_t ps[8];
+#pragma unroll
+    for (int w = 0; w < 8; w++) ps[w] = __ldg(spos + 32 * w + lane);
+    // this lane's three patch words (idx = lane + 32 k -> patch row r, word w)
+    int pr[3], pw[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int idx = lane + 32 * k;
+        pr[k] = idx / BP_WORDS;
+        pw[k] = idx - pr[k] * BP_WORDS;
     }
     const uint8_t *S = blur + (size_t)f * frame_stride;
+    uint32_t *P = patch[warp];
     bool oob = false;
-    uint32_t mine = 0;
-    if (row + 8 < H && col + 8 < W) {
-        // interior keypoint (warp-uniform): no sample can wrap or leave the buffer.  Stage the 17 x 17
-        // neighbourhood with aligned word loads (85 words, 3 rounds), then sample bytes from shared memory:
-        // 512 scattered single-byte global loads per keypoint become ~17 cache lines.
-        const int c0 = (col - 8) & ~3, phase = (col - 8) & 3;
-        const int last_w = (col + 8 - c0) >> 2;  // last word of a row that holds a needed byte
-        uint32_t *P = patch[warp];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const int idx = lane + 32 * k;
-            const int r = idx / BP_WORDS, w = idx - r * BP_WORDS;
-            if (idx < BP_ROWS * BP_WORDS && w <= last_w)
-                P[idx] = __ldg(reinterpret_cast<const uint32_t *>(S + (size_t)(row - 8 + r) * pitch + c0) + w);
+    for (int kp = kp0; kp < min(kp0 + BP_KPW, n); kp++) {
+        const int row = rows[(size_t)f * kp_stride + kp], col = cols[(size_t)f * kp_stride + kp];
+        uint32_t *d = desc + ((size_t)f * kp_stride + kp) * 8;
+        const bool ok = brief_admits(row, col, H, W);
+        if (valid && lane == 0) valid[(size_t)f * kp_stride + kp] = ok ? 1 : 0;
+        if (!ok) {
+            if (lane < 8) d[lane] = 0u;
+            continue;
         }
-        __syncwarp();
-        const uint8_t *Pb = reinterpret_cast<const uint8_t *>(P) + phase;
+        uint32_t mine = 0;
+        if (row + 8 < H && col + 8 < W) {
+            // interior keypoint (warp-uniform): no sample can wrap or leave the buffer.  Stage the 17 x 17
+            // neighbourhood with aligned word loads (85 words, 3 rounds), then sample bytes from shared memory:
+            // 512 scattered single-byte global loads per keypoint become ~17 cache lines.
+            const int c0 = (col - 8) & ~3, phase = (col - 8) & 3;
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(S + (size_t)(row - 8) * pitch + c0);
+            const int pitch_w = pitch >> 2;
+            __syncwarp();  // the previous keypoint's samples are done with the patch
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
-            const uint32_t ps = spos[32 * w + lane];
-            const unsigned word = __ballot_sync(0xffffffffu, Pb[ps & 0xffff] > Pb[ps >> 16]);
-            if (lane == w) mine = word;
-        }
-    } else {
+            for (int k = 0; k < 3; k++)
+                if (lane + 32 * k < BP_ROWS * BP_WORDS) P[lane + 32 * k] = __ldg(src + pr[k] * pitch_w + pw[k]);
+            __syncwarp();
+            const uint8_t *Pb = reinterpret_cast<const uint8_t *>(P) + phase;
 #pragma unroll
-        for (int w = 0; w < 8; w++) {
-            const uint32_t o = soff[32 * w + lane];
-            const int r1 = row + (int)(int8_t)(o & 0xff), c1 = col + (int)(int8_t)((o >> 8) & 0xff);
-            const int r2 = row + (int)(int8_t)((o >> 16) & 0xff), c2 = col + (int)(int8_t)(o >> 24);
-            const int va = brief_sample(S, pitch, H, W, r1, c1, &oob);
-            const int vb = brief_sample(S, pitch, H, W, r2, c2, &oob);
-            const unsigned word = __ballot_sync(0xffffffffu, va > vb);
-            if (lane == w) mine = word;
+            for (int w = 0; w < 8; w++) {
+                const unsigned word = __ballot_sync(0xffffffffu, Pb[ps[w] & 0xffff] > Pb[ps[w] >> 16]);
+                if (lane == w) mine = word;
+            }
+        } else {
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t o = __ldg(offs + 32 * w + lane);
+                const int r1 = row + (int)(int8_t)(o & 0xff), c1 = col + (int)(int8_t)((o >> 8) & 0xff);
+                const int r2 = row + (int)(int8_t)((o >> 16) & 0xff), c2 = col + (int)(int8_t)(o >> 24);
+                const int va = brief_sample(S, pitch, H, W, r1, c1, &oob);
+                const int vb = brief_sample(S, pitch, H, W, r2, c2, &oob);
+                const unsigned word = __ballot_sync(0xffffffffu, va > vb);
+                if (lane == w) mine = word;
+            }
+            if (n_oob) {
+                const unsigned any = __ballot_sync(0xffffffffu, oob);
+                if (lane == 0 && any) atomicAdd(n_oob, 1);
+                oob = false;
+            }
         }
-    }
-    if (lane < 8) d[lane] = mine;
-    if (n_oob) {
-        const unsigned any = __ballot_sync(0xffffffffu, oob);
-        if (lane == 0 && any) atomicAdd(n_oob, 1);
+        if (lane < 8) d[lane] = mine;
     }
 }
 
