@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
     if not (force or stale):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "yavo_capi.cu")]
+    extra = os.environ.get("YAVO_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DYAVO_SEL_SMEM_ENTS=4096
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_CSRC, "yavo_capi.cu")]
     subprocess.check_call(cmd, cwd=_CSRC)
     return LIB_PATH
 

@@ -326,7 +326,13 @@ compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, in
 // ================================================================================================
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
-constexpr int SEL_SMEM_ENTS = 8192;     // candidates kept in shared memory once the active prefix fits
+#ifndef YAVO_SEL_SMEM_ENTS
+#define YAVO_SEL_SMEM_ENTS 8192
+#endif
+#ifndef YAVO_SEL_MIN_CTAS
+#define YAVO_SEL_MIN_CTAS 2
+#endif
+constexpr int SEL_SMEM_ENTS = YAVO_SEL_SMEM_ENTS;  // candidates kept in shared memory once the active prefix fits
 constexpr int SEL_WARP_MAX = 512;       // ranges up to this size are partitioned by one warp
 constexpr int SEL_QCAP = 512;           // shared work queue (ring)
 constexpr int SEL_STACK = 32;           // per-warp overflow stack
@@ -631,7 +637,7 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
     return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
 }
 
-__global__ void __launch_bounds__(SEL_THREADS, 2)
+__global__ void __launch_bounds__(SEL_THREADS, YAVO_SEL_MIN_CTAS)
 select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch,
                    yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
                    uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride, int score_on_load,
