@@ -327,7 +327,7 @@ compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, in
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 #ifndef YAVO_SEL_SMEM_ENTS
-#define YAVO_SEL_SMEM_ENTS 8192
+#define YAVO_SEL_SMEM_ENTS 6144  // measured on B200: 6144 entries at 2 CTAs/SM beat 4096@3, 4096@2 and 8192@2 (leaves L1 for the scoring loads)
 #endif
 #ifndef YAVO_SEL_MIN_CTAS
 #define YAVO_SEL_MIN_CTAS 2
