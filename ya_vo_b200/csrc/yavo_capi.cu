@@ -675,10 +675,10 @@ static int match_device(yavo_ctx *ctx, const uint32_t *dq, int n1, const uint32_
     dim3 grid((n1 + MQ - 1) / MQ, chunks, 1);
     if (o_sec)  // second-best tracking only when the caller asked for it (ratio-test extension)
         PROF(KC_MATCH, match_partial_kernel<true><<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk,
-                                                                                 chunks, n1, ctx->d_part_key, ctx->d_part_sec));
+                                                                                 chunks, n1, ctx->d_part_key, ctx->d_part_sec, 1u << 22));
     else
         PROF(KC_MATCH, match_partial_kernel<false><<<grid, MQ, 0, ctx->stream>>>(dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, chunk,
-                                                                                  chunks, n1, ctx->d_part_key, ctx->d_part_sec));
+                                                                                  chunks, n1, ctx->d_part_key, ctx->d_part_sec, 1u << 22));
     CK_LAUNCH();
     PROF(KC_MATCH_REDUCE, match_reduce_kernel<<<dim3((n1 + 127) / 128, 1), 128, 0, ctx->stream>>>(
         ctx->d_part_key, ctx->d_part_sec, nullptr, n1, 0, nullptr, n2, 0, chunk, chunks, n1, o_idx, o_dist, o_sec));
@@ -781,7 +781,7 @@ static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool l
         dim3 grid((ctx->max_kp + MQ - 1) / MQ, chunks, pairs);
         PROF(KC_MATCH, match_partial_kernel<false><<<grid, MQ, 0, ctx->stream>>>(
             ctx->d_desc + mo * 8, ctx->d_nbk + m0, 0, ctx->d_desc + mo * 8, ctx->d_nbk + m0, 0,
-            (size_t)ctx->max_kp * 8, 0, 1, chunk, chunks, ctx->max_kp, ctx->d_part_key, ctx->d_part_sec));
+            (size_t)ctx->max_kp * 8, 0, 1, chunk, chunks, ctx->max_kp, ctx->d_part_key, ctx->d_part_sec, 1u << 22));
         CK_LAUNCH();
         PROF(KC_MATCH_REDUCE, match_reduce_kernel<<<dim3((ctx->max_kp + 127) / 128, pairs), 128, 0, ctx->stream>>>(
             ctx->d_part_key, ctx->d_part_sec, ctx->d_nbk + m0, 0, 0, ctx->d_nbk + m0, 0, 1, chunk, chunks,

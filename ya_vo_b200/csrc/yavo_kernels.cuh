@@ -947,7 +947,8 @@ match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict_
                      const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
                      size_t set_stride_words, int q_set_offset, int t_set_offset, int chunk,
                      int n_chunks, int out_stride, uint32_t *__restrict__ part_key,
-                     uint32_t *__restrict__ part_sec) {
+                     uint32_t *__restrict__ part_sec, uint32_t key_mul /* 1 << 22, passed at run time so that
+                     key = d * key_mul + j stays an IMAD on the FMA pipe instead of a LEA on the ALU */) {
     __shared__ uint4 st[MT][2];
     const int pair = blockIdx.z;
     const uint32_t *dq = dq_all + (size_t)(pair + q_set_offset) * set_stride_words;
@@ -971,11 +972,11 @@ match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict_
         for (int i = threadIdx.x; i < nt_tile * 2; i += MQ)
             st[i >> 1][i & 1] = __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)t0 * 8) + i);
         __syncthreads();
+        if (SECOND) {
 #pragma unroll 4
-        for (int j = 0; j < nt_tile; j++) {
-            const uint32_t d = hamming256(a0, a1, st[j][0], st[j][1]);
-            const uint32_t key = imad(d, 1u << 22, (uint32_t)(t0 + j));
-            if (SECOND) {
+            for (int j = 0; j < nt_tile; j++) {
+                const uint32_t d = hamming256(a0, a1, st[j][0], st[j][1]);
+                const uint32_t key = imad(d, key_mul, (uint32_t)(t0 + j));
                 // ascending j and strict '<' == min over key; sec = second smallest distance
                 if (key < best) {
                     sec = (best == MATCH_NONE) ? sec : (best >> 22);
@@ -983,8 +984,19 @@ match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict_
                 } else if (d < sec) {
                     sec = d;
                 }
-            } else {
-                best = min(best, key);
+            }
+        } else {
+            // two pairs per step: one 3-input minimum (VIMNMX3) per two keys, keys built by IMAD (FMA pipe)
+            const int even = nt_tile & ~1;
+#pragma unroll 2
+            for (int j = 0; j < even; j += 2) {
+                const uint32_t d0 = hamming256(a0, a1, st[j][0], st[j][1]);
+                const uint32_t d1 = hamming256(a0, a1, st[j + 1][0], st[j + 1][1]);
+                best = __vimin3_u32(best, imad(d0, key_mul, (uint32_t)(t0 + j)), imad(d1, key_mul, (uint32_t)(t0 + j + 1)));
+            }
+            if (even < nt_tile) {
+                const uint32_t d = hamming256(a0, a1, st[even][0], st[even][1]);
+                best = min(best, imad(d, key_mul, (uint32_t)(t0 + even)));
             }
         }
     }
