@@ -1,0 +1,16 @@
+"""Debug: per-phase cycle counts of the select kernel (build with YAVO_NVCC_EXTRA=-DYAVO_SEL_TIMING)."""
+import ctypes as C, sys
+import numpy as np
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
+from ya_vo_b200 import capi, synth
+frames = synth.synth_batch(64, sys.argv[1] if len(sys.argv) > 1 else "G30", 1000)
+with capi.Context(device=0, n_slots=64, max_rows=376, max_cols=1241, max_kp=2000) as ctx:
+    ctx.set_brief_offsets(synth.brief_offsets())
+    ctx.upload_batch(0, frames)
+    for n in (64, 1):
+        for _ in range(2):
+            ctx.frontend_batch(0, n, False)
+        out = np.zeros((64, 8), np.int64)
+        capi.lib().yavo_debug_select_timing(ctx._h, out.ctypes.data_as(C.c_void_p))
+        d = np.diff(out[:n, :6], axis=1)
+        print("frames in flight", n, "mean cycles per phase [load+score, phase1, switch, phase2, output]:", d.mean(axis=0).round(0), "total", d.sum(axis=1).mean().round(0))

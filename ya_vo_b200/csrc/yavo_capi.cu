@@ -971,6 +971,16 @@ int yavo_filter_pairs(yavo_ctx *ctx, int slot0, int n, int threshold, int32_t *n
     return 0;
 }
 
+#ifdef YAVO_SEL_TIMING
+// debug build only: phase timestamps (clock64) of the first 64 select CTAs of the last launch
+extern "C" int yavo_debug_select_timing(yavo_ctx *ctx, long long *out /* 64 x 8 */) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(out, ctx->d_scratch, sizeof(long long) * 64 * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+#endif
+
 int yavo_set_sub_batch(yavo_ctx *ctx, int frames) {
     if (!ctx || frames < 0) return YAVO_ERR_INVALID;
     ctx->sub_batch = frames;

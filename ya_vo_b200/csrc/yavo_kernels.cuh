@@ -652,6 +652,13 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
 
     const int f = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#ifdef YAVO_SEL_TIMING
+    long long tmark[6];
+    tmark[0] = clock64();
+#define SEL_MARK(i) do { __syncthreads(); tmark[i] = clock64(); } while (0)
+#else
+#define SEL_MARK(i) do { } while (0)
+#endif
     const int N = ncand[f];
     if (N > max_cand) {  // candidate buffer overflow: report, never return a silently truncated order
         if (tid == 0) { atomicExch(status, 1); nkp[f] = 0; nbk[f] = 0; }
@@ -692,6 +699,7 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     }
     __syncthreads();
 
+    SEL_MARK(1);
     // ---- phase 1: ranges larger than SEL_WARP_MAX, whole CTA, level by level -------------------------
     int cur = 0;
     while (S.nbig[cur] > 0) {
@@ -733,6 +741,7 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
         cur = nxt;
         __syncthreads();
     }
+    SEL_MARK(2);
     // move the active prefix into shared memory if it fits (phase 2 then never touches global memory)
     if (!in_smem) {
         int E = min(N, K);
@@ -747,12 +756,14 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     if (tid == 0) S.pending = S.q_tail;
     __syncthreads();
 
+    SEL_MARK(3);
     // ---- phase 2: warps drain the queue ------------------------------------------------------------------
     {
         SelRange t;
         while (sel_pop(S, t)) sel_warp_work(S, A, t, K);
     }
     __syncthreads();
+    SEL_MARK(4);
 
     // ---- outputs: first min(N,K) in order, plus the checkBoundry-compacted list -------------------
     const int nout = min(N, K);
@@ -793,6 +804,11 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
         __syncthreads();
     }
     if (tid == 0) { nkp[f] = nout; nbk[f] = run; }
+#ifdef YAVO_SEL_TIMING
+    SEL_MARK(5);
+    if (tid == 0 && f < 64)
+        for (int i = 0; i < 6; i++) reinterpret_cast<long long *>(scratch_all)[f * 8 + i] = tmark[i];
+#endif
 }
 
 // ================================================================================================
