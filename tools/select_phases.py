@@ -10,7 +10,10 @@ with capi.Context(device=0, n_slots=64, max_rows=376, max_cols=1241, max_kp=2000
     for n in (64, 1):
         for _ in range(2):
             ctx.frontend_batch(0, n, False)
-        out = np.zeros((64, 8), np.int64)
+        out = np.zeros(64 * 8 + 8 * 16 * 4, np.int64)
         capi.lib().yavo_debug_select_timing(ctx._h, out.ctypes.data_as(C.c_void_p))
+        w = out[64 * 8:].reshape(8, 16, 4)
+        out = out[:64 * 8].reshape(64, 8)
         d = np.diff(out[:n, :6], axis=1)
         print("frames in flight", n, "mean cycles per phase [load+score, phase1, switch, phase2, output]:", d.mean(axis=0).round(0), "total", d.sum(axis=1).mean().round(0))
+        print("   frame 0 per warp: pop-wait cycles", w[0, :, 0].tolist(), "work cycles", w[0, :, 1].tolist(), "tasks", w[0, :, 2].tolist())

@@ -976,7 +976,7 @@ int yavo_filter_pairs(yavo_ctx *ctx, int slot0, int n, int threshold, int32_t *n
 extern "C" int yavo_debug_select_timing(yavo_ctx *ctx, long long *out /* 64 x 8 */) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(out, ctx->d_scratch, sizeof(long long) * 64 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, ctx->d_scratch, sizeof(long long) * (64 * 8 + 8 * 16 * 4), cudaMemcpyDeviceToHost));
     return 0;
 }
 #endif

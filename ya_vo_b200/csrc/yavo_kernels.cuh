@@ -335,7 +335,8 @@ constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_SMEM_ENTS = YAVO_SEL_SMEM_ENTS;  // candidates kept in shared memory once the active prefix fits
 constexpr int SEL_WARP_MAX = 512;       // ranges up to this size are partitioned by one warp
 constexpr int SEL_QCAP = 512;           // shared work queue (ring)
-constexpr int SEL_STACK = 32;           // per-warp overflow stack
+constexpr int SEL_STACK = 48;           // per-warp private stack
+constexpr int SEL_LOCAL = 64;           // right children up to this size stay with the warp that produced them
 constexpr int SEL_BIG = 64;             // per-level list of CTA-partitioned ranges
 
 struct SelRange {
@@ -509,9 +510,25 @@ __device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *Lpos = S.wscratch[warp][0], *Rpos = S.wscratch[warp][1];
     const int n = l - f;
-    if (lane == 0) yavo_median_to_first(A, f, l);
-    __syncwarp();
-    const yavo_ent piv = A[f];
+    // __move_median_to_first(first, first+1, mid, last-1): lanes 0..3 fetch first / a / b / c in parallel
+    yavo_ent piv;
+    {
+        const int mid = f + n / 2;
+        const int pos = lane == 0 ? f : (lane == 1 ? f + 1 : (lane == 2 ? mid : l - 1));
+        const yavo_ent v = lane < 4 ? A[pos] : 0ull;
+        const yavo_ent v0 = __shfl_sync(0xffffffffu, v, 0), va = __shfl_sync(0xffffffffu, v, 1);
+        const yavo_ent vb = __shfl_sync(0xffffffffu, v, 2), vc = __shfl_sync(0xffffffffu, v, 3);
+        int m;  // which of a (1), b (2), c (3) is the median, by libstdc++'s comparison sequence
+        if (yavo_before(va, vb)) m = yavo_before(vb, vc) ? 2 : (yavo_before(va, vc) ? 3 : 1);
+        else m = yavo_before(va, vc) ? 1 : (yavo_before(vb, vc) ? 3 : 2);
+        piv = m == 1 ? va : (m == 2 ? vb : vc);
+        const int mpos = m == 1 ? f + 1 : (m == 2 ? mid : l - 1);
+        if (lane == 0) {
+            A[f] = piv;
+            A[mpos] = v0;
+        }
+        __syncwarp();
+    }
     const int cap = n / 2 + 1;
     int runL = 0, runR = 0;
     for (int base = 0; base < n - 1; base += 32) {
@@ -530,21 +547,28 @@ __device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
     __syncwarp();
     const int nL = min(runL, cap), nR = min(runR, cap);
     const int npairs = min(nL, nR);
-    int cnt = 0;
-    for (int i = lane; i < npairs; i += 32) {
-        const int a = Lpos[i], b = Rpos[i];
-        if (a < b) {
+    int m = 0;  // number of swaps: the pairs with L_i < R_i form a prefix
+    for (int i0 = 0; i0 < npairs; i0 += 32) {
+        const int i = i0 + lane;
+        bool ok = false;
+        int a = 0, b = 0;
+        if (i < npairs) {
+            a = Lpos[i];
+            b = Rpos[i];
+            ok = a < b;
+        }
+        if (ok) {
             const yavo_ent t = A[f + a];
             A[f + a] = A[f + b];
             A[f + b] = t;
-            cnt++;
         }
+        const unsigned bo = __ballot_sync(0xffffffffu, ok);
+        m += __popc(bo);
+        if (bo != 0xffffffffu) break;
     }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     int cut = 0x7fffffff;
-    if (cnt < nL) cut = Lpos[cnt];
-    if (cnt >= 1) cut = min(cut, (int)Rpos[cnt - 1]);
+    if (m < nL) cut = Lpos[m];
+    if (m >= 1) cut = min(cut, (int)Rpos[m - 1]);
     __syncwarp();
     return f + cut;
 }
@@ -568,9 +592,12 @@ __device__ __forceinline__ void sel_warp_leaf(yavo_ent *A, int f, int l) {
 // phase 2: one warp works a range down to its leaves, handing right children to the queue
 __device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int sp = 0;  // private overflow stack (only used when the ring is full)
+    // Right children of at most SEL_LOCAL elements stay on this warp's private stack: no queue traffic, no
+    // atomics — most partitions are of small ranges.  Larger ones go to the shared queue so idle warps can take
+    // them.  S.pending counts queue-level tasks only: this warp's task ends when its private stack is empty.
+    int sp = 0;
     for (;;) {
-        // cur is counted in S.pending and satisfies cur.f < K, cur.l - cur.f > 1
+        // cur satisfies cur.f < K, cur.l - cur.f > 1
         const int n = cur.l - cur.f;
         bool finished = false;
         if (n <= YAVO_SORT_THRESHOLD) {
@@ -580,52 +607,58 @@ __device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
             if (lane == 0) yavo_serial_heapsort(A, cur.f, cur.l);  // libstdc++'s depth-limit fallback
             __syncwarp();
             finished = true;
+        } else if (n > SEL_WARP_MAX) {  // cannot happen: phase 1 leaves only ranges <= SEL_WARP_MAX; stay exact anyway
+            if (lane == 0) yavo_serial_introsort(A, cur.f, cur.l, cur.d, K);
+            __syncwarp();
+            finished = true;
         } else {
-            const int cut = (n <= SEL_WARP_MAX) ? sel_warp_partition(S, A, cur.f, cur.l) : -1;
-            if (cut < 0) {  // cannot happen: phase 1 leaves only ranges <= SEL_WARP_MAX; stay exact anyway
-                if (lane == 0) yavo_serial_introsort(A, cur.f, cur.l, cur.d, K);
-                __syncwarp();
-                finished = true;
-            } else {
-                const SelRange left = {cur.f, cut, cur.d - 1}, right = {cut, cur.l, cur.d - 1};
-                const bool vL = cut - cur.f > 1;               // left starts at cur.f < K
-                const bool vR = cut < K && cur.l - cut > 1;
-                if (vL && vR) {
+            const int cut = sel_warp_partition(S, A, cur.f, cur.l);
+            const SelRange left = {cur.f, cut, cur.d - 1}, right = {cut, cur.l, cur.d - 1};
+            const bool vL = cut - cur.f > 1;               // left starts at cur.f < K
+            const bool vR = cut < K && cur.l - cut > 1;
+            if (vL && vR) {
+                bool stacked = false;
+                if (right.l - right.f <= SEL_LOCAL && sp < SEL_STACK) {
+                    stacked = true;
+                } else {
                     int pushed = 0;
                     if (lane == 0) {
                         atomicAdd(&S.pending, 1);
                         pushed = sel_push(S, right) ? 1 : 0;
+                        if (!pushed) atomicSub(&S.pending, 1);
                     }
                     pushed = __shfl_sync(0xffffffffu, pushed, 0);
                     if (!pushed) {
                         if (sp < SEL_STACK) {
-                            if (lane == 0) S.stack[warp][sp] = right;
-                            sp++;
-                            __syncwarp();
-                        } else {  // both full: finish the child serially (exact, slow, practically unreachable)
-                            if (lane == 0) {
-                                yavo_serial_introsort(A, right.f, right.l, right.d, K);
-                                atomicSub(&S.pending, 1);
-                            }
+                            stacked = true;
+                        } else {  // queue and stack full: finish the child serially (exact, practically unreachable)
+                            if (lane == 0) yavo_serial_introsort(A, right.f, right.l, right.d, K);
                             __syncwarp();
                         }
                     }
-                    cur = left;
-                } else if (vL) {
-                    cur = left;
-                } else if (vR) {
-                    cur = right;
-                } else {
-                    finished = true;
                 }
+                if (stacked) {
+                    if (lane == 0) S.stack[warp][sp] = right;
+                    sp++;
+                    __syncwarp();
+                }
+                cur = left;
+            } else if (vL) {
+                cur = left;
+            } else if (vR) {
+                cur = right;
+            } else {
+                finished = true;
             }
         }
         if (finished) {
-            if (lane == 0) {
-                __threadfence_block();
-                atomicSub(&S.pending, 1);
+            if (sp == 0) {
+                if (lane == 0) {
+                    __threadfence_block();
+                    atomicSub(&S.pending, 1);
+                }
+                return;
             }
-            if (sp == 0) return;
             sp--;
             cur = S.stack[warp][sp];
         }
@@ -760,7 +793,25 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     // ---- phase 2: warps drain the queue ------------------------------------------------------------------
     {
         SelRange t;
+#ifdef YAVO_SEL_TIMING
+        long long t_pop = 0, t_work = 0, n_task = 0, c0 = clock64();
+        for (;;) {
+            const bool got = sel_pop(S, t);
+            const long long c1 = clock64();
+            t_pop += c1 - c0;
+            if (!got) break;
+            sel_warp_work(S, A, t, K);
+            c0 = clock64();
+            t_work += c0 - c1;
+            n_task++;
+        }
+        if (lane == 0 && f < 8) {
+            long long *dbg = reinterpret_cast<long long *>(scratch_all) + 64 * 8 + (f * SEL_WARPS + warp) * 4;
+            dbg[0] = t_pop; dbg[1] = t_work; dbg[2] = n_task; dbg[3] = 0;
+        }
+#else
         while (sel_pop(S, t)) sel_warp_work(S, A, t, K);
+#endif
     }
     __syncthreads();
     SEL_MARK(4);
