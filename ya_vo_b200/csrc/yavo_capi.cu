@@ -977,6 +977,11 @@ extern "C" int yavo_debug_select_timing(yavo_ctx *ctx, long long *out /* 64 x 8 
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaMemcpy(out, ctx->d_scratch, sizeof(long long) * (64 * 8 + 8 * 16 * 4), cudaMemcpyDeviceToHost));
+    long long dbg[8], zero[8] = {0};
+    CK(cudaMemcpyFromSymbol(dbg, yavo::g_sel_dbg, sizeof dbg));
+    CK(cudaMemcpyToSymbol(yavo::g_sel_dbg, zero, sizeof zero));
+    fprintf(stderr, "select dbg (CTA 0, all launches since last call): partition cycles %lld count %lld elems %lld | leaf cycles %lld count %lld\n",
+            dbg[0], dbg[1], dbg[4], dbg[2], dbg[3]);
     return 0;
 }
 #endif

@@ -324,7 +324,13 @@ compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, in
 // scratch list; the swaps are independent.  The depth-limit fallback (heapsort) is replayed by a
 // single lane (never reached on real score lists; kept for exactness).
 // ================================================================================================
-constexpr int SEL_THREADS = 512;
+#ifndef YAVO_SEL_THREADS
+#define YAVO_SEL_THREADS 512
+#endif
+#ifndef YAVO_SEL_SLEEP
+#define YAVO_SEL_SLEEP 64
+#endif
+constexpr int SEL_THREADS = YAVO_SEL_THREADS;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 #ifndef YAVO_SEL_SMEM_ENTS
 #define YAVO_SEL_SMEM_ENTS 6144  // measured on B200: 6144 entries at 2 CTAs/SM beat 4096@3, 4096@2 and 8192@2 (leaves L1 for the scoring loads)
@@ -382,7 +388,7 @@ __device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
                 continue;
             }
             if (*(volatile int *)&S.pending <= 0) break;
-            __nanosleep(64);
+            __nanosleep(YAVO_SEL_SLEEP);
         }
         if (got >= 0) {
             while (*(volatile int *)&S.ready[got % SEL_QCAP] != got + 1) {
@@ -590,6 +596,13 @@ __device__ __forceinline__ void sel_warp_leaf(yavo_ent *A, int f, int l) {
 }
 
 // phase 2: one warp works a range down to its leaves, handing right children to the queue
+#ifdef YAVO_SEL_TIMING
+__device__ long long g_sel_dbg[8];  // [0] partition cycles [1] partitions [2] leaf cycles [3] leaves [4] elements partitioned
+#define SEL_DBG_ADD(i, v) do { if ((threadIdx.x & 31) == 0 && blockIdx.x == 0) atomicAdd((unsigned long long *)&g_sel_dbg[i], (unsigned long long)(v)); } while (0)
+#else
+#define SEL_DBG_ADD(i, v) do { } while (0)
+#endif
+
 __device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Right children of at most SEL_LOCAL elements stay on this warp's private stack: no queue traffic, no
@@ -601,7 +614,14 @@ __device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
         const int n = cur.l - cur.f;
         bool finished = false;
         if (n <= YAVO_SORT_THRESHOLD) {
+#ifdef YAVO_SEL_TIMING
+            const long long c0 = clock64();
+#endif
             sel_warp_leaf(A, cur.f, cur.l);
+#ifdef YAVO_SEL_TIMING
+            SEL_DBG_ADD(2, clock64() - c0);
+            SEL_DBG_ADD(3, 1);
+#endif
             finished = true;
         } else if (cur.d == 0) {
             if (lane == 0) yavo_serial_heapsort(A, cur.f, cur.l);  // libstdc++'s depth-limit fallback
@@ -612,7 +632,15 @@ __device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
             __syncwarp();
             finished = true;
         } else {
+#ifdef YAVO_SEL_TIMING
+            const long long c0 = clock64();
+#endif
             const int cut = sel_warp_partition(S, A, cur.f, cur.l);
+#ifdef YAVO_SEL_TIMING
+            SEL_DBG_ADD(0, clock64() - c0);
+            SEL_DBG_ADD(1, 1);
+            SEL_DBG_ADD(4, n);
+#endif
             const SelRange left = {cur.f, cut, cur.d - 1}, right = {cut, cur.l, cur.d - 1};
             const bool vL = cut - cur.f > 1;               // left starts at cur.f < K
             const bool vR = cut < K && cur.l - cut > 1;
