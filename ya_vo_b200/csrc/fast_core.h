@@ -133,6 +133,19 @@ YAVO_HD uint32_t yavo_fast4(const WP rm3, const WP rm2, const WP rm1, const WP r
     return (((r >> 7) & 0x01010101u) * 0x01020408u) >> 24;
 }
 
+// The four ring positions every 12-window needs besides D0 (0, 4, 7, 8): a cheap necessary condition.  The
+// detect kernel runs it for every quad and the full test only for the quads that survive it.
+template <typename WP>
+YAVO_HD uint32_t yavo_fast4_core(const WP r0, const WP rp1, const WP rp3) {
+    const uint32_t c4 = r0[0];
+    const uint32_t a0 = r0[-1], a1 = r0[1];
+    const uint32_t d0 = yavo_differs4(c4, yavo_shift_bytes<-3>(a0, c4, a1));
+    const uint32_t d8 = yavo_differs4(c4, yavo_shift_bytes<3>(a0, c4, a1));
+    const uint32_t d7 = yavo_differs4(c4, yavo_shift_bytes<3>(rp1[-1], rp1[0], rp1[1]));
+    const uint32_t d4 = yavo_differs4(c4, rp3[0]);
+    return d0 & d7 & d4 & d8;
+}
+
 // scalar form of the same test (one pixel, ring values in ring order) — used for checks
 YAVO_HD bool yavo_fast1(int c, const int ring[16]) {
     uint32_t d = 0;

@@ -157,23 +157,44 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     }
 
     if (DO_FAST) {
-        // segment test: warp -> tile row, lane -> quad; 8 lanes assemble one 32-pixel mask word
-        uint32_t colmask = 0;  // interior columns only: 4 <= col < W-4
+        // Segment test, warp -> 4 tile rows, lane -> quad (4 pixels).  Pass A runs the cheap necessary
+        // condition (ring 0, 4, 7, 8 all differ) on every quad and packs the survivors' addresses into a
+        // per-warp list; pass B runs the full 16-position test only on the survivors, densely packed 32 to a
+        // warp step (on real frames a few percent of the quads); pass C assembles the 32-pixel mask words.
+        constexpr int NW = K1_THREADS / 32, RPW = TH / NW;
+        __shared__ uint8_t fnib[NW][RPW][32];
+        __shared__ uint8_t flist[NW][RPW * 32];
+        const unsigned lt = (1u << lane) - 1u;
+        int cnt = 0;
 #pragma unroll
-        for (int b = 0; b < 4; b++)
-            if (x0 + 4 * lane + b >= 4 && x0 + 4 * lane + b < W - 4) colmask |= 1u << b;
-        for (int tr = warp; tr < TH; tr += K1_THREADS / 32) {
-            const int gr = y0 + tr;
-            uint32_t nib = 0;
-            if (gr >= 4 && gr < H - 4) {  // warp-uniform
-                const int sr = tr + HALO;
-                bool pre;
-                nib = yavo_fast4(&tile[sr - 3][lane + SPX], &tile[sr - 2][lane + SPX], &tile[sr - 1][lane + SPX],
-                                 &tile[sr][lane + SPX], &tile[sr + 1][lane + SPX], &tile[sr + 2][lane + SPX],
-                                 &tile[sr + 3][lane + SPX], &pre);
-                nib &= colmask;
-            }
-            uint32_t v = nib << (4 * (lane & 7));
+        for (int k = 0; k < RPW; k++) {
+            const int tr = warp + NW * k, gr = y0 + tr, sr = tr + HALO;
+            bool live = false;
+            if (gr >= 4 && gr < H - 4)  // warp-uniform
+                live = yavo_fast4_core(&tile[sr][lane + SPX], &tile[sr + 1][lane + SPX], &tile[sr + 3][lane + SPX]) != 0;
+            fnib[warp][k][lane] = 0;
+            const unsigned bl = __ballot_sync(0xffffffffu, live);
+            if (live) flist[warp][cnt + __popc(bl & lt)] = (uint8_t)(k * 32 + lane);
+            cnt += __popc(bl);
+        }
+        __syncwarp();
+        for (int i = lane; i < cnt; i += 32) {
+            const int e = flist[warp][i], k = e >> 5, q = e & 31;
+            const int sr = warp + NW * k + HALO;
+            bool pre;
+            uint32_t nib = yavo_fast4(&tile[sr - 3][q + SPX], &tile[sr - 2][q + SPX], &tile[sr - 1][q + SPX],
+                                      &tile[sr][q + SPX], &tile[sr + 1][q + SPX], &tile[sr + 2][q + SPX],
+                                      &tile[sr + 3][q + SPX], &pre);
+#pragma unroll
+            for (int bb = 0; bb < 4; bb++)  // interior columns only: 4 <= col < W-4
+                if (x0 + 4 * q + bb < 4 || x0 + 4 * q + bb >= W - 4) nib &= ~(1u << bb);
+            fnib[warp][k][q] = (uint8_t)nib;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < RPW; k++) {
+            const int tr = warp + NW * k, gr = y0 + tr;
+            uint32_t v = (uint32_t)fnib[warp][k][lane] << (4 * (lane & 7));
             v |= __shfl_xor_sync(0xffffffffu, v, 1);
             v |= __shfl_xor_sync(0xffffffffu, v, 2);
             v |= __shfl_xor_sync(0xffffffffu, v, 4);
