@@ -162,7 +162,7 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
         // per-warp list; pass B runs the full 16-position test only on the survivors, densely packed 32 to a
         // warp step (on real frames a few percent of the quads); pass C assembles the 32-pixel mask words.
         constexpr int NW = K1_THREADS / 32, RPW = TH / NW;
-        __shared__ uint8_t fnib[NW][RPW][32];
+        __shared__ __align__(8) uint8_t fnib[NW][RPW][32];
         __shared__ uint8_t flist[NW][RPW * 32];
         const unsigned lt = (1u << lane) - 1u;
         int cnt = 0;
@@ -191,22 +191,20 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
             fnib[warp][k][q] = (uint8_t)nib;
         }
         __syncwarp();
-#pragma unroll
-        for (int k = 0; k < RPW; k++) {
-            const int tr = warp + NW * k, gr = y0 + tr;
-            uint32_t v = (uint32_t)fnib[warp][k][lane] << (4 * (lane & 7));
-            v |= __shfl_xor_sync(0xffffffffu, v, 1);
-            v |= __shfl_xor_sync(0xffffffffu, v, 2);
-            v |= __shfl_xor_sync(0xffffffffu, v, 4);
-            if (gr < H) {
-                if ((lane & 7) == 0)
-                    mask[((size_t)f * rows_alloc + gr) * mask_words + (x0 >> 5) + (lane >> 3)] = v;
-                // row total for this tile: lanes 0,8,16,24 hold the four words
-                int c = ((lane & 7) == 0) ? __popc(v) : 0;
-                c += __shfl_xor_sync(0xffffffffu, c, 8);
-                c += __shfl_xor_sync(0xffffffffu, c, 16);
-                if (lane == 0 && c) atomicAdd(&rowcnt[(size_t)f * rows_alloc + gr], c);
-            }
+        // pass C: lane l < 4*RPW packs the eight nibbles of mask word (row l/4, word l%4) in one go
+        if (lane < 4 * RPW) {
+            const int k = lane >> 2, w = lane & 3;
+            const int gr = y0 + warp + NW * k;
+            const uint2 nb = *reinterpret_cast<const uint2 *>(&fnib[warp][k][8 * w]);  // 8 bytes, low nibble used
+            // [n0,n1,n2,n3] -> n0 | n1<<4 in byte 0, n2 | n3<<4 in byte 2; then gather the four packed bytes
+            const uint32_t lo = (nb.x & 0x000f000fu) | ((nb.x & 0x0f000f00u) >> 4);
+            const uint32_t hi = (nb.y & 0x000f000fu) | ((nb.y & 0x0f000f00u) >> 4);
+            const uint32_t v = __byte_perm(lo, hi, 0x6420);
+            int c = __popc(v);
+            if (gr < H) mask[((size_t)f * rows_alloc + gr) * mask_words + (x0 >> 5) + w] = v;
+            c += __shfl_xor_sync((1u << (4 * RPW)) - 1u, c, 1);
+            c += __shfl_xor_sync((1u << (4 * RPW)) - 1u, c, 2);
+            if (w == 0 && c && gr < H) atomicAdd(&rowcnt[(size_t)f * rows_alloc + gr], c);
         }
     }
 
