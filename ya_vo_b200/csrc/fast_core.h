@@ -273,24 +273,33 @@ YAVO_HD void yavo_blur_h4(uint32_t wm, uint32_t w0, uint32_t wp, uint32_t out[4]
 // from five vertical pairs P[i] = (h[r-4+2i] | h[r-3+2i] << 16):
 //   out(r)   = g0 h[r-4] + g1 h[r-3] + ... + g8 h[r+4]
 //   out(r+1) = g0 h[r-3] + ... + g8 h[r+5]
-YAVO_HD void yavo_blur_v2(const uint32_t P[5], uint32_t *o0, uint32_t *o1) {
+// raw form: the two fixed-point sums with the rounding constant already added; the blurred pixels are
+// bits 16..23 of each (sum < 2^24), which the kernel extracts with byte permutes while packing four outputs
+YAVO_HD void yavo_blur_v2_raw(const uint32_t P[5], uint32_t *ra, uint32_t *rb) {
     const uint32_t wA = YAVO_PK(YAVO_G0, YAVO_G1, YAVO_G2, YAVO_G3);  // lo: g0,g1  hi: g2,g3
     const uint32_t wB = YAVO_PK(YAVO_G4, YAVO_G3, YAVO_G2, YAVO_G1);  // lo: g4,g5  hi: g6,g7
     const uint32_t wC = YAVO_PK(YAVO_G0, 0u, 0u, YAVO_G0);            // lo: g8,0   hi: 0,g0
     const uint32_t wD = YAVO_PK(YAVO_G1, YAVO_G2, YAVO_G3, YAVO_G4);  // lo: g1,g2  hi: g3,g4
     const uint32_t wE = YAVO_PK(YAVO_G3, YAVO_G2, YAVO_G1, YAVO_G0);  // lo: g5,g6  hi: g7,g8
-    uint32_t a = yavo_dp2a_lo(P[0], wA, 0u);
+    uint32_t a = yavo_dp2a_lo(P[0], wA, 32768u);
     a = yavo_dp2a_hi(P[1], wA, a);
     a = yavo_dp2a_lo(P[2], wB, a);
     a = yavo_dp2a_hi(P[3], wB, a);
     a = yavo_dp2a_lo(P[4], wC, a);
-    uint32_t b = yavo_dp2a_hi(P[0], wC, 0u);
+    uint32_t b = yavo_dp2a_hi(P[0], wC, 32768u);
     b = yavo_dp2a_lo(P[1], wD, b);
     b = yavo_dp2a_hi(P[2], wD, b);
     b = yavo_dp2a_lo(P[3], wE, b);
     b = yavo_dp2a_hi(P[4], wE, b);
-    *o0 = (a + 32768u) >> 16;
-    *o1 = (b + 32768u) >> 16;
+    *ra = a;
+    *rb = b;
+}
+
+YAVO_HD void yavo_blur_v2(const uint32_t P[5], uint32_t *o0, uint32_t *o1) {
+    uint32_t a, b;
+    yavo_blur_v2_raw(P, &a, &b);
+    *o0 = a >> 16;
+    *o1 = b >> 16;
 }
 
 #endif  // YAVO_FAST_CORE_H

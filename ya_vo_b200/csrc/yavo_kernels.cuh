@@ -217,30 +217,33 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
             uint4 p[5];
 #pragma unroll
             for (int k = 0; k < 5; k++) p[k] = hpair[j + k][q];
-            uint32_t o0[4], o1[4];
+            uint32_t o0[4], o1[4];  // rounded fixed-point sums: the output pixel is byte 2 of each
             {
                 const uint32_t P[5] = {p[0].x, p[1].x, p[2].x, p[3].x, p[4].x};
-                yavo_blur_v2(P, &o0[0], &o1[0]);
+                yavo_blur_v2_raw(P, &o0[0], &o1[0]);
             }
             {
                 const uint32_t P[5] = {p[0].y, p[1].y, p[2].y, p[3].y, p[4].y};
-                yavo_blur_v2(P, &o0[1], &o1[1]);
+                yavo_blur_v2_raw(P, &o0[1], &o1[1]);
             }
             {
                 const uint32_t P[5] = {p[0].z, p[1].z, p[2].z, p[3].z, p[4].z};
-                yavo_blur_v2(P, &o0[2], &o1[2]);
+                yavo_blur_v2_raw(P, &o0[2], &o1[2]);
             }
             {
                 const uint32_t P[5] = {p[0].w, p[1].w, p[2].w, p[3].w, p[4].w};
-                yavo_blur_v2(P, &o0[3], &o1[3]);
+                yavo_blur_v2_raw(P, &o0[3], &o1[3]);
             }
+            // byte 2 of four sums -> one word: two 2-way gathers, then interleave
+            const uint32_t w0 = __byte_perm(__byte_perm(o0[0], o0[1], 0x0062), __byte_perm(o0[2], o0[3], 0x0062), 0x5410);
+            const uint32_t w1 = __byte_perm(__byte_perm(o1[0], o1[1], 0x0062), __byte_perm(o1[2], o1[3], 0x0062), 0x5410);
             const int gr = y0 + 2 * j, gc = x0 + 4 * q;
             if (gc < pitch) {
                 uint8_t *dst = blur + (size_t)f * frame_stride + (size_t)gr * pitch + gc;
                 if (gr < H)
-                    *reinterpret_cast<uint32_t *>(dst) = o0[0] | (o0[1] << 8) | (o0[2] << 16) | (o0[3] << 24);
+                    *reinterpret_cast<uint32_t *>(dst) = w0;
                 if (gr + 1 < H)
-                    *reinterpret_cast<uint32_t *>(dst + pitch) = o1[0] | (o1[1] << 8) | (o1[2] << 16) | (o1[3] << 24);
+                    *reinterpret_cast<uint32_t *>(dst + pitch) = w1;
             }
         }
     }
