@@ -54,6 +54,26 @@ void emul_fast_mask(const uint8_t *img, int H, int W, uint8_t *out) {
         }
 }
 
+// the cheap necessary condition the detect kernel runs first: returns the number of pixels where the full test
+// fires but the necessary condition does not (must be 0), and counts the quads each one lets through
+int emul_fast_core_violations(const uint8_t *img, int H, int W, long long *core_quads, long long *full_quads) {
+    Padded P(img, H, W);
+    int bad = 0;
+    *core_quads = *full_quads = 0;
+    for (int r = 4; r < H - 4; r++)
+        for (int x = 0; x < W; x += 4) {
+            bool pre;
+            const uint32_t nib = yavo_fast4(P.word(r - 3, x), P.word(r - 2, x), P.word(r - 1, x), P.word(r, x),
+                                            P.word(r + 1, x), P.word(r + 2, x), P.word(r + 3, x), &pre);
+            const uint32_t core = yavo_fast4_core(P.word(r, x), P.word(r + 1, x), P.word(r + 3, x));
+            const uint32_t cn = (((core >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+            if (nib & ~cn) bad++;
+            *core_quads += core != 0;
+            *full_quads += nib != 0;
+        }
+    return bad;
+}
+
 float emul_harris(const uint8_t *img, int W, int row, int col) {
     int a, b, c;
     yavo_structure_tensor([&](int r, int cc) { return (int)img[(size_t)r * W + cc]; }, row, col, &a, &b, &c);

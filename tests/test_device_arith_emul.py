@@ -81,3 +81,15 @@ def test_select_model_equals_std_sort(emul, oracle):
             s3, p3 = s.copy(), pay.copy()
             emul.emul_serial_sort(p(s3), p(p3), n, 1 << 30, depth)
             assert np.array_equal(o_p, p3), (t, n, depth)
+
+
+def test_necessary_condition_never_drops_a_corner(emul, kitti):
+    """yavo_fast4_core (ring 0,4,7,8) must hold wherever the full segment test fires: the detect kernel only runs
+    the full test on quads that pass it."""
+    for img in (kitti, synth.synth_frame("U", 0), synth.synth_frame("G30", 1), synth.synth_frame("B4", 2)):
+        H, W = img.shape
+        core = C.c_longlong()
+        full = C.c_longlong()
+        bad = emul.emul_fast_core_violations(p(img), H, W, C.byref(core), C.byref(full))
+        assert bad == 0
+        assert full.value <= core.value

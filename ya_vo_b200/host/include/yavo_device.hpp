@@ -32,6 +32,8 @@ class Device {
     // slot holding img's current pixels; uploads them if the slot table has no (id, checksum) match
     int slotFor(const Image &img);
     void check(int rc) const;  // throws DeviceError with yavo_last_error on rc < 0
+    // passes the 256 x 4 BRIEF table to the device unless it is the one already there
+    void setBriefOffsets(const int32_t *table1024);
     std::mutex &mutex() { return mu_; }
 
     static const int kSlots = 4;
@@ -48,6 +50,7 @@ class Device {
     int maxRows_ = 0, maxCols_ = 0;
     std::vector<Slot> slots_;
     uint64_t clock_ = 0;
+    std::vector<int32_t> offsets_;  // table currently on the device
     std::mutex mu_;
 };
 

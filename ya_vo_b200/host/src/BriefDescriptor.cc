@@ -36,7 +36,7 @@ void Brief::computeBrief(const std::vector<cv::Point> &detectedCornerPoints, Ima
     int32_t table[1024];
     for (int j = 0; j < 256; j++)
         for (int k = 0; k < 4; k++) table[4 * j + k] = offsets[j][k];
-    dev.check(yavo_set_brief_offsets(dev.ctx(), table));
+    dev.setBriefOffsets(table);
     std::vector<int32_t> rows(n), cols(n);
     for (int i = 0; i < n; i++) {
         rows[i] = detectedCornerPoints[i].x;

@@ -39,6 +39,12 @@ void Device::check(int rc) const {
     if (rc < 0) throw DeviceError(std::string("yavo: ") + yavo_last_error(ctx_));
 }
 
+void Device::setBriefOffsets(const int32_t *table1024) {
+    if (offsets_.size() == 1024 && std::equal(offsets_.begin(), offsets_.end(), table1024)) return;
+    check(yavo_set_brief_offsets(ctx_, table1024));
+    offsets_.assign(table1024, table1024 + 1024);
+}
+
 int Device::slotFor(const Image &img) {
     const uint64_t id = img.yavoId(), sum = img.yavoChecksum();
     int victim = 0;
