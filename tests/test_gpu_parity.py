@@ -278,3 +278,31 @@ def test_argument_errors_are_reported(cuda_lib, offsets):
         assert d.shape == (0, 32)
     with pytest.raises(cuda_lib.YavoError):
         cuda_lib.Context(device=99)
+
+
+def test_randomised_frames_against_oracle(cuda_lib, oracle, offsets):
+    """40 random shapes / contents (noise, blocky ties, gradients with planted corners): candidates, order, scores,
+    descriptors — all through one context, so stale slot state would show."""
+    rng = np.random.default_rng(2024)
+    with cuda_lib.Context(device=0, n_slots=2, max_rows=300, max_cols=700, max_kp=300) as c:
+        c.set_brief_offsets(offsets)
+        for t in range(40):
+            H, W = int(rng.integers(10, 301)), int(rng.integers(10, 701))
+            kind = ("U", "G30", "B4")[t % 3]
+            img = synth.synth_frame(kind, 5000 + t, H, W)
+            if t % 5 == 0:  # smooth ramp with a few bright squares: few, strong corners
+                yy, xx = np.mgrid[0:H, 0:W]
+                img = ((yy + xx) % 200).astype(np.uint8)
+                for _ in range(6):
+                    r0, c0 = int(rng.integers(0, max(1, H - 12))), int(rng.integers(0, max(1, W - 12)))
+                    img[r0:r0 + 9, c0:c0 + 9] = 255
+            slot = t & 1
+            c.upload(slot, img)
+            r, cc, s, nc = c.fast_detect(slot)
+            er, ec, es, enc = oracle.fast_detect(img, 300)
+            assert nc == enc, (t, H, W, kind)
+            assert np.array_equal(r, er) and np.array_equal(cc, ec), (t, H, W, kind)
+            assert np.array_equal(s.view(np.uint32), es.view(np.uint32)), (t, H, W, kind)
+            d, v, oob = c.brief_describe(slot, r, cc)
+            ed, ev, eoob = oracle.brief(img, offsets, er, ec)
+            assert np.array_equal(v, ev) and np.array_equal(d, ed) and oob == eoob, (t, H, W, kind)
