@@ -914,8 +914,9 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
 
 // ================================================================================================
 // K4  BRIEF  (reference src/BriefDescriptor.cc:86-124)
-// One warp per keypoint.  Lane l evaluates tests l, l+32, ..., l+224 on the smoothed plane; a
-// ballot per group of 32 tests yields descriptor word w directly (bit j of the descriptor is bit
+// A warp handles BP_KPW keypoints one after the other; for each it stages the 17 x 17 smoothed neighbourhood
+// in shared memory, lane l evaluates tests l, l+32, ..., l+224 and a ballot per group of 32 tests yields
+// descriptor word w directly (bit j of the descriptor is bit
 // j%32 of word j/32, i.e. byte j/8 bit j%8 little-endian — the reference layout).
 // Reads follow Image::getPixelVal's unchecked linear indexing (src/Image.cc:15-17): a column index
 // equal to W wraps to column 0 of the next row; a linear index >= H*W (undefined behaviour in the
