@@ -291,6 +291,10 @@ int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
 int check_status(yavo_ctx *ctx) {
     CK(cudaMemcpyAsync(ctx->h_small, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_small[0] == 2) {
+        CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+        return fail(ctx, YAVO_ERR_CUDA, "select kernel watchdog fired (work queue did not drain); results are invalid");
+    }
     if (ctx->h_small[0] != 0) {
         CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
         return fail(ctx, YAVO_ERR_CAPACITY,

@@ -379,7 +379,7 @@ struct SelShared {
     uint16_t bscratch[2][SEL_SMEM_ENTS / 2 + 2];  // CTA-partition stopper lists while the data is in smem
     SelRange big[2][SEL_BIG];
     int nbig[2];
-    int q_head, q_tail, pending;
+    int q_head, q_tail, pending, watchdog;
     int wtot[SEL_WARPS];
     int bcast[4];
 };
@@ -400,6 +400,7 @@ __device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
     const int lane = threadIdx.x & 31;
     int got = -1;
     if (lane == 0) {
+        int spins = 0;
         for (;;) {
             const int h = *(volatile int *)&S.q_head, t = *(volatile int *)&S.q_tail;
             if (h < t) {
@@ -411,6 +412,11 @@ __device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
             }
             if (*(volatile int *)&S.pending <= 0) break;
             __nanosleep(YAVO_SEL_SLEEP);
+            if (++spins > (1 << 22)) {  // watchdog (~0.5 s): never hang the GPU on a scheduling bug; report instead
+                atomicExch(&S.watchdog, 1);
+                atomicExch(&S.pending, 0);
+                break;
+            }
         }
         if (got >= 0) {
             while (*(volatile int *)&S.ready[got % SEL_QCAP] != got + 1) {
@@ -752,7 +758,7 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     uint32_t *Rpos = Lpos + (max_cand / 2 + 2);
 
     for (int i = tid; i < SEL_QCAP; i += SEL_THREADS) S.ready[i] = 0;
-    if (tid == 0) { S.nbig[0] = S.nbig[1] = 0; S.q_head = S.q_tail = 0; S.pending = 0; }
+    if (tid == 0) { S.nbig[0] = S.nbig[1] = 0; S.q_head = S.q_tail = 0; S.pending = 0; S.watchdog = 0; }
     __syncthreads();
 
     // load the candidate list (positions in scan order) and score it on the way in: Harris response from
@@ -864,6 +870,7 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
 #endif
     }
     __syncthreads();
+    if (tid == 0 && S.watchdog) atomicExch(status, 2);
     SEL_MARK(4);
 
     // ---- outputs: first min(N,K) in order, plus the checkBoundry-compacted list -------------------
