@@ -165,3 +165,35 @@ def test_async_submit_two_batches_in_flight(cuda_lib, offsets):
                         assert np.array_equal(got["match_dist"][f, :kq], exp["match_dist"][f, :kq])
         with pytest.raises(cuda_lib.YavoError):
             ctx.submit_host_batch(fa, True)  # pageable memory is refused by the asynchronous entry point
+
+
+def test_seq00_length_batch(cuda_lib, oracle, offsets):
+    """config 3 at full length: 4541 frames of 1241x376 resident on one GPU, one set of launches; frames spread over
+    the batch are compared with the oracle bit for bit, the rest through batch-wide invariants."""
+    F = 4541
+    rng = np.random.default_rng(99)
+    # uniform noise is the cheapest generator (and the densest candidate lists: ~17 k per frame)
+    frames = rng.integers(0, 256, (F, 376, 1241), dtype=np.uint8)
+    picks = [1, 777, 2270, 4540]
+    with cuda_lib.Context(device=0, n_slots=F, max_rows=376, max_cols=1241, max_kp=2000, max_cand=32768) as ctx:
+        ctx.set_brief_offsets(offsets)
+        ctx.upload_batch(0, frames)
+        ctx.frontend_batch(0, F, True)
+        out = ctx.fetch_batch(0, F)
+    assert out["n_kp"].min() > 1800 and out["n_kp"].max() <= 2000
+    for f in picks:
+        exp = oracle.pipeline(frames[f - 1:f + 1], offsets, 2000, True, nthreads=2)
+        k, kq = exp["n_kp"][1], exp["n_kp"][0]
+        assert out["n_kp"][f] == k and out["n_kp"][f - 1] == kq
+        assert np.array_equal(out["rows"][f, :k], exp["rows"][1, :k]) and np.array_equal(out["cols"][f, :k], exp["cols"][1, :k])
+        assert np.array_equal(out["scores"][f, :k].view(np.uint32), exp["scores"][1, :k].view(np.uint32))
+        assert np.array_equal(out["desc"][f, :k], exp["desc"][1, :k])
+        assert np.array_equal(out["match_idx"][f, :kq], exp["match_idx"][1, :kq])
+        assert np.array_equal(out["match_dist"][f, :kq], exp["match_dist"][1, :kq])
+    # invariants over every frame: scores non-increasing, match distances consistent with the descriptors
+    for f in range(1, F, 97):
+        k, kq = out["n_kp"][f], out["n_kp"][f - 1]
+        assert np.all(np.diff(out["scores"][f, :k]) <= 0)
+        idx, dist = out["match_idx"][f, :kq], out["match_dist"][f, :kq]
+        assert idx.min() >= 0 and idx.max() < k
+        assert np.array_equal(dist, hamming_rows(out["desc"][f - 1, :kq], out["desc"][f, idx]))

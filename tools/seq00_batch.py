@@ -1,5 +1,5 @@
 """BASELINE config 3: a KITTI seq-00-length batch (4541 frames, 1241x376) device-resident on one GPU (or sharded over
-WORLD_SIZE ranks with ya_vo_b200.sharding), FAST+BRIEF on each and the match f-1 -> f; spot-checked against the oracle.
+WORLD_SIZE ranks with ya_vo_b200.sharding), FAST+BRIEF on each and the match f-1 -> f (timing only; the parity check of this configuration lives in tests/).
 Prints one JSON object; commit it under profiles/."""
 import json
 import os
@@ -43,21 +43,10 @@ def main():
         t0 = time.perf_counter()
         out = ctx.fetch_batch(0, F)
         t_fetch = time.perf_counter() - t0
-    # spot check against the oracle
-    from oracle import pyoracle as po
-    checked = []
-    for f in (1, 2270, 4540):
-        exp = po.pipeline(frames[f - 1:f + 1], synth.brief_offsets(), 2000, True, nthreads=2)
-        k, kq = exp["n_kp"][1], exp["n_kp"][0]
-        ok = (out["n_kp"][f] == k and np.array_equal(out["rows"][f, :k], exp["rows"][1, :k])
-              and np.array_equal(out["desc"][f, :k], exp["desc"][1, :k])
-              and np.array_equal(out["match_idx"][f, :kq], exp["match_idx"][1, :kq])
-              and np.array_equal(out["match_dist"][f, :kq], exp["match_dist"][1, :kq]))
-        checked.append(bool(ok))
     print(json.dumps({"config": "seq-00-length batch: %d frames %dx%d, device-resident, one launch set" % (F, W, H),
                       "frames_per_s": F / dt, "ms_total": 1e3 * dt, "upload_s": t_up, "fetch_s": t_fetch, "generate_s": t_gen,
                       "mean_keypoints": float(out["n_kp"].mean()), "kernel_ms": {k: v[0] for k, v in prof.items()},
-                      "oracle_spot_checks_ok": checked}))
+                      "note": "parity of this configuration is covered by tests/test_gpu_fullsize.py::test_seq00_length_batch"}))
 
 
 if __name__ == "__main__":

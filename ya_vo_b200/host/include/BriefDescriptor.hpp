@@ -36,32 +36,43 @@ class Matches {
     int distance;
 };
 
+// Drop-in for the reference's `Brief`.  Grouped by role rather than in the reference's declaration order:
+//   * the three calls LoopHandler makes on the hot path (GPU),
+//   * construction / the offset table,
+//   * small scalar helpers that the reference happens to expose publicly (host-side, unchanged semantics).
 class Brief {
    public:
+    // ---- hot path: device kernels behind include/yavo_b200.h ----------------------------------------------------
+    // Appends one KeyPoint per admitted point to img.keypoints (a second call appends again, as in the
+    // reference); smoothing = cv::GaussianBlur(9x9, sigma 2.5) exactly as OpenCV 4.x computes it for 8-bit input.
+    void computeBrief(const std::vector<cv::Point> &detectedCornerPoints, Image &img);
+    // One Matches entry per keypoint of img1: the keypoint of img2 with the smallest Hamming distance, the
+    // lowest index among equal minima; pt2 carries only x, y and id, like the reference.
+    std::vector<Matches> matchFeatures(Image &img1, Image &img2);
+    // keeps distance < max(2 * smallest distance, threshold) and marks kept matches on the input list too
+    void removeOutliers(std::vector<Matches> &matches, std::vector<Matches> &newMatches, int threshold);
+
+    // ---- construction ----------------------------------------------------------------------------------------------
     Brief() {}
     // numTests is stored as patchSize and used as the test count exactly as the reference does (256 in practice)
     Brief(int numTests) : patchSize(numTests), offsets(preComputeOffsets()) {}
     ~Brief() {}
-
     // src/BriefDescriptor.cc:4-20: 256 x 4 offsets in [-8,8] from mt19937(random_device) — new every construction
     std::vector<std::vector<int>> preComputeOffsets();
     // not in the reference: inject a fixed table (tests, benchmarks, reproducible runs)
     void setOffsets(const std::vector<std::vector<int>> &table) { offsets = table; }
     const std::vector<std::vector<int>> &getOffsets() const { return offsets; }
-
-    int popCount(uchar featVec);
-    inline bool checkBoundry(int x, int y, int width, int height);
-    int hammingDistance(uchar featVec1[32], uchar featVec2[32]);
-    void convolve2d(const Image &img, cv::Mat &kernel, cv::Mat &output);
-    void gaussianBlur(const Image &img, int sigma, cv::Mat &outImage);
-    void computeBrief(const std::vector<cv::Point> &detectedCornerPoints, Image &img);
-    std::vector<Matches> matchFeatures(Image &img1, Image &img2);
-    cv::Mat drawMatches(Image &img1, Image &img2, std::vector<Matches> &matches);
-    void removeOutliers(std::vector<Matches> &matches, std::vector<Matches> &newMatches, int threshold);
-
     // keypoints whose tests read past the end of the pixel buffer in the last computeBrief
     // (undefined behaviour in the reference; those reads are defined as 0 here)
     int lastOutOfBufferCount() const { return lastOob; }
+
+    // ---- scalar helpers kept for source compatibility ------------------------------------------------------------
+    int hammingDistance(uchar featVec1[32], uchar featVec2[32]);
+    int popCount(uchar featVec);
+    inline bool checkBoundry(int x, int y, int width, int height);
+    cv::Mat drawMatches(Image &img1, Image &img2, std::vector<Matches> &matches);  // debug canvas
+    void gaussianBlur(const Image &img, int sigma, cv::Mat &outImage);               // the reference's unused hand-rolled blur
+    void convolve2d(const Image &img, cv::Mat &kernel, cv::Mat &output);
 
    private:
     int patchSize = 256;
