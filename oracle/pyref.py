@@ -118,3 +118,28 @@ def write_golden(path):
     out["names"] = np.array(names)
     np.savez_compressed(path, **out)
     print("ref_golden: %d frames, %s" % (len(names), ", ".join("%s:%d kp" % (n, out[n + "_fast_rows"].size) for n in names)))
+
+
+class Stream:
+    """Steady-state timing form: push(frame) = getFastFeatures + computeBrief on the frame and
+    matchFeatures(previous, frame) + removeOutliers, all inside the reference's own object code."""
+
+    def __init__(self, offsets):
+        L = lib()
+        L.ref_stream_new.restype = C.c_void_p
+        L.ref_stream_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ref_stream_free.argtypes = [C.c_void_p]
+        off = np.ascontiguousarray(offsets, np.int32).reshape(-1)
+        self.h = L.ref_stream_new(_p(off))
+
+    def push(self, frame, threshold=20):
+        frame = np.ascontiguousarray(frame, np.uint8)
+        nk = np.zeros(1, np.int32)
+        kept = np.zeros(1, np.int32)
+        lib().ref_stream_push(self.h, _p(frame), frame.shape[0], frame.shape[1], int(threshold), _p(nk), _p(kept))
+        return int(nk[0]), int(kept[0])
+
+    def close(self):
+        if self.h:
+            lib().ref_stream_free(self.h)
+            self.h = None

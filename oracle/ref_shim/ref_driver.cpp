@@ -99,4 +99,68 @@ int ref_match(const uint8_t *d1, int n1, const uint8_t *d2, int n2, int threshol
     return (int)m.size();
 }
 
+// The benchmark call order of tests/BriefDescriptorTest.cc:13-44 over a run of n consecutive frames:
+// getFastFeatures + computeBrief on every frame, matchFeatures(previous, current) + removeOutliers(.., threshold)
+// for every frame (the first frame is matched against the last one, so n frames cost n detections and n matches).
+// stdout chatter of the reference is left alone: the caller points fd 1 at /dev/null.
+// Returns the number of frames processed; per-frame keypoint and kept-match counts are written when asked for.
+int ref_sequence(const uint8_t *frames, int n, int H, int W, const int32_t *offsets, int threshold, int32_t *out_nkp,
+                 int32_t *out_nkept) {
+    FastDetector fd(12, 50);
+    Brief brief(256);
+    for (int j = 0; j < 256; j++)
+        for (int k = 0; k < 4; k++) brief.offsets[j][k] = offsets[4 * j + k];
+    std::vector<Image> imgs;
+    for (int f = 0; f < n; f++) {
+        imgs.emplace_back(wrap(frames + (size_t)f * H * W, H, W));
+        Image &im = imgs.back();
+        std::vector<cv::Point> pts = fd.getFastFeatures(im);
+        brief.computeBrief(pts, im);
+        if (out_nkp) out_nkp[f] = (int)im.keypoints.size();
+    }
+    for (int f = 0; f < n; f++) {
+        Image &prev = imgs[(f + n - 1) % n], &cur = imgs[f];
+        std::vector<Matches> m = brief.matchFeatures(prev, cur), kept;
+        if (!m.empty()) brief.removeOutliers(m, kept, threshold);
+        if (out_nkept) out_nkept[f] = (int)kept.size();
+    }
+    return n;
+}
+
+// Steady-state form of the same call order for timing (bench.py --impl reference): one detector, one descriptor
+// object and the previous frame are kept; every push runs getFastFeatures + computeBrief on the new frame and
+// matchFeatures(previous, new) + removeOutliers, as LoopHandler does per frame (src/LoopHandler.cc:468-485,534-537).
+struct RefStream {
+    FastDetector fd{12, 50};
+    Brief brief{256};
+    std::vector<Image> prev;  // 0 or 1 element (Image has no default constructor)
+};
+
+void *ref_stream_new(const int32_t *offsets) {
+    RefStream *s = new RefStream();
+    for (int j = 0; j < 256; j++)
+        for (int k = 0; k < 4; k++) s->brief.offsets[j][k] = offsets[4 * j + k];
+    return s;
+}
+
+int ref_stream_push(void *h, const uint8_t *frame, int H, int W, int threshold, int32_t *out_nkp, int32_t *out_nkept) {
+    RefStream *s = (RefStream *)h;
+    Image cur(wrap(frame, H, W));
+    std::vector<cv::Point> pts = s->fd.getFastFeatures(cur);
+    s->brief.computeBrief(pts, cur);
+    if (out_nkp) *out_nkp = (int)cur.keypoints.size();
+    int kept_n = 0;
+    if (!s->prev.empty()) {
+        std::vector<Matches> m = s->brief.matchFeatures(s->prev[0], cur), kept;
+        if (!m.empty()) s->brief.removeOutliers(m, kept, threshold);
+        kept_n = (int)kept.size();
+    }
+    if (out_nkept) *out_nkept = kept_n;
+    s->prev.clear();
+    s->prev.push_back(cur);
+    return 0;
+}
+
+void ref_stream_free(void *h) { delete (RefStream *)h; }
+
 }  // extern "C"

@@ -71,6 +71,42 @@ def test_live_shimmed_reference_matches_fixture(gold):
     assert pyref.check_contiguous(img, 25, 25) is False
 
 
+def test_live_reference_stream_agrees_with_oracle(oracle, gold):
+    """The steady-state timing form bench.py --impl reference uses (oracle/_ref ref_stream_push) produces the
+    oracle's keypoint counts and kept-match counts on a short frame sequence."""
+    from oracle import pyref
+    if not pyref.available():
+        pytest.skip("oracle/_ref not built (needs the reference checkout)")
+    import subprocess, sys, json, textwrap
+    names = frames(gold)[:3]
+    # the reference prints on every call: run it in a child whose stdout is discarded
+    code = textwrap.dedent("""
+        import os, sys, json, numpy as np
+        keep = os.dup(1); os.dup2(os.open(os.devnull, os.O_WRONLY), 1)
+        sys.path.insert(0, %r)
+        from oracle import pyref
+        g = np.load(%r)
+        st = pyref.Stream(g["offsets"])
+        out = [st.push(g[n + "_img"]) for n in %r]
+        os.dup2(keep, 1)
+        print(json.dumps(out))
+    """ % (os.path.dirname(os.path.dirname(os.path.dirname(GOLDEN))), GOLDEN, names))
+    got = json.loads(subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1])
+    off = gold["offsets"]
+    prev = None
+    for n, (nk, kept) in zip(names, got):
+        img = gold[n + "_img"]
+        r, c, s, nc = oracle.fast_detect(img, 2000)
+        d, v, _ = oracle.brief(img, off, r, c)
+        assert nk == int(v.sum()), n
+        if prev is not None and prev.shape[0] and int(v.sum()):
+            idx, dist = oracle.match(prev, d[v])
+            assert kept == int(np.count_nonzero(oracle.remove_outliers(dist, 20))), n
+        else:
+            assert kept == 0
+        prev = d[v]
+
+
 @pytest.mark.gpu
 def test_cuda_reproduces_reference_outputs(cuda_lib, gold):
     off = gold["offsets"]

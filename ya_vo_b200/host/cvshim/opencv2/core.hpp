@@ -106,13 +106,16 @@ class Mat {
     static Mat zeros(int r, int c, int type) { return Mat(r, c, type, Scalar(0)); }
     static Mat zeros(Size sz, int type) { return Mat(sz, type, Scalar(0)); }
 
-    void create(int r, int c, int type) {
+    void create(int r, int c, int type) { allocate(r, c, type, true); }
+    void allocate(int r, int c, int type, bool zero_pixels) {
         rows = r; cols = c; type_ = type;
         step = (size_t)c * elemSize();
         // 64 KiB of zeroed slack after the pixels: Image::getPixelVal-style unchecked linear reads slightly past
         // the end (the reference's BRIEF does this when row + 8 == H) see zeros instead of heap contents
-        buf_ = std::shared_ptr<uchar>(new uchar[step * r + 65536](), std::default_delete<uchar[]>());
+        const size_t n = step * r;
+        buf_ = std::shared_ptr<uchar>(new uchar[n + 65536], std::default_delete<uchar[]>());
         data = buf_.get();
+        std::memset(zero_pixels ? data : data + n, 0, zero_pixels ? n + 65536 : 65536);
     }
     int type() const { return type_; }
     int depth() const { return type_ & 7; }
@@ -153,6 +156,16 @@ class Mat {
         dst = out;
     }
     Mat mul(const Mat &o) const {  // element-wise product
+        if (type_ == CV_32FC1 && o.type_ == CV_32FC1) {  // the only case on the hot path: plain float rows, no zero fill
+            Mat out;
+            out.allocate(rows, cols, type_, false);
+            for (int r = 0; r < rows; r++) {
+                const float *a = ptr<float>(r), *b = o.ptr<float>(r);
+                float *d = out.ptr<float>(r);
+                for (int c = 0; c < cols; c++) d[c] = a[c] * b[c];
+            }
+            return out;
+        }
         Mat out(rows, cols, type_);
         for (int r = 0; r < rows; r++)
             for (int c = 0; c < cols; c++)
