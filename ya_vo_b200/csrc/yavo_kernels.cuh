@@ -1097,6 +1097,9 @@ match_partial_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict_
         for (int i = threadIdx.x; i < nt_tile * 2; i += MQ)
             st[i >> 1][i & 1] = __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)t0 * 8) + i);
         __syncthreads();
+        // warps whose 32 queries all lie beyond nq (three of the four warps of a frame's last CTA at ~1950
+        // keypoints) only help staging the tiles: their issue slots go to the other resident CTAs
+        if (q0 + (int)(threadIdx.x & ~31u) >= nq) continue;
         if (SECOND) {
 #pragma unroll 4
             for (int j = 0; j < nt_tile; j++) {
