@@ -16,7 +16,7 @@ INT_MAX = 2**31 - 1
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("yavo_oracle.cpp", "yavo_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("yavo_oracle.cpp", "yavo_oracle_klt.cpp", "yavo_oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -208,3 +208,47 @@ def pipeline(frames, offsets, max_kp=2000, do_match=True, nthreads=1, outputs=Tr
     lib().yavo_oracle_pipeline(_p(frames), F, H, W, _p(off), max_kp, int(do_match), int(nthreads),
                                _p(r), _p(c), _p(s), _p(d), _p(n), _p(mi), _p(md))
     return dict(rows=r, cols=c, scores=s, desc=d, n_kp=n, match_idx=mi, match_dist=md)
+
+
+# ---- sparse pyramidal Lucas-Kanade ----------------------------------------------------------
+def pyr_down(img):
+    img = _u8(img)
+    H, W = img.shape
+    out = np.zeros(((H + 1) // 2, (W + 1) // 2), np.uint8)
+    lib().yavo_oracle_pyr_down(_p(img), H, W, _p(out))
+    return out
+
+
+def scharr(img):
+    img = _u8(img)
+    H, W = img.shape
+    dx = np.zeros((H, W), np.int16)
+    dy = np.zeros((H, W), np.int16)
+    lib().yavo_oracle_scharr(_p(img), H, W, _p(dx), _p(dy))
+    return dx, dy
+
+
+def klt_levels(H, W, win=(11, 11), max_level=3):
+    return lib().yavo_oracle_klt_levels(int(H), int(W), int(win[0]), int(win[1]), int(max_level))
+
+
+def klt_track(prev, nxt, prev_pts, win=(11, 11), max_level=3, crit_type=3, max_count=30, epsilon=0.01, flags=0,
+              min_eig=1e-3, init_pts=None):
+    """cv::calcOpticalFlowPyrLK restated (src/LoopHandler.cc:372-375).  Points are (x = col, y = row) float32.
+    Returns next_pts (n,2) f32, status (n,) u8, err (n,) f32."""
+    prev, nxt = _u8(prev), _u8(nxt)
+    assert prev.shape == nxt.shape
+    H, W = prev.shape
+    pp = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+    n = pp.shape[0]
+    nx = np.zeros((n, 2), np.float32)
+    if init_pts is not None:
+        nx[:] = np.asarray(init_pts, np.float32).reshape(-1, 2)
+    st = np.zeros(n, np.uint8)
+    er = np.zeros(n, np.float32)
+    f = lib().yavo_oracle_klt
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double]
+    f(_p(prev), _p(nxt), H, W, _p(pp), n, _p(nx), _p(st), _p(er), int(win[0]), int(win[1]), int(max_level),
+      int(crit_type), int(max_count), float(epsilon), int(flags), float(min_eig))
+    return nx, st, er

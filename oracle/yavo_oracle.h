@@ -91,6 +91,19 @@ int yavo_oracle_pipeline(const uint8_t *frames, int F, int H, int W, const int32
                          uint8_t *kp_desc, int32_t *n_kp,
                          int32_t *match_idx, int32_t *match_dist);
 
+/* ---- sparse pyramidal Lucas-Kanade (yavo_oracle_klt.cpp) ----------------------------------
+ * cv::calcOpticalFlowPyrLK as src/LoopHandler.cc:372-375 calls it, restated for 8-bit single-channel images.
+ * Points are OpenCV's (x = column, y = row), interleaved x0,y0,x1,y1,...  crit_type: 1 = COUNT, 2 = EPS.
+ * flags: 4 = OPTFLOW_USE_INITIAL_FLOW (next_xy is read), 8 = OPTFLOW_LK_GET_MIN_EIGENVALS.
+ * err is meaningful only where status == 1 (OpenCV leaves the rest uninitialised; here 0 or the last value).
+ * Returns the top pyramid level actually used. */
+void yavo_oracle_pyr_down(const uint8_t *img, int H, int W, uint8_t *out /* ((H+1)/2) x ((W+1)/2) */);
+void yavo_oracle_scharr(const uint8_t *img, int H, int W, int16_t *dx, int16_t *dy);
+int yavo_oracle_klt_levels(int H, int W, int win_w, int win_h, int max_level);
+int yavo_oracle_klt(const uint8_t *prev, const uint8_t *next, int H, int W, const float *prev_xy, int n, float *next_xy,
+                    uint8_t *status, float *err, int win_w, int win_h, int max_level, int crit_type, int max_count,
+                    double epsilon, int flags, double min_eig_threshold);
+
 #ifdef __cplusplus
 }
 #endif
