@@ -192,6 +192,42 @@ int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int row
                             int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores,
                             uint8_t *desc, int32_t *match_idx, int32_t *match_dist);
 
+/* ---- tracking step: cv::calcOpticalFlowPyrLK (src/LoopHandler.cc:372-375) ----------------------
+ * The reference's steady-state per-frame cost after feature extraction: LoopHandler::trackLastFrame projects the
+ * last frame's map points and tracks them with OpenCV's sparse pyramidal Lucas-Kanade,
+ *   calcOpticalFlowPyrLK(last, cur, lastKpt, curKpt, status, error, Size(11,11), 3,
+ *                        TermCriteria(COUNT + EPS, 30, 0.01), 0, 0.001).
+ * These entry points run that call on device-resident frame slots.  Unlike the rest of this header, points here
+ * are OpenCV's: interleaved float (x = column, y = row), exactly what the reference hands to OpenCV
+ * (it swaps its (row, col) keypoints at :343-347).  crit_type: 1 = COUNT, 2 = EPS (cv::TermCriteria::Type);
+ * flags: 4 = OPTFLOW_USE_INITIAL_FLOW (next_xy is read), 8 = OPTFLOW_LK_GET_MIN_EIGENVALS.  Window sides 1..31.
+ * Results are bit-identical to cv2 4.13 (tests/golden/klt_golden.npz); err is defined where status == 1
+ * (OpenCV leaves it uninitialised elsewhere; here it is 0 or the last minimum eigenvalue). */
+#define YAVO_KLT_MAX_LEVEL 7
+#define YAVO_KLT_MAX_WIN 31
+
+/* cv::buildOpticalFlowPyramid (the pyrDown chain inside calcOpticalFlowPyrLK): builds levels 1..L of slots
+ * [slot0, slot0+n), L = min(max_level, levels OpenCV would keep for this frame size and window); *levels = L.
+ * Called implicitly by the tracking entry points; a slot's pyramid is kept until the slot is uploaded again. */
+int yavo_build_pyramid(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, int max_level, int *levels);
+/* copies pyramid level `level` (>= 1) of a slot to the host; out is rows x cols as reported, capacity checked */
+int yavo_pyramid_level(yavo_ctx *ctx, int slot, int level, uint8_t *out, size_t out_bytes, int *rows, int *cols);
+
+/* One call of calcOpticalFlowPyrLK: tracks n points from the frame in slot_prev to the frame in slot_next.
+ * prev_xy [2n] in; next_xy [2n] out (in/out with flag 4); status [n]; err [n] (may be NULL). */
+int yavo_klt_track(yavo_ctx *ctx, int slot_prev, int slot_next, const float *prev_xy, int n, float *next_xy,
+                   uint8_t *status, float *err, int win_w, int win_h, int max_level, int crit_type, int max_count,
+                   double epsilon, int flags, double min_eig_threshold);
+
+/* Batch form over consecutive slots: for every f in [slot0, slot0+n-1) the keypoints yavo_frontend_batch (or
+ * yavo_fast_detect) left in slot f — the reference's features, as (x, y) = (col, row) — are tracked into slot
+ * f+1.  Results stay on the device until yavo_klt_fetch.  flags may not contain OPTFLOW_USE_INITIAL_FLOW. */
+int yavo_klt_track_batch(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, int max_level, int crit_type,
+                         int max_count, double epsilon, int flags, double min_eig_threshold);
+/* rows f of the outputs ([n x max_kp x 2], [n x max_kp], [n x max_kp]; any may be NULL) hold the tracks of slot
+ * slot0+f's keypoints into slot slot0+f+1; the last row of the batch is unused. */
+int yavo_klt_fetch(yavo_ctx *ctx, int slot0, int n, float *next_xy, uint8_t *status, float *err);
+
 #ifdef __cplusplus
 }
 #endif

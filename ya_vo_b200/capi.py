@@ -26,6 +26,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch",
 ]
 
 
@@ -127,7 +128,7 @@ class Context:
         return int(self._L.yavo_get_stream(self._h) or 0)
 
     KERNEL_CLASSES = ("repitch", "detect_blur", "compact_score", "select_topk", "brief", "match_partial", "match_reduce",
-                      "filter_pairs")
+                      "filter_pairs", "pyr_down", "klt_track")
 
     def set_profiling(self, on):
         self._ck(self._L.yavo_set_profiling(self._h, int(bool(on))))
@@ -283,6 +284,51 @@ class Context:
         for i in range(n):
             self._shape[i] = (H, W)
         return out
+
+    # ---- tracking step: cv::calcOpticalFlowPyrLK (src/LoopHandler.cc:372-375) ----
+    def build_pyramid(self, slot0, n, win=(11, 11), max_level=3):
+        lv = C.c_int()
+        self._ck(self._L.yavo_build_pyramid(self._h, int(slot0), int(n), int(win[0]), int(win[1]), int(max_level), C.byref(lv)))
+        return lv.value
+
+    def pyramid_level(self, slot, level):
+        H, W = self._shape[slot]
+        for _ in range(level):
+            H, W = (H + 1) // 2, (W + 1) // 2
+        out = np.empty((H, W), np.uint8)
+        r, c = C.c_int(), C.c_int()
+        self._ck(self._L.yavo_pyramid_level(self._h, int(slot), int(level), _p(out), C.c_size_t(out.size), C.byref(r), C.byref(c)))
+        assert (r.value, c.value) == (H, W)
+        return out
+
+    def klt_track(self, slot_prev, slot_next, prev_pts, win=(11, 11), max_level=3, crit_type=3, max_count=30, epsilon=0.01,
+                  flags=0, min_eig=1e-3, init_pts=None):
+        """Points are OpenCV's (x = col, y = row) float32.  Returns next_pts (n,2), status (n,) u8, err (n,) f32."""
+        pp = np.ascontiguousarray(prev_pts, np.float32).reshape(-1, 2)
+        n = pp.shape[0]
+        nx = np.zeros((n, 2), np.float32)
+        if init_pts is not None:
+            nx[:] = np.asarray(init_pts, np.float32).reshape(-1, 2)
+        st = np.zeros(n, np.uint8)
+        er = np.zeros(n, np.float32)
+        self._ck(self._L.yavo_klt_track(self._h, int(slot_prev), int(slot_next), _p(pp), n, _p(nx), _p(st), _p(er),
+                                        int(win[0]), int(win[1]), int(max_level), int(crit_type), int(max_count),
+                                        C.c_double(epsilon), int(flags), C.c_double(min_eig)))
+        return nx, st, er
+
+    def klt_track_batch(self, slot0, n, win=(11, 11), max_level=3, crit_type=3, max_count=30, epsilon=0.01, flags=0,
+                        min_eig=1e-3):
+        self._ck(self._L.yavo_klt_track_batch(self._h, int(slot0), int(n), int(win[0]), int(win[1]), int(max_level),
+                                              int(crit_type), int(max_count), C.c_double(epsilon), int(flags),
+                                              C.c_double(min_eig)))
+
+    def klt_fetch(self, slot0, n):
+        K = self.max_kp
+        xy = np.zeros((n, K, 2), np.float32)
+        st = np.zeros((n, K), np.uint8)
+        er = np.zeros((n, K), np.float32)
+        self._ck(self._L.yavo_klt_fetch(self._h, int(slot0), int(n), _p(xy), _p(st), _p(er)))
+        return xy, st, er
 
 
 def ring_points(xc, yc):

@@ -1,0 +1,332 @@
+// klt_kernels.cuh — sm_100a kernels for the tracking step that follows the feature front end in the
+// reference's VO loop:
+//     cv::calcOpticalFlowPyrLK(last, cur, lastKpt, curKpt, status, error, Size(11,11), 3,
+//                              TermCriteria(COUNT+EPS, 30, 0.01), 0, 0.001)          src/LoopHandler.cc:372-375
+// K7 pyr_down_kernel   one pyramid level from the one below (cv::pyrDown: [1 4 6 4 1]^2, REFLECT_101,
+//                      (sum + 128) >> 8), a batch of frame slots per launch — the only image pyramid the
+//                      reference builds (inside OpenCV).
+// K8 klt_track_kernel  one warp per point, all pyramid levels inside the kernel.  The Scharr derivatives are
+//                      computed on the fly from a staged raw patch of the previous frame (they are needed
+//                      only under tracked points, so no derivative planes are written to HBM); bilinear
+//                      weights, descaling and the 2x2 solve follow OpenCV's fixed-point / float32 sequence,
+//                      and the float sums are accumulated in the ORDER of OpenCV's 128-bit SIMD loops (lane
+//                      accumulators over groups of 8 columns + a scalar tail), which makes positions, status
+//                      and err bit-identical to cv2 4.13 (tests/golden/klt_golden.npz).
+// Float arithmetic uses the _rn intrinsics: nothing may be contracted to FMA or reassociated.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace yavo {
+
+constexpr int KLT_MAX_LEVELS = 7;   // pyramid levels above level 0 a context can hold
+constexpr int KLT_MAX_WIN = 31;     // largest window side
+constexpr int KLT_WARPS = 4;        // points per CTA
+
+struct KltLevels {
+    const uint8_t *img[KLT_MAX_LEVELS + 1];   // level l of slot 0 (level 0 = the frame slots themselves)
+    unsigned long long slot_stride[KLT_MAX_LEVELS + 1];
+    int pitch[KLT_MAX_LEVELS + 1], H[KLT_MAX_LEVELS + 1], W[KLT_MAX_LEVELS + 1];
+    int top;                                   // highest level used
+};
+
+struct KltParams {
+    int ww, wh, max_count, flags;
+    double eps2;        // criteria.epsilon squared (double, as OpenCV compares delta.ddot(delta))
+    float min_eig;
+};
+
+__device__ __forceinline__ int klt_refl(int p, int n) {  // BORDER_REFLECT_101
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * (n - 1) - p;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: thread = one output pixel.  Horizontal [1 4 6 4 1] on five source rows, then vertical.
+// grid (ceil(ow/128), oh, slots)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pyr_down_kernel(const uint8_t *__restrict__ src, size_t src_stride, int src_pitch, int sH, int sW,
+                uint8_t *__restrict__ dst, size_t dst_stride, int dst_pitch, int oW) {
+    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
+    if (x >= oW) return;
+    const uint8_t *s = src + (size_t)blockIdx.z * src_stride;
+    int c[5];
+    const bool inner = (2 * x - 2 >= 0) && (2 * x + 2 < sW);
+#pragma unroll
+    for (int k = 0; k < 5; k++) c[k] = inner ? 2 * x - 2 + k : klt_refl(2 * x - 2 + k, sW);
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const int r = klt_refl(2 * y - 2 + j, sH);
+        const uint8_t *row = s + (size_t)r * src_pitch;
+        const int h = __ldg(row + c[0]) + 4 * __ldg(row + c[1]) + 6 * __ldg(row + c[2]) + 4 * __ldg(row + c[3]) + __ldg(row + c[4]);
+        acc += h * ((j == 0 || j == 4) ? 1 : (j == 2 ? 6 : 4));
+    }
+    dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dst_pitch + x] = (uint8_t)((acc + 128) >> 8);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K8
+// ------------------------------------------------------------------------------------------------
+struct KltW {
+    int w00, w01, w10, w11;
+};
+__device__ __forceinline__ KltW klt_weights(float a, float b) {  // 14-bit bilinear weights, cvRound = half to even
+    const float oa = __fsub_rn(1.f, a), ob = __fsub_rn(1.f, b);
+    KltW w;
+    w.w00 = __float2int_rn(__fmul_rn(__fmul_rn(oa, ob), 16384.f));
+    w.w01 = __float2int_rn(__fmul_rn(__fmul_rn(a, ob), 16384.f));
+    w.w10 = __float2int_rn(__fmul_rn(__fmul_rn(oa, b), 16384.f));
+    w.w11 = 16384 - w.w00 - w.w01 - w.w10;
+    return w;
+}
+
+// Ordered float accumulation of one row-major int16 plane product, as OpenCV's SIMD loop does it:
+// lane role k (0..3) owns columns k and k+4 of every group of 8; role 4 owns the tail columns.
+// MODE 0: (float)a * (float)b summed (gradient matrix: float products);  MODE 1: int pair sums / int tail
+// products converted to float (mismatch vector).
+template <int MODE>
+__device__ __forceinline__ float klt_chain(const int16_t *__restrict__ A, const int16_t *__restrict__ B, int ww, int wh,
+                                           int role) {
+    const int vec = ww & ~7;
+    float acc = 0.f;
+    if (role < 4) {
+        for (int y = 0; y < wh; y++) {
+            const int16_t *a = A + y * ww, *b = B + y * ww;
+            for (int g = role; g < vec; g += 8) {
+                if (MODE == 0) {
+                    acc = __fadd_rn(__fmul_rn((float)a[g], (float)b[g]), acc);
+                    acc = __fadd_rn(__fmul_rn((float)a[g + 4], (float)b[g + 4]), acc);
+                } else {
+                    acc = __fadd_rn(acc, __int2float_rn((int)a[g] * (int)b[g] + (int)a[g + 4] * (int)b[g + 4]));
+                }
+            }
+        }
+    } else {
+        for (int y = 0; y < wh; y++) {
+            const int16_t *a = A + y * ww, *b = B + y * ww;
+            for (int x = vec; x < ww; x++) acc = __fadd_rn(acc, __int2float_rn((int)a[x] * (int)b[x]));
+        }
+    }
+    return acc;
+}
+
+// tail + ((q0 + q2) + (q1 + q3)) with q_k in lanes base..base+3 and the tail in lane base_tail (v_reduce_sum order)
+__device__ __forceinline__ float klt_combine(float v, int base, int tail_lane) {
+    const float q0 = __shfl_sync(0xffffffffu, v, base), q1 = __shfl_sync(0xffffffffu, v, base + 1);
+    const float q2 = __shfl_sync(0xffffffffu, v, base + 2), q3 = __shfl_sync(0xffffffffu, v, base + 3);
+    const float t = __shfl_sync(0xffffffffu, v, tail_lane);
+    return __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
+}
+
+__host__ __device__ __forceinline__ size_t klt_smem_per_warp(int ww, int wh) {
+    const size_t area = (size_t)ww * wh;
+    size_t b = 4 * ((area * 2 + 3) & ~size_t(3));                        // Iw, Ix, Iy, diff (int16)
+    b += ((size_t)(ww + 3) * (wh + 3) + 3) & ~size_t(3);                 // raw patch / J patch (u8)
+    b += (size_t)(ww + 1) * (wh + 1) * 4;                                // derivative patch (short2)
+    return b;
+}
+
+// Staged (wh+1) x (ww+1) patch of image `im` with origin (oy, ox), REFLECT_101 outside the image.
+__device__ __forceinline__ void klt_stage_patch(uint8_t *dst, const uint8_t *im, int pitch, int H, int W, int oy, int ox,
+                                                int ph, int pw, int lane) {
+    const bool inside = oy >= 0 && ox >= 0 && oy + ph <= H && ox + pw <= W;
+    for (int p = lane; p < ph * pw; p += 32) {
+        const int r = p / pw, c = p - r * pw;
+        const int yy = inside ? oy + r : klt_refl(oy + r, H), xx = inside ? ox + c : klt_refl(ox + c, W);
+        dst[p] = __ldg(im + (size_t)yy * pitch + xx);
+    }
+}
+
+__global__ void __launch_bounds__(KLT_WARPS * 32)
+klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
+                 const float2 *__restrict__ prev_xy,                                  // explicit points, or
+                 const int32_t *__restrict__ kp_row, const int32_t *__restrict__ kp_col,  // keypoints (row, col) per slot
+                 const int *__restrict__ n_all, int n_fixed, int pts_stride,
+                 const float2 *__restrict__ init_xy, float2 *__restrict__ next_xy, uint8_t *__restrict__ status,
+                 float *__restrict__ err) {
+    extern __shared__ __align__(16) uint8_t klt_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.y;
+    const int pt = blockIdx.x * KLT_WARPS + warp;
+    const int n = n_all ? n_all[prev_slot0 + pair] : n_fixed;
+    if (pt >= n) return;
+    const int ww = P.ww, wh = P.wh, area = ww * wh;
+    const size_t plane = ((size_t)area * 2 + 3) & ~size_t(3);
+    uint8_t *base = klt_smem + (size_t)warp * klt_smem_per_warp(ww, wh);
+    int16_t *sI = reinterpret_cast<int16_t *>(base), *sIx = reinterpret_cast<int16_t *>(base + plane),
+            *sIy = reinterpret_cast<int16_t *>(base + 2 * plane), *sD = reinterpret_cast<int16_t *>(base + 3 * plane);
+    uint8_t *sR = base + 4 * plane;
+    short2 *sG = reinterpret_cast<short2 *>(sR + (((size_t)(ww + 3) * (wh + 3) + 3) & ~size_t(3)));
+
+    const size_t o = (size_t)pair * pts_stride + pt;
+    float2 p0;
+    if (prev_xy) p0 = prev_xy[o];
+    else p0 = make_float2((float)kp_col[(size_t)(prev_slot0 + pair) * pts_stride + pt],
+                          (float)kp_row[(size_t)(prev_slot0 + pair) * pts_stride + pt]);
+    const float halfx = __fmul_rn((float)(ww - 1), 0.5f), halfy = __fmul_rn((float)(wh - 1), 0.5f);
+    const bool use_initial = (P.flags & 4) != 0, get_min_eig = (P.flags & 8) != 0;
+    float outx = 0.f, outy = 0.f, ev = 0.f;
+    bool st = true;
+
+    for (int level = L.top; level >= 0; level--) {
+        const int H = L.H[level], W = L.W[level], pitch = L.pitch[level];
+        const uint8_t *I = L.img[level] + (size_t)(prev_slot0 + pair) * L.slot_stride[level];
+        const uint8_t *J = L.img[level] + (size_t)(next_slot0 + pair) * L.slot_stride[level];
+        const float sc = __int_as_float((127 - level) << 23);  // 1 / (1 << level)
+        float px = __fmul_rn(p0.x, sc), py = __fmul_rn(p0.y, sc);
+        float nx, ny;
+        if (level == L.top) {
+            if (use_initial) {
+                const float2 q = init_xy[o];
+                nx = __fmul_rn(q.x, sc);
+                ny = __fmul_rn(q.y, sc);
+            } else {
+                nx = px;
+                ny = py;
+            }
+        } else {
+            nx = __fmul_rn(outx, 2.f);
+            ny = __fmul_rn(outy, 2.f);
+        }
+        outx = nx;
+        outy = ny;
+        px = __fsub_rn(px, halfx);
+        py = __fsub_rn(py, halfy);
+        const int ix = __float2int_rd(px), iy = __float2int_rd(py);
+        if (ix < -ww || ix >= W || iy < -wh || iy >= H) {
+            if (level == 0) {
+                st = false;
+                ev = 0.f;
+            }
+            continue;
+        }
+        KltW w = klt_weights(__fsub_rn(px, (float)ix), __fsub_rn(py, (float)iy));
+
+        // ---- raw patch rows iy-1 .. iy+wh+1, cols ix-1 .. ix+ww+1 of the previous frame ----------------
+        __syncwarp();
+        klt_stage_patch(sR, I, pitch, H, W, iy - 1, ix - 1, wh + 3, ww + 3, lane);
+        __syncwarp();
+        const int rw = ww + 3, gw = ww + 1;
+        // Scharr (dx, dy) at window positions (iy + r, ix + c), r <= wh, c <= ww; zero outside the image
+        for (int p = lane; p < (wh + 1) * gw; p += 32) {
+            const int r = p / gw, c = p - r * gw;
+            short2 g = make_short2(0, 0);
+            if (iy + r >= 0 && iy + r < H && ix + c >= 0 && ix + c < W) {
+                const uint8_t *q0 = sR + r * rw + c, *q1 = q0 + rw, *q2 = q1 + rw;
+                const int t0a = (q0[0] + q2[0]) * 3 + q1[0] * 10, t0c = (q0[2] + q2[2]) * 3 + q1[2] * 10;
+                const int t1a = q2[0] - q0[0], t1b = q2[1] - q0[1], t1c = q2[2] - q0[2];
+                g.x = (short)(t0c - t0a);
+                g.y = (short)((t1c + t1a) * 3 + t1b * 10);
+            }
+            sG[p] = g;
+        }
+        __syncwarp();
+        // bilinear samples of the patch and its derivatives
+        for (int p = lane; p < area; p += 32) {
+            const int y = p / ww, x = p - y * ww;
+            const uint8_t *q = sR + (y + 1) * rw + (x + 1);
+            const int iv = (q[0] * w.w00 + q[1] * w.w01 + q[rw] * w.w10 + q[rw + 1] * w.w11 + (1 << 8)) >> 9;
+            const short2 g00 = sG[y * gw + x], g01 = sG[y * gw + x + 1], g10 = sG[(y + 1) * gw + x], g11 = sG[(y + 1) * gw + x + 1];
+            const int gx = (g00.x * w.w00 + g01.x * w.w01 + g10.x * w.w10 + g11.x * w.w11 + (1 << 13)) >> 14;
+            const int gy = (g00.y * w.w00 + g01.y * w.w01 + g10.y * w.w10 + g11.y * w.w11 + (1 << 13)) >> 14;
+            sI[p] = (int16_t)iv;
+            sIx[p] = (int16_t)gx;
+            sIy[p] = (int16_t)gy;
+        }
+        __syncwarp();
+        // gradient matrix: lanes 0-3 A11, 4-7 A12, 8-11 A22 lane accumulators; 12-14 their tails
+        float v = 0.f;
+        if (lane < 12) {
+            const int s = lane >> 2;
+            v = klt_chain<0>(s == 2 ? sIy : sIx, s == 0 ? sIx : sIy, ww, wh, lane & 3);
+        } else if (lane < 15) {
+            const int s = lane - 12;
+            v = klt_chain<0>(s == 2 ? sIy : sIx, s == 0 ? sIx : sIy, ww, wh, 4);
+        }
+        const float FLT_SCALE = 1.f / (1 << 20);
+        const float A11 = __fmul_rn(klt_combine(v, 0, 12), FLT_SCALE), A12 = __fmul_rn(klt_combine(v, 4, 13), FLT_SCALE),
+                    A22 = __fmul_rn(klt_combine(v, 8, 14), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = __fsub_rn(A11, A22);
+        const float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * ww * wh));
+        if (get_min_eig) ev = minEig;
+        if (minEig < P.min_eig || D < 1.1920928955078125e-07f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, halfx);
+        ny = __fsub_rn(ny, halfy);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < P.max_count; j++) {
+            const int jx = __float2int_rd(nx), jy = __float2int_rd(ny);
+            if (jx < -ww || jx >= W || jy < -wh || jy >= H) {
+                if (level == 0) st = false;
+                break;
+            }
+            w = klt_weights(__fsub_rn(nx, (float)jx), __fsub_rn(ny, (float)jy));
+            __syncwarp();
+            klt_stage_patch(sR, J, pitch, H, W, jy, jx, wh + 1, gw, lane);
+            __syncwarp();
+            for (int p = lane; p < area; p += 32) {
+                const int y = p / ww, x = p - y * ww;
+                const uint8_t *q = sR + y * gw + x;
+                const int jv = (q[0] * w.w00 + q[1] * w.w01 + q[gw] * w.w10 + q[gw + 1] * w.w11 + (1 << 8)) >> 9;
+                sD[p] = (int16_t)(jv - sI[p]);
+            }
+            __syncwarp();
+            float u = 0.f;
+            if (lane < 8) u = klt_chain<1>(sD, (lane >> 2) ? sIy : sIx, ww, wh, lane & 3);
+            else if (lane < 10) u = klt_chain<1>(sD, (lane - 8) ? sIy : sIx, ww, wh, 4);
+            const float b1 = __fmul_rn(klt_combine(u, 0, 8), FLT_SCALE), b2 = __fmul_rn(klt_combine(u, 4, 9), FLT_SCALE);
+            const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, ddx);
+            ny = __fadd_rn(ny, ddy);
+            outx = __fadd_rn(nx, halfx);
+            outy = __fadd_rn(ny, halfy);
+            if (__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)) <= P.eps2) break;
+            if (j > 0 && fabs((double)__fadd_rn(ddx, pdx)) < 0.01 && fabs((double)__fadd_rn(ddy, pdy)) < 0.01) {
+                outx = __fsub_rn(outx, __fmul_rn(ddx, 0.5f));
+                outy = __fsub_rn(outy, __fmul_rn(ddy, 0.5f));
+                break;
+            }
+            pdx = ddx;
+            pdy = ddy;
+        }
+        if (st && level == 0 && !get_min_eig) {
+            // err = mean absolute difference of the patch at the final position (5 fractional bits removed)
+            const float qx = __fsub_rn(outx, halfx), qy = __fsub_rn(outy, halfy);
+            const int jx = __float2int_rd(qx), jy = __float2int_rd(qy);
+            if (jx < -ww || jx >= W || jy < -wh || jy >= H) {
+                st = false;
+                continue;
+            }
+            w = klt_weights(__fsub_rn(qx, (float)jx), __fsub_rn(qy, (float)jy));
+            __syncwarp();
+            klt_stage_patch(sR, J, pitch, H, W, jy, jx, wh + 1, gw, lane);
+            __syncwarp();
+            int e = 0;
+            for (int p = lane; p < area; p += 32) {
+                const int y = p / ww, x = p - y * ww;
+                const uint8_t *q = sR + y * gw + x;
+                const int jv = (q[0] * w.w00 + q[1] * w.w01 + q[gw] * w.w10 + q[gw + 1] * w.w11 + (1 << 8)) >> 9;
+                e += abs(jv - sI[p]);
+            }
+#pragma unroll
+            for (int s = 16; s; s >>= 1) e += __shfl_xor_sync(0xffffffffu, e, s);
+            ev = __fdiv_rn(__fmul_rn((float)e, 1.f), (float)(32 * ww * wh));  // integer partial sums: order-free
+        }
+    }
+    if (lane == 0) {
+        next_xy[o] = make_float2(outx, outy);
+        status[o] = st ? 1 : 0;
+        err[o] = ev;
+    }
+}
+
+}  // namespace yavo

@@ -13,6 +13,7 @@
 
 #include "../../include/yavo_b200.h"
 #include "yavo_kernels.cuh"
+#include "klt_kernels.cuh"
 
 using namespace yavo;
 
@@ -80,6 +81,20 @@ struct yavo_ctx {
     char raw_used[2] = {0, 0};
     int pipeline_chunk = 0;  // frames per copy/compute stage of the host-batch path (0 = automatic)
     int sub_batch = 0;  // frames per kernel sub-batch of yavo_frontend_batch (0 = the whole batch in one set of launches)
+    // tracking step (klt_kernels.cuh): pyramid levels 1..KLT_MAX_LEVELS per slot, allocated on first use
+    uint8_t *d_pyr = nullptr;
+    size_t pyr_slot_stride = 0;
+    size_t pyr_off[KLT_MAX_LEVELS + 1] = {};
+    int pyr_pitch[KLT_MAX_LEVELS + 1] = {};
+    int pyr_levels_alloc = 0;
+    std::vector<int> slot_pyr;  // pyramid levels currently built for the slot (0 = none)
+    float2 *d_klt_prev = nullptr, *d_klt_next = nullptr;  // explicit-point scratch
+    uint8_t *d_klt_status = nullptr;
+    float *d_klt_err = nullptr;
+    int klt_cap = 0;
+    float2 *d_trk_xy = nullptr;  // batch results, per slot max_kp
+    uint8_t *d_trk_status = nullptr;
+    float *d_trk_err = nullptr;
     // optional per-kernel timing (CUDA events on the context's stream around every launch)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -88,7 +103,7 @@ struct yavo_ctx {
     std::string err;
 };
 
-enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_COUNT };
+enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_PYR, KC_KLT, KC_COUNT };
 
 namespace {
 
@@ -190,6 +205,7 @@ int launch_repitch(yavo_ctx *ctx, const uint8_t *d_src, size_t src_pitch, int sl
         ctx->slot_rows[slot0 + i] = rows;
         ctx->slot_cols[slot0 + i] = cols;
         ctx->slot_blur_valid[slot0 + i] = 0;
+        ctx->slot_pyr[slot0 + i] = 0;
     }
     return 0;
 }
@@ -324,6 +340,120 @@ int ensure_partials(yavo_ctx *ctx, size_t n) {
     return 0;
 }
 
+// ---- tracking step helpers ------------------------------------------------------------------------------
+// cv::buildOpticalFlowPyramid keeps a level while both of its sides exceed the window's
+int klt_levels_for(int H, int W, int ww, int wh, int max_level) {
+    int lv = 0;
+    while (lv < max_level && lv < KLT_MAX_LEVELS) {
+        const int nh = (H + 1) / 2, nw = (W + 1) / 2;
+        if (nw <= ww || nh <= wh) break;
+        H = nh;
+        W = nw;
+        lv++;
+    }
+    return lv;
+}
+
+int ensure_pyramid_alloc(yavo_ctx *ctx) {
+    if (ctx->d_pyr) return 0;
+    size_t off = 0;
+    int r = ctx->max_rows, c = ctx->max_cols, lv = 0;
+    while (lv < KLT_MAX_LEVELS && (r > 1 || c > 1)) {
+        r = (r + 1) / 2;
+        c = (c + 1) / 2;
+        lv++;
+        ctx->pyr_pitch[lv] = (c + 15) & ~15;
+        ctx->pyr_off[lv] = off;
+        off += (size_t)ctx->pyr_pitch[lv] * r;
+    }
+    ctx->pyr_levels_alloc = lv;
+    ctx->pyr_slot_stride = (off + 127) & ~size_t(127);
+    CK(dalloc(&ctx->d_pyr, ctx->pyr_slot_stride * ctx->n_slots));
+    return 0;
+}
+
+void level_dims(int H, int W, int level, int *h, int *w) {
+    for (int l = 0; l < level; l++) {
+        H = (H + 1) / 2;
+        W = (W + 1) / 2;
+    }
+    *h = H;
+    *w = W;
+}
+
+// K7 over slots [slot0, slot0+n): levels 1..levels (all slots hold frames of one size)
+int launch_pyramid(yavo_ctx *ctx, int slot0, int n, int levels) {
+    if (int r = ensure_pyramid_alloc(ctx)) return r;
+    if (levels > ctx->pyr_levels_alloc)
+        return fail(ctx, YAVO_ERR_CAPACITY, "pyramid level %d exceeds the %d levels this context can hold", levels, ctx->pyr_levels_alloc);
+    // contiguous runs of slots that lack some of the requested levels
+    int s = slot0;
+    while (s < slot0 + n) {
+        if (ctx->slot_pyr[s] >= levels) { s++; continue; }
+        int e = s;
+        while (e < slot0 + n && ctx->slot_pyr[e] < levels) e++;
+        const int H0 = ctx->slot_rows[s], W0 = ctx->slot_cols[s];
+        for (int l = 1; l <= levels; l++) {
+            int sh, sw, oh, ow;
+            level_dims(H0, W0, l - 1, &sh, &sw);
+            level_dims(H0, W0, l, &oh, &ow);
+            const uint8_t *src = l == 1 ? ctx->d_frames + ctx->frame_stride * s : ctx->d_pyr + ctx->pyr_slot_stride * s + ctx->pyr_off[l - 1];
+            const size_t sstride = l == 1 ? ctx->frame_stride : ctx->pyr_slot_stride;
+            const int spitch = l == 1 ? ctx->pitch : ctx->pyr_pitch[l - 1];
+            dim3 grid((ow + 127) / 128, oh, e - s);
+            PROF(KC_PYR, pyr_down_kernel<<<grid, 128, 0, ctx->stream>>>(src, sstride, spitch, sh, sw,
+                                                                         ctx->d_pyr + ctx->pyr_slot_stride * s + ctx->pyr_off[l],
+                                                                         ctx->pyr_slot_stride, ctx->pyr_pitch[l], ow));
+            CK_LAUNCH();
+        }
+        for (int k = s; k < e; k++) ctx->slot_pyr[k] = levels;
+        s = e;
+    }
+    return 0;
+}
+
+int klt_check_params(yavo_ctx *ctx, int ww, int wh, int max_level, int flags) {
+    if (ww < 1 || wh < 1 || ww > KLT_MAX_WIN || wh > KLT_MAX_WIN)
+        return fail(ctx, YAVO_ERR_INVALID, "window %dx%d outside 1..%d", ww, wh, KLT_MAX_WIN);
+    if (max_level < 0) return fail(ctx, YAVO_ERR_INVALID, "max_level %d < 0", max_level);
+    if (flags & ~(4 | 8)) return fail(ctx, YAVO_ERR_INVALID, "unsupported flags 0x%x (4 = USE_INITIAL_FLOW, 8 = GET_MIN_EIGENVALS)", flags);
+    return 0;
+}
+
+// criteria clamping of cv::SparsePyrLKOpticalFlow::calc
+KltParams klt_params(int ww, int wh, int crit_type, int max_count, double epsilon, int flags, double min_eig) {
+    KltParams P;
+    P.ww = ww;
+    P.wh = wh;
+    P.max_count = (crit_type & 1) ? std::min(std::max(max_count, 0), 100) : 30;
+    const double e = (crit_type & 2) ? std::min(std::max(epsilon, 0.), 10.) : 0.01;
+    P.eps2 = e * e;
+    P.flags = flags;
+    P.min_eig = (float)min_eig;
+    return P;
+}
+
+KltLevels klt_levels_struct(yavo_ctx *ctx, int H, int W, int top) {
+    KltLevels L;
+    memset(&L, 0, sizeof L);
+    L.top = top;
+    for (int l = 0; l <= top; l++) {
+        level_dims(H, W, l, &L.H[l], &L.W[l]);
+        L.img[l] = l == 0 ? ctx->d_frames : ctx->d_pyr + ctx->pyr_off[l];
+        L.slot_stride[l] = l == 0 ? ctx->frame_stride : ctx->pyr_slot_stride;
+        L.pitch[l] = l == 0 ? ctx->pitch : ctx->pyr_pitch[l];
+    }
+    return L;
+}
+
+size_t klt_smem_bytes(int ww, int wh) { return klt_smem_per_warp(ww, wh) * KLT_WARPS; }
+
+int klt_set_smem(yavo_ctx *ctx, size_t bytes) {
+    if (bytes > 48 * 1024)
+        CK(cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -360,6 +490,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     c->slot_rows.assign(n_slots, 0);
     c->slot_cols.assign(n_slots, 0);
     c->slot_blur_valid.assign(n_slots, 0);
+    c->slot_pyr.assign(n_slots, 0);
     ctx = c;
 #define CKC(call)                                                                                      \
     do {                                                                                               \
@@ -420,7 +551,9 @@ void yavo_destroy(yavo_ctx *c) {
                     c->d_bk_id,  c->d_nbk,     c->d_desc,    c->d_midx,     c->d_mdist,    c->d_status, c->d_noob,
                     c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
                     c->d_mo_idx, c->d_mo_dist, c->d_mo_sec,  c->d_part_key, c->d_part_sec, c->d_raw,
-                    c->d_pairs,  c->d_npairs,  c->d_minDist, c->d_spos};
+                    c->d_pairs,  c->d_npairs,  c->d_minDist, c->d_spos,
+                    c->d_pyr,    c->d_klt_prev, c->d_klt_next, c->d_klt_status, c->d_klt_err, c->d_trk_xy,
+                    c->d_trk_status, c->d_trk_err};
     for (void *b : bufs)
         if (b) cudaFree(b);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1000,6 +1133,136 @@ int yavo_set_sub_batch(yavo_ctx *ctx, int frames) {
 int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames) {
     if (!ctx || frames < 0) return YAVO_ERR_INVALID;
     ctx->pipeline_chunk = frames;
+    return 0;
+}
+
+// ---- tracking step (cv::calcOpticalFlowPyrLK, src/LoopHandler.cc:372-375) ------------------------------------
+
+int yavo_build_pyramid(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, int max_level, int *levels) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (int r = klt_check_params(ctx, win_w, win_h, max_level, 0)) return r;
+    if (levels) *levels = 0;
+    if (n == 0) return 0;
+    if (int r = check_uploaded(ctx, slot0, n)) return r;
+    CK(cudaSetDevice(ctx->device));
+    const int top = klt_levels_for(ctx->slot_rows[slot0], ctx->slot_cols[slot0], win_w, win_h, max_level);
+    if (levels) *levels = top;
+    return top > 0 ? launch_pyramid(ctx, slot0, n, top) : 0;
+}
+
+int yavo_pyramid_level(yavo_ctx *ctx, int slot, int level, uint8_t *out, size_t out_bytes, int *rows, int *cols) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (int r = check_uploaded(ctx, slot, 1)) return r;
+    if (level < 1 || level > ctx->slot_pyr[slot])
+        return fail(ctx, YAVO_ERR_STATE, "slot %d holds pyramid levels 1..%d, asked for %d", slot, ctx->slot_pyr[slot], level);
+    int h, w;
+    level_dims(ctx->slot_rows[slot], ctx->slot_cols[slot], level, &h, &w);
+    if (rows) *rows = h;
+    if (cols) *cols = w;
+    if (!out || out_bytes < (size_t)h * w) return fail(ctx, YAVO_ERR_INVALID, "level %d is %dx%d, buffer holds %zu bytes", level, h, w, out_bytes);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpy2DAsync(out, w, ctx->d_pyr + ctx->pyr_slot_stride * slot + ctx->pyr_off[level], ctx->pyr_pitch[level], w, h,
+                         cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int yavo_klt_track(yavo_ctx *ctx, int slot_prev, int slot_next, const float *prev_xy, int n, float *next_xy,
+                   uint8_t *status, float *err, int win_w, int win_h, int max_level, int crit_type, int max_count,
+                   double epsilon, int flags, double min_eig_threshold) {
+    if (int r = check_slot(ctx, slot_prev)) return r;
+    if (int r = check_slot(ctx, slot_next)) return r;
+    if (int r = klt_check_params(ctx, win_w, win_h, max_level, flags)) return r;
+    if (n < 0 || (n > 0 && (!prev_xy || !next_xy || !status))) return fail(ctx, YAVO_ERR_INVALID, "bad point arrays (n=%d)", n);
+    if (n == 0) return 0;
+    if (int r = check_uploaded(ctx, slot_prev, 1)) return r;
+    if (int r = check_uploaded(ctx, slot_next, 1)) return r;
+    if (ctx->slot_rows[slot_prev] != ctx->slot_rows[slot_next] || ctx->slot_cols[slot_prev] != ctx->slot_cols[slot_next])
+        return fail(ctx, YAVO_ERR_INVALID, "slots %d and %d hold frames of different sizes", slot_prev, slot_next);
+    CK(cudaSetDevice(ctx->device));
+    const int H = ctx->slot_rows[slot_prev], W = ctx->slot_cols[slot_prev];
+    const int top = klt_levels_for(H, W, win_w, win_h, max_level);
+    if (top > 0) {
+        if (int r = launch_pyramid(ctx, slot_prev, 1, top)) return r;
+        if (int r = launch_pyramid(ctx, slot_next, 1, top)) return r;
+    } else if (int r = ensure_pyramid_alloc(ctx)) return r;
+    if (n > ctx->klt_cap) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        void *old[] = {ctx->d_klt_prev, ctx->d_klt_next, ctx->d_klt_status, ctx->d_klt_err};
+        for (void *b : old)
+            if (b) CK(cudaFree(b));
+        ctx->d_klt_prev = ctx->d_klt_next = nullptr;
+        ctx->d_klt_status = nullptr;
+        ctx->d_klt_err = nullptr;
+        ctx->klt_cap = 0;
+        const int cap = std::max(n, 4096);
+        CK(dalloc(&ctx->d_klt_prev, cap));
+        CK(dalloc(&ctx->d_klt_next, cap));
+        CK(dalloc(&ctx->d_klt_status, cap));
+        CK(dalloc(&ctx->d_klt_err, cap));
+        ctx->klt_cap = cap;
+    }
+    CK(cudaMemcpyAsync(ctx->d_klt_prev, prev_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (flags & 4) CK(cudaMemcpyAsync(ctx->d_klt_next, next_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    const KltParams P = klt_params(win_w, win_h, crit_type, max_count, epsilon, flags, min_eig_threshold);
+    const KltLevels L = klt_levels_struct(ctx, H, W, top);
+    const size_t smem = klt_smem_bytes(win_w, win_h);
+    if (int r = klt_set_smem(ctx, smem)) return r;
+    dim3 grid((n + KLT_WARPS - 1) / KLT_WARPS, 1);
+    PROF(KC_KLT, klt_track_kernel<<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(
+        L, P, slot_prev, slot_next, ctx->d_klt_prev, nullptr, nullptr, nullptr, n, 0, ctx->d_klt_next, ctx->d_klt_next,
+        ctx->d_klt_status, ctx->d_klt_err));
+    CK_LAUNCH();
+    CK(cudaMemcpyAsync(next_xy, ctx->d_klt_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(status, ctx->d_klt_status, n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (err) CK(cudaMemcpyAsync(err, ctx->d_klt_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int yavo_klt_track_batch(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, int max_level, int crit_type,
+                         int max_count, double epsilon, int flags, double min_eig_threshold) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (int r = klt_check_params(ctx, win_w, win_h, max_level, flags)) return r;
+    if (flags & 4) return fail(ctx, YAVO_ERR_INVALID, "the batch form starts from the keypoints themselves (no OPTFLOW_USE_INITIAL_FLOW)");
+    if (n < 2) return 0;
+    if (int r = check_uploaded(ctx, slot0, n)) return r;
+    CK(cudaSetDevice(ctx->device));
+    const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
+    const int top = klt_levels_for(H, W, win_w, win_h, max_level);
+    if (top > 0) {
+        if (int r = launch_pyramid(ctx, slot0, n, top)) return r;
+    } else if (int r = ensure_pyramid_alloc(ctx)) return r;
+    if (!ctx->d_trk_xy) {
+        const size_t S = (size_t)ctx->n_slots * ctx->max_kp;
+        CK(dalloc(&ctx->d_trk_xy, S));
+        CK(dalloc(&ctx->d_trk_status, S));
+        CK(dalloc(&ctx->d_trk_err, S));
+    }
+    const KltParams P = klt_params(win_w, win_h, crit_type, max_count, epsilon, flags, min_eig_threshold);
+    const KltLevels L = klt_levels_struct(ctx, H, W, top);
+    const size_t smem = klt_smem_bytes(win_w, win_h);
+    if (int r = klt_set_smem(ctx, smem)) return r;
+    dim3 grid((ctx->max_kp + KLT_WARPS - 1) / KLT_WARPS, n - 1);
+    const size_t o = (size_t)slot0 * ctx->max_kp;
+    // keypoint arrays and counts are indexed by absolute slot inside the kernel; outputs by pair from `o`
+    PROF(KC_KLT, klt_track_kernel<<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(
+        L, P, slot0, slot0 + 1, nullptr, ctx->d_kp_row, ctx->d_kp_col, ctx->d_nkp, 0, ctx->max_kp, nullptr,
+        ctx->d_trk_xy + o, ctx->d_trk_status + o, ctx->d_trk_err + o));
+    CK_LAUNCH();
+    return 0;
+}
+
+int yavo_klt_fetch(yavo_ctx *ctx, int slot0, int n, float *next_xy, uint8_t *status, float *err) {
+    if (int r = check_slot(ctx, slot0, n)) return r;
+    if (n == 0) return 0;
+    if (!ctx->d_trk_xy) return fail(ctx, YAVO_ERR_STATE, "yavo_klt_track_batch has not run");
+    CK(cudaSetDevice(ctx->device));
+    const size_t o = (size_t)slot0 * ctx->max_kp, cnt = (size_t)n * ctx->max_kp;
+    if (next_xy) CK(cudaMemcpyAsync(next_xy, ctx->d_trk_xy + o, sizeof(float2) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (status) CK(cudaMemcpyAsync(status, ctx->d_trk_status + o, cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (err) CK(cudaMemcpyAsync(err, ctx->d_trk_err + o, sizeof(float) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 
