@@ -167,3 +167,40 @@ def test_argument_errors(ctx, cuda_lib, kitti):
     assert nxt.shape == (0, 2)
     with pytest.raises(cuda_lib.YavoError):
         ctx.pyramid_level(0, 7)                     # level never built
+
+
+def test_python_mirror_reads_like_the_cv2_call(gold, images):
+    """ya_vo_b200.tracking.calcOpticalFlowPyrLK with the reference's arguments (src/LoopHandler.cc:372-375)."""
+    from ya_vo_b200 import tracking as tr
+    a, b = images["kitti"]
+    key = "kitti_fast_c0"
+    nextPts, status, err = tr.calcOpticalFlowPyrLK(a, b, gold[key + "_pts"], None, winSize=(11, 11), maxLevel=3,
+                                                   criteria=(tr.TERM_CRITERIA_COUNT + tr.TERM_CRITERIA_EPS, 30, 0.01),
+                                                   flags=0, minEigThreshold=0.001)
+    assert nextPts.shape == (2000, 2) and status.shape == (2000, 1) and err.shape == (2000, 1)
+    check_case(gold, key, nextPts, status.ravel(), err.ravel())
+    p3 = gold[key + "_pts"][:10].reshape(10, 1, 2)
+    n3, s3, e3 = tr.calcOpticalFlowPyrLK(a, b, p3, None, winSize=(11, 11), maxLevel=3, minEigThreshold=0.001)
+    assert n3.shape == (10, 1, 2) and np.array_equal(n3.reshape(10, 2), nextPts[:10])
+
+
+def test_cpp_drop_in_tracks_like_opencv(cuda_lib, gold, images, tmp_path):
+    """yavo::calcOpticalFlowPyrLK (ya_vo_b200/host/include/Tracking.hpp) on the FAST keypoints of the KITTI frame:
+    the same points and parameters as fixture case kitti_fast_c0, so the answer is cv2's."""
+    import os
+    import subprocess
+    host = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ya_vo_b200", "host")
+    subprocess.check_call(["make", "-C", host, "-s"])
+    a, b = images["kitti"]
+    pa, pb, out = (tmp_path / n for n in ("a.bin", "b.bin", "out.bin"))
+    a.tofile(pa)
+    b.tofile(pb)
+    r = subprocess.run([os.path.join(host, "host_tests"), "track", str(pa), str(pb), str(a.shape[0]), str(a.shape[1]), str(out)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    buf = open(out, "rb").read()
+    n = int(np.frombuffer(buf, "<i4", 1)[0])
+    rec = np.frombuffer(buf, np.dtype([("px", "<f4"), ("py", "<f4"), ("nx", "<f4"), ("ny", "<f4"), ("err", "<f4"), ("st", "<i4")]), n, 4)
+    key = "kitti_fast_c0"
+    assert n == 2000 and np.array_equal(np.stack([rec["px"], rec["py"]], 1), gold[key + "_pts"])
+    check_case(gold, key, np.stack([rec["nx"], rec["ny"]], 1).copy(), rec["st"].astype(np.uint8), rec["err"].copy())

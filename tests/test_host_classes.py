@@ -42,6 +42,10 @@ def test_headers_keep_reference_signatures():
                 "void removeOutliers(std::vector<Matches> &matches, std::vector<Matches> &newMatches, int threshold)",
                 "int hammingDistance(uchar featVec1[32], uchar featVec2[32])", "uchar featVec[32]"):
         assert sig in br, sig
+    tk = open(os.path.join(HOST, "include", "Tracking.hpp")).read()
+    for sig in ("void calcOpticalFlowPyrLK(const cv::Mat &prevImg, const cv::Mat &nextImg, const std::vector<cv::Point2f> &prevPts,",
+                "cv::Size winSize = cv::Size(21, 21), int maxLevel = 3", "int flags = 0, double minEigThreshold = 1e-4"):
+        assert sig in tk, sig
     for sig in ("Image(const cv::Mat &img)", "cv::Mat rawImage", "std::vector<KeyPoint> keypoints",
                 "uint8_t getPixelVal(int i, int j) const"):
         assert sig in im, sig

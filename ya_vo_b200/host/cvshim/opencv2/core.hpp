@@ -56,6 +56,14 @@ struct Size {
     Size(int w, int h) : width(w), height(h) {}
 };
 
+struct TermCriteria {  // cv::TermCriteria (type: COUNT = 1, EPS = 2)
+    enum Type { COUNT = 1, MAX_ITER = COUNT, EPS = 2 };
+    int type, maxCount;
+    double epsilon;
+    TermCriteria() : type(0), maxCount(0), epsilon(0) {}
+    TermCriteria(int t, int c, double e) : type(t), maxCount(c), epsilon(e) {}
+};
+
 struct Scalar {
     double val[4];
     Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }

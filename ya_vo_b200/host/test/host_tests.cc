@@ -20,6 +20,7 @@
 
 #include "../include/BriefDescriptor.hpp"
 #include "../include/FastDetector.hpp"
+#include "../include/Tracking.hpp"
 #include "../include/Image.hpp"
 #include "../include/yavo_device.hpp"
 
@@ -187,14 +188,58 @@ static int pipeline(char **a) {
     return g_fail ? 1 : 0;
 }
 
+// LoopHandler::trackLastFrame's OpenCV call (src/LoopHandler.cc:372-375) through yavo::calcOpticalFlowPyrLK:
+// the FAST keypoints of frame A, swapped to (x = col, y = row) as the reference does at :343-347, tracked into B.
+static int track(char **a) {
+    const int H = std::atoi(a[2]), W = std::atoi(a[3]);
+    std::vector<uint8_t> A = slurp(a[0]), B = slurp(a[1]);
+    if ((int)A.size() != H * W || (int)B.size() != H * W) {
+        std::printf("bad inputs\n");
+        return 2;
+    }
+    cv::Mat m1(H, W, CV_8UC1, A.data()), m2(H, W, CV_8UC1, B.data());
+    Image lastFrame(m1), currentFrame(m2);
+    FastDetector fd(12, 50);
+    auto features = fd.getFastFeatures(lastFrame);
+    std::vector<cv::Point2f> lastFrameKpt, currFrameKpt;
+    for (auto &p : features) lastFrameKpt.push_back(cv::Point2f((float)p.y, (float)p.x));
+    std::vector<uchar> flowStatus;
+    std::vector<float> error;
+    yavo::calcOpticalFlowPyrLK(lastFrame, currentFrame, lastFrameKpt, currFrameKpt, flowStatus, error, cv::Size(11, 11), 3,
+                               cv::TermCriteria(cv::TermCriteria::COUNT + cv::TermCriteria::EPS, 30, 0.01), 0, 0.001);
+    // the cv::Mat form (what the reference passes) must agree
+    std::vector<cv::Point2f> again;
+    std::vector<uchar> st2;
+    std::vector<float> er2;
+    yavo::calcOpticalFlowPyrLK(lastFrame.rawImage, currentFrame.rawImage, lastFrameKpt, again, st2, er2, cv::Size(11, 11), 3,
+                               cv::TermCriteria(cv::TermCriteria::COUNT + cv::TermCriteria::EPS, 30, 0.01), 0, 0.001);
+    EXPECT_EQ(again.size(), currFrameKpt.size());
+    for (size_t i = 0; i < again.size(); i++) {
+        EXPECT_TRUE(again[i] == currFrameKpt[i]);
+        EXPECT_EQ((int)st2[i], (int)flowStatus[i]);
+    }
+    std::ofstream f(a[4], std::ios::binary);
+    put<int32_t>(f, (int32_t)lastFrameKpt.size());
+    for (size_t i = 0; i < lastFrameKpt.size(); i++) {
+        put<float>(f, lastFrameKpt[i].x); put<float>(f, lastFrameKpt[i].y);
+        put<float>(f, currFrameKpt[i].x); put<float>(f, currFrameKpt[i].y);
+        put<float>(f, error[i]); put<int32_t>(f, (int32_t)flowStatus[i]);
+    }
+    f.close();
+    yavo_host::Device::shutdown();
+    std::printf("track: %zu points (%d failures)\n", lastFrameKpt.size(), g_fail);
+    return g_fail ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
     try {
         if (argc == 3 && !std::strcmp(argv[1], "known")) return known(argv[2]);
         if (argc == 8 && !std::strcmp(argv[1], "pipeline")) return pipeline(argv + 2);
+        if (argc == 7 && !std::strcmp(argv[1], "track")) return track(argv + 2);
     } catch (const std::exception &e) {
         std::printf("exception: %s\n", e.what());
         return 3;
     }
-    std::printf("usage: host_tests known <bres.bin> | pipeline <A.bin> <B.bin> <H> <W> <offsets.bin> <out.bin>\n");
+    std::printf("usage: host_tests known <bres.bin> | pipeline <A.bin> <B.bin> <H> <W> <offsets.bin> <out.bin> | track <A.bin> <B.bin> <H> <W> <out.bin>\n");
     return 2;
 }
