@@ -83,37 +83,53 @@ __device__ __forceinline__ KltW klt_weights(float a, float b) {  // 14-bit bilin
     return w;
 }
 
-// Ordered float accumulation of one row-major int16 plane product, as OpenCV's SIMD loop does it:
-// lane role k (0..3) owns columns k and k+4 of every group of 8; role 4 owns the tail columns.
-// MODE 0: (float)a * (float)b summed (gradient matrix: float products);  MODE 1: int pair sums / int tail
-// products converted to float (mismatch vector).
-template <int MODE>
-__device__ __forceinline__ float klt_chain(const int16_t *__restrict__ A, const int16_t *__restrict__ B, int ww, int wh,
-                                           int role) {
+// Ordered float accumulation as OpenCV's 128-bit SIMD loops do it.  Columns are taken in groups of 8: accumulator
+// k (0..3) owns columns k and k+4 of every group; the columns past the last full group go to a scalar "tail"
+// accumulator in scan order.  The result is tail + ((q0 + q2) + (q1 + q3)) (v_reduce_sum).
+// Gradient matrix: the terms are float products (exact: |gradient| <= 4080), added one by one.
+__device__ __forceinline__ float klt_chain_f(const float *__restrict__ T, int ww, int wh, int role) {
     const int vec = ww & ~7;
     float acc = 0.f;
     if (role < 4) {
+#pragma unroll
         for (int y = 0; y < wh; y++) {
-            const int16_t *a = A + y * ww, *b = B + y * ww;
-            for (int g = role; g < vec; g += 8) {
-                if (MODE == 0) {
-                    acc = __fadd_rn(__fmul_rn((float)a[g], (float)b[g]), acc);
-                    acc = __fadd_rn(__fmul_rn((float)a[g + 4], (float)b[g + 4]), acc);
-                } else {
-                    acc = __fadd_rn(acc, __int2float_rn((int)a[g] * (int)b[g] + (int)a[g + 4] * (int)b[g + 4]));
-                }
+#pragma unroll
+            for (int g = 0; g < vec; g += 8) {
+                acc = __fadd_rn(T[y * ww + g + role], acc);
+                acc = __fadd_rn(T[y * ww + g + role + 4], acc);
             }
         }
     } else {
+#pragma unroll
         for (int y = 0; y < wh; y++) {
-            const int16_t *a = A + y * ww, *b = B + y * ww;
-            for (int x = vec; x < ww; x++) acc = __fadd_rn(acc, __int2float_rn((int)a[x] * (int)b[x]));
+#pragma unroll
+            for (int x = vec; x < ww; x++) acc = __fadd_rn(acc, T[y * ww + x]);
+        }
+    }
+    return acc;
+}
+// Mismatch vector: the int32 products of columns (x, x+4) are added as integers, converted to float and
+// accumulated; tail products are converted one by one.
+__device__ __forceinline__ float klt_chain_i(const int *__restrict__ Q, int ww, int wh, int role) {
+    const int vec = ww & ~7;
+    float acc = 0.f;
+    if (role < 4) {
+#pragma unroll
+        for (int y = 0; y < wh; y++) {
+#pragma unroll
+            for (int g = 0; g < vec; g += 8) acc = __fadd_rn(acc, __int2float_rn(Q[y * ww + g + role] + Q[y * ww + g + role + 4]));
+        }
+    } else {
+#pragma unroll
+        for (int y = 0; y < wh; y++) {
+#pragma unroll
+            for (int x = vec; x < ww; x++) acc = __fadd_rn(acc, __int2float_rn(Q[y * ww + x]));
         }
     }
     return acc;
 }
 
-// tail + ((q0 + q2) + (q1 + q3)) with q_k in lanes base..base+3 and the tail in lane base_tail (v_reduce_sum order)
+// tail + ((q0 + q2) + (q1 + q3)) with q_k in lanes base..base+3 and the tail in lane tail_lane
 __device__ __forceinline__ float klt_combine(float v, int base, int tail_lane) {
     const float q0 = __shfl_sync(0xffffffffu, v, base), q1 = __shfl_sync(0xffffffffu, v, base + 1);
     const float q2 = __shfl_sync(0xffffffffu, v, base + 2), q3 = __shfl_sync(0xffffffffu, v, base + 3);
@@ -121,25 +137,45 @@ __device__ __forceinline__ float klt_combine(float v, int base, int tail_lane) {
     return __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
 }
 
+// per-warp shared memory: I / Ix / Iy window samples (int16), a 12-byte-per-pixel region holding the three float
+// term planes of the gradient matrix and later the two int product planes of the mismatch vector, the staged raw
+// patch (u8, reused for the patches of the next frame) and the derivative patch (short2)
 __host__ __device__ __forceinline__ size_t klt_smem_per_warp(int ww, int wh) {
     const size_t area = (size_t)ww * wh;
-    size_t b = 4 * ((area * 2 + 3) & ~size_t(3));                        // Iw, Ix, Iy, diff (int16)
-    b += ((size_t)(ww + 3) * (wh + 3) + 3) & ~size_t(3);                 // raw patch / J patch (u8)
-    b += (size_t)(ww + 1) * (wh + 1) * 4;                                // derivative patch (short2)
+    size_t b = 3 * ((area * 2 + 3) & ~size_t(3));
+    b += 12 * area;
+    b += ((size_t)(ww + 3) * (wh + 3) + 3) & ~size_t(3);
+    b += (size_t)(ww + 1) * (wh + 1) * 4;
     return b;
 }
 
-// Staged (wh+1) x (ww+1) patch of image `im` with origin (oy, ox), REFLECT_101 outside the image.
-__device__ __forceinline__ void klt_stage_patch(uint8_t *dst, const uint8_t *im, int pitch, int H, int W, int oy, int ox,
-                                                int ph, int pw, int lane) {
-    const bool inside = oy >= 0 && ox >= 0 && oy + ph <= H && ox + pw <= W;
-    for (int p = lane; p < ph * pw; p += 32) {
-        const int r = p / pw, c = p - r * pw;
-        const int yy = inside ? oy + r : klt_refl(oy + r, H), xx = inside ? ox + c : klt_refl(ox + c, W);
-        dst[p] = __ldg(im + (size_t)yy * pitch + xx);
+// Staged ph x pw patch of image `im` with origin (oy, ox), REFLECT_101 outside the image.
+__device__ __forceinline__ void klt_stage_patch(uint8_t *dst, const uint8_t *__restrict__ im, int pitch, int H, int W, int oy,
+                                                int ox, int ph, int pw, int lane) {
+    if (oy >= 0 && ox >= 0 && oy + ph <= H && ox + pw <= W) {
+        const uint8_t *src = im + (size_t)oy * pitch + ox;
+#pragma unroll
+        for (int p = lane; p < ph * pw; p += 32) {
+            const int r = p / pw, c = p - r * pw;
+            dst[p] = __ldg(src + r * pitch + c);
+        }
+    } else {
+#pragma unroll
+        for (int p = lane; p < ph * pw; p += 32) {
+            const int r = p / pw, c = p - r * pw;
+            dst[p] = __ldg(im + (size_t)klt_refl(oy + r, H) * pitch + klt_refl(ox + c, W));
+        }
     }
 }
 
+// bilinear sample of the staged next-frame patch minus the stored previous-frame sample (5 fractional bits)
+__device__ __forceinline__ int klt_diff(const uint8_t *q, int gw, const KltW &w, int iv) {
+    return ((q[0] * w.w00 + q[1] * w.w01 + q[gw] * w.w10 + q[gw + 1] * w.w11 + (1 << 8)) >> 9) - iv;
+}
+
+// CW x CH = compile-time window (0 = taken from P at run time): the reference's 11 x 11 gets constant trip counts,
+// divisions by constants and fully unrolled accumulation chains.
+template <int CW, int CH>
 __global__ void __launch_bounds__(KLT_WARPS * 32)
 klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
                  const float2 *__restrict__ prev_xy,                                  // explicit points, or
@@ -153,13 +189,16 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
     const int pt = blockIdx.x * KLT_WARPS + warp;
     const int n = n_all ? n_all[prev_slot0 + pair] : n_fixed;
     if (pt >= n) return;
-    const int ww = P.ww, wh = P.wh, area = ww * wh;
+    const int ww = CW ? CW : P.ww, wh = CH ? CH : P.wh, area = ww * wh;
+    const int rw = ww + 3, gw = ww + 1;
     const size_t plane = ((size_t)area * 2 + 3) & ~size_t(3);
     uint8_t *base = klt_smem + (size_t)warp * klt_smem_per_warp(ww, wh);
     int16_t *sI = reinterpret_cast<int16_t *>(base), *sIx = reinterpret_cast<int16_t *>(base + plane),
-            *sIy = reinterpret_cast<int16_t *>(base + 2 * plane), *sD = reinterpret_cast<int16_t *>(base + 3 * plane);
-    uint8_t *sR = base + 4 * plane;
-    short2 *sG = reinterpret_cast<short2 *>(sR + (((size_t)(ww + 3) * (wh + 3) + 3) & ~size_t(3)));
+            *sIy = reinterpret_cast<int16_t *>(base + 2 * plane);
+    float *sT = reinterpret_cast<float *>(base + 3 * plane);   // T11 | T12 | T22
+    int *sQ = reinterpret_cast<int *>(sT);                      // Q1 | Q2 (after the gradient matrix is done)
+    uint8_t *sR = base + 3 * plane + 12 * (size_t)area;
+    short2 *sG = reinterpret_cast<short2 *>(sR + (((size_t)rw * (wh + 3) + 3) & ~size_t(3)));
 
     const size_t o = (size_t)pair * pts_stride + pt;
     float2 p0;
@@ -168,6 +207,7 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
                           (float)kp_row[(size_t)(prev_slot0 + pair) * pts_stride + pt]);
     const float halfx = __fmul_rn((float)(ww - 1), 0.5f), halfy = __fmul_rn((float)(wh - 1), 0.5f);
     const bool use_initial = (P.flags & 4) != 0, get_min_eig = (P.flags & 8) != 0;
+    const float FLT_SCALE = 1.f / (1 << 20);
     float outx = 0.f, outy = 0.f, ev = 0.f;
     bool st = true;
 
@@ -207,14 +247,15 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
 
         // ---- raw patch rows iy-1 .. iy+wh+1, cols ix-1 .. ix+ww+1 of the previous frame ----------------
         __syncwarp();
-        klt_stage_patch(sR, I, pitch, H, W, iy - 1, ix - 1, wh + 3, ww + 3, lane);
+        klt_stage_patch(sR, I, pitch, H, W, iy - 1, ix - 1, wh + 3, rw, lane);
         __syncwarp();
-        const int rw = ww + 3, gw = ww + 1;
         // Scharr (dx, dy) at window positions (iy + r, ix + c), r <= wh, c <= ww; zero outside the image
+        const bool all_in = iy >= 0 && ix >= 0 && iy + wh < H && ix + ww < W;
+#pragma unroll
         for (int p = lane; p < (wh + 1) * gw; p += 32) {
             const int r = p / gw, c = p - r * gw;
             short2 g = make_short2(0, 0);
-            if (iy + r >= 0 && iy + r < H && ix + c >= 0 && ix + c < W) {
+            if (all_in || (iy + r >= 0 && iy + r < H && ix + c >= 0 && ix + c < W)) {
                 const uint8_t *q0 = sR + r * rw + c, *q1 = q0 + rw, *q2 = q1 + rw;
                 const int t0a = (q0[0] + q2[0]) * 3 + q1[0] * 10, t0c = (q0[2] + q2[2]) * 3 + q1[2] * 10;
                 const int t1a = q2[0] - q0[0], t1b = q2[1] - q0[1], t1c = q2[2] - q0[2];
@@ -224,7 +265,8 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
             sG[p] = g;
         }
         __syncwarp();
-        // bilinear samples of the patch and its derivatives
+        // bilinear samples of the patch and its derivatives; float terms of the gradient matrix
+#pragma unroll
         for (int p = lane; p < area; p += 32) {
             const int y = p / ww, x = p - y * ww;
             const uint8_t *q = sR + (y + 1) * rw + (x + 1);
@@ -235,18 +277,16 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
             sI[p] = (int16_t)iv;
             sIx[p] = (int16_t)gx;
             sIy[p] = (int16_t)gy;
+            const float fx = (float)gx, fy = (float)gy;
+            sT[p] = __fmul_rn(fx, fx);
+            sT[area + p] = __fmul_rn(fx, fy);
+            sT[2 * area + p] = __fmul_rn(fy, fy);
         }
         __syncwarp();
         // gradient matrix: lanes 0-3 A11, 4-7 A12, 8-11 A22 lane accumulators; 12-14 their tails
         float v = 0.f;
-        if (lane < 12) {
-            const int s = lane >> 2;
-            v = klt_chain<0>(s == 2 ? sIy : sIx, s == 0 ? sIx : sIy, ww, wh, lane & 3);
-        } else if (lane < 15) {
-            const int s = lane - 12;
-            v = klt_chain<0>(s == 2 ? sIy : sIx, s == 0 ? sIx : sIy, ww, wh, 4);
-        }
-        const float FLT_SCALE = 1.f / (1 << 20);
+        if (lane < 12) v = klt_chain_f(sT + (lane >> 2) * area, ww, wh, lane & 3);
+        else if (lane < 15) v = klt_chain_f(sT + (lane - 12) * area, ww, wh, 4);
         const float A11 = __fmul_rn(klt_combine(v, 0, 12), FLT_SCALE), A12 = __fmul_rn(klt_combine(v, 4, 13), FLT_SCALE),
                     A22 = __fmul_rn(klt_combine(v, 8, 14), FLT_SCALE);
         float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -272,16 +312,17 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
             __syncwarp();
             klt_stage_patch(sR, J, pitch, H, W, jy, jx, wh + 1, gw, lane);
             __syncwarp();
+#pragma unroll
             for (int p = lane; p < area; p += 32) {
                 const int y = p / ww, x = p - y * ww;
-                const uint8_t *q = sR + y * gw + x;
-                const int jv = (q[0] * w.w00 + q[1] * w.w01 + q[gw] * w.w10 + q[gw + 1] * w.w11 + (1 << 8)) >> 9;
-                sD[p] = (int16_t)(jv - sI[p]);
+                const int d = klt_diff(sR + y * gw + x, gw, w, sI[p]);
+                sQ[p] = d * sIx[p];
+                sQ[area + p] = d * sIy[p];
             }
             __syncwarp();
             float u = 0.f;
-            if (lane < 8) u = klt_chain<1>(sD, (lane >> 2) ? sIy : sIx, ww, wh, lane & 3);
-            else if (lane < 10) u = klt_chain<1>(sD, (lane - 8) ? sIy : sIx, ww, wh, 4);
+            if (lane < 8) u = klt_chain_i(sQ + (lane >> 2) * area, ww, wh, lane & 3);
+            else if (lane < 10) u = klt_chain_i(sQ + (lane - 8) * area, ww, wh, 4);
             const float b1 = __fmul_rn(klt_combine(u, 0, 8), FLT_SCALE), b2 = __fmul_rn(klt_combine(u, 4, 9), FLT_SCALE);
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
@@ -311,11 +352,10 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
             klt_stage_patch(sR, J, pitch, H, W, jy, jx, wh + 1, gw, lane);
             __syncwarp();
             int e = 0;
+#pragma unroll
             for (int p = lane; p < area; p += 32) {
                 const int y = p / ww, x = p - y * ww;
-                const uint8_t *q = sR + y * gw + x;
-                const int jv = (q[0] * w.w00 + q[1] * w.w01 + q[gw] * w.w10 + q[gw + 1] * w.w11 + (1 << 8)) >> 9;
-                e += abs(jv - sI[p]);
+                e += abs(klt_diff(sR + y * gw + x, gw, w, sI[p]));
             }
 #pragma unroll
             for (int s = 16; s; s >>= 1) e += __shfl_xor_sync(0xffffffffu, e, s);

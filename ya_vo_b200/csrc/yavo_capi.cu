@@ -446,11 +446,24 @@ KltLevels klt_levels_struct(yavo_ctx *ctx, int H, int W, int top) {
     return L;
 }
 
-size_t klt_smem_bytes(int ww, int wh) { return klt_smem_per_warp(ww, wh) * KLT_WARPS; }
-
-int klt_set_smem(yavo_ctx *ctx, size_t bytes) {
-    if (bytes > 48 * 1024)
-        CK(cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+// one launch of K8; the reference's 11 x 11 window (and OpenCV's default 21 x 21) run the specialised instances
+int launch_klt(yavo_ctx *ctx, dim3 grid, const KltLevels &L, const KltParams &P, int prev_slot0, int next_slot0,
+               const float2 *prev_xy, const int32_t *kp_row, const int32_t *kp_col, const int *n_all, int n_fixed,
+               int pts_stride, const float2 *init_xy, float2 *next_xy, uint8_t *status, float *err) {
+    const size_t smem = klt_smem_per_warp(P.ww, P.wh) * KLT_WARPS;
+#define KLT_LAUNCH(CW, CH)                                                                                              \
+    do {                                                                                                                \
+        if (smem > 48 * 1024)                                                                                           \
+            CK(cudaFuncSetAttribute(klt_track_kernel<CW, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        PROF(KC_KLT, klt_track_kernel<CW, CH><<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(                             \
+                         L, P, prev_slot0, next_slot0, prev_xy, kp_row, kp_col, n_all, n_fixed, pts_stride, init_xy,    \
+                         next_xy, status, err));                                                                        \
+    } while (0)
+    if (P.ww == 11 && P.wh == 11) KLT_LAUNCH(11, 11);
+    else if (P.ww == 21 && P.wh == 21) KLT_LAUNCH(21, 21);
+    else KLT_LAUNCH(0, 0);
+#undef KLT_LAUNCH
+    CK_LAUNCH();
     return 0;
 }
 
@@ -1206,13 +1219,10 @@ int yavo_klt_track(yavo_ctx *ctx, int slot_prev, int slot_next, const float *pre
     if (flags & 4) CK(cudaMemcpyAsync(ctx->d_klt_next, next_xy, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
     const KltParams P = klt_params(win_w, win_h, crit_type, max_count, epsilon, flags, min_eig_threshold);
     const KltLevels L = klt_levels_struct(ctx, H, W, top);
-    const size_t smem = klt_smem_bytes(win_w, win_h);
-    if (int r = klt_set_smem(ctx, smem)) return r;
     dim3 grid((n + KLT_WARPS - 1) / KLT_WARPS, 1);
-    PROF(KC_KLT, klt_track_kernel<<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(
-        L, P, slot_prev, slot_next, ctx->d_klt_prev, nullptr, nullptr, nullptr, n, 0, ctx->d_klt_next, ctx->d_klt_next,
-        ctx->d_klt_status, ctx->d_klt_err));
-    CK_LAUNCH();
+    if (int r = launch_klt(ctx, grid, L, P, slot_prev, slot_next, ctx->d_klt_prev, nullptr, nullptr, nullptr, n, 0,
+                           ctx->d_klt_next, ctx->d_klt_next, ctx->d_klt_status, ctx->d_klt_err))
+        return r;
     CK(cudaMemcpyAsync(next_xy, ctx->d_klt_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(status, ctx->d_klt_status, n, cudaMemcpyDeviceToHost, ctx->stream));
     if (err) CK(cudaMemcpyAsync(err, ctx->d_klt_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1241,16 +1251,11 @@ int yavo_klt_track_batch(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, 
     }
     const KltParams P = klt_params(win_w, win_h, crit_type, max_count, epsilon, flags, min_eig_threshold);
     const KltLevels L = klt_levels_struct(ctx, H, W, top);
-    const size_t smem = klt_smem_bytes(win_w, win_h);
-    if (int r = klt_set_smem(ctx, smem)) return r;
     dim3 grid((ctx->max_kp + KLT_WARPS - 1) / KLT_WARPS, n - 1);
     const size_t o = (size_t)slot0 * ctx->max_kp;
     // keypoint arrays and counts are indexed by absolute slot inside the kernel; outputs by pair from `o`
-    PROF(KC_KLT, klt_track_kernel<<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(
-        L, P, slot0, slot0 + 1, nullptr, ctx->d_kp_row, ctx->d_kp_col, ctx->d_nkp, 0, ctx->max_kp, nullptr,
-        ctx->d_trk_xy + o, ctx->d_trk_status + o, ctx->d_trk_err + o));
-    CK_LAUNCH();
-    return 0;
+    return launch_klt(ctx, grid, L, P, slot0, slot0 + 1, nullptr, ctx->d_kp_row, ctx->d_kp_col, ctx->d_nkp, 0, ctx->max_kp,
+                      nullptr, ctx->d_trk_xy + o, ctx->d_trk_status + o, ctx->d_trk_err + o);
 }
 
 int yavo_klt_fetch(yavo_ctx *ctx, int slot0, int n, float *next_xy, uint8_t *status, float *err) {
