@@ -100,6 +100,7 @@ int yavo_oracle_pipeline(const uint8_t *frames, int F, int H, int W, const int32
 void yavo_oracle_pyr_down(const uint8_t *img, int H, int W, uint8_t *out /* ((H+1)/2) x ((W+1)/2) */);
 void yavo_oracle_scharr(const uint8_t *img, int H, int W, int16_t *dx, int16_t *dy);
 int yavo_oracle_klt_levels(int H, int W, int win_w, int win_h, int max_level);
+long long yavo_oracle_klt_iterations(void); /* Newton steps taken by the last yavo_oracle_klt call */
 int yavo_oracle_klt(const uint8_t *prev, const uint8_t *next, int H, int W, const float *prev_xy, int n, float *next_xy,
                     uint8_t *status, float *err, int win_w, int win_h, int max_level, int crit_type, int max_count,
                     double epsilon, int flags, double min_eig_threshold);

@@ -106,9 +106,13 @@ inline int der(const std::vector<int16_t> &d, int H, int W, int y, int x) {  // 
     return (y >= 0 && y < H && x >= 0 && x < W) ? d[(size_t)y * W + x] : 0;
 }
 
+long long g_iterations = 0;  // Newton steps of the last yavo_oracle_klt call (workload statistics for the benchmarks)
+
 }  // namespace
 
 extern "C" {
+
+long long yavo_oracle_klt_iterations(void) { return g_iterations; }
 
 
 void yavo_oracle_pyr_down(const uint8_t *img, int H, int W, uint8_t *out) { pyr_down(img, H, W, out); }
@@ -137,6 +141,7 @@ int yavo_oracle_klt(const uint8_t *prev, const uint8_t *next, int H, int W, cons
     else epsilon = std::min(std::max(epsilon, 0.), 10.);
     epsilon *= epsilon;
     const bool use_initial = (flags & 4) != 0, get_min_eig = (flags & 8) != 0;
+    g_iterations = 0;
 
     const int levels = yavo_oracle_klt_levels(H, W, win_w, win_h, max_level);
     std::vector<Level> pyr(levels + 1);
@@ -247,6 +252,7 @@ int yavo_oracle_klt(const uint8_t *prev, const uint8_t *next, int H, int W, cons
                     break;
                 }
                 w = weights(nx - jx, ny - jy);
+                g_iterations++;
                 float qb0[4] = {0, 0, 0, 0}, qb1[4] = {0, 0, 0, 0}, tb1 = 0, tb2 = 0;
                 const int vecB = (win_w / 8) * 8;
                 for (int y = 0; y < win_h; y++) {

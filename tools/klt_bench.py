@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=32)
     args = ap.parse_args()
     B = args.batch
+    if os.environ.get("YAVO_REBUILD"):
+        capi.build(force=True)  # tuning runs: YAVO_NVCC_EXTRA=-D... YAVO_REBUILD=1
     frames = np.empty((B, H, W), np.uint8)
     frames[0] = synth.synth_frame(args.kind, 500, H, W)
     for f in range(1, B):

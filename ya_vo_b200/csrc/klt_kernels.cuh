@@ -108,23 +108,18 @@ __device__ __forceinline__ float klt_chain_f(const float *__restrict__ T, int ww
     }
     return acc;
 }
-// Mismatch vector: the int32 products of columns (x, x+4) are added as integers, converted to float and
-// accumulated; tail products are converted one by one.
-__device__ __forceinline__ float klt_chain_i(const int *__restrict__ Q, int ww, int wh, int role) {
-    const int vec = ww & ~7;
+// Mismatch vector: the terms arrive as one contiguous float list per accumulator, already in accumulation order
+// (pair sums of columns (x, x+4) added as int32 and converted, tail products converted one by one), so a chain is
+// 128-bit loads plus dependent adds.  `cnt` terms, list 16-byte aligned, padding never added.
+__device__ __forceinline__ float klt_chain_list(const float *__restrict__ F, int cnt) {
     float acc = 0.f;
-    if (role < 4) {
 #pragma unroll
-        for (int y = 0; y < wh; y++) {
-#pragma unroll
-            for (int g = 0; g < vec; g += 8) acc = __fadd_rn(acc, __int2float_rn(Q[y * ww + g + role] + Q[y * ww + g + role + 4]));
-        }
-    } else {
-#pragma unroll
-        for (int y = 0; y < wh; y++) {
-#pragma unroll
-            for (int x = vec; x < ww; x++) acc = __fadd_rn(acc, __int2float_rn(Q[y * ww + x]));
-        }
+    for (int i = 0; i < cnt; i += 4) {
+        const float4 v = *reinterpret_cast<const float4 *>(F + i);
+        acc = __fadd_rn(acc, v.x);
+        if (i + 1 < cnt) acc = __fadd_rn(acc, v.y);
+        if (i + 2 < cnt) acc = __fadd_rn(acc, v.z);
+        if (i + 3 < cnt) acc = __fadd_rn(acc, v.w);
     }
     return acc;
 }
@@ -137,16 +132,21 @@ __device__ __forceinline__ float klt_combine(float v, int base, int tail_lane) {
     return __fadd_rn(t, __fadd_rn(__fadd_rn(q0, q2), __fadd_rn(q1, q3)));
 }
 
-// per-warp shared memory: I / Ix / Iy window samples (int16), a 12-byte-per-pixel region holding the three float
-// term planes of the gradient matrix and later the two int product planes of the mismatch vector, the staged raw
-// patch (u8, reused for the patches of the next frame) and the derivative patch (short2)
+// per-warp shared memory: I / Ix / Iy window samples (int16); a region holding the three float term planes of the
+// gradient matrix and later the term lists of the mismatch vector; the staged raw patch (u8, reused for the patches
+// of the next frame); the derivative patch (short2)
+// term lists of the mismatch vector: 8 lane accumulators (b1: 0-3, b2: 4-7) of LV floats, then two tails of LT
+__host__ __device__ __forceinline__ int klt_list_v(int ww, int wh) { return (wh * (ww >> 3) + 3) & ~3; }
+__host__ __device__ __forceinline__ int klt_list_t(int ww, int wh) { return (wh * (ww & 7) + 3) & ~3; }
+
 __host__ __device__ __forceinline__ size_t klt_smem_per_warp(int ww, int wh) {
     const size_t area = (size_t)ww * wh;
-    size_t b = 3 * ((area * 2 + 3) & ~size_t(3));
-    b += 12 * area;
+    size_t b = (3 * ((area * 2 + 3) & ~size_t(3)) + 15) & ~size_t(15);
+    const size_t lists = 4 * (size_t)(8 * klt_list_v(ww, wh) + 2 * klt_list_t(ww, wh));
+    b += ((12 * area > lists ? 12 * area : lists) + 15) & ~size_t(15);
     b += ((size_t)(ww + 3) * (wh + 3) + 3) & ~size_t(3);
     b += (size_t)(ww + 1) * (wh + 1) * 4;
-    return b;
+    return (b + 15) & ~size_t(15);
 }
 
 // Staged ph x pw patch of image `im` with origin (oy, ox), REFLECT_101 outside the image.
@@ -175,8 +175,11 @@ __device__ __forceinline__ int klt_diff(const uint8_t *q, int gw, const KltW &w,
 
 // CW x CH = compile-time window (0 = taken from P at run time): the reference's 11 x 11 gets constant trip counts,
 // divisions by constants and fully unrolled accumulation chains.
+#ifndef YAVO_KLT_MIN_CTAS
+#define YAVO_KLT_MIN_CTAS 4
+#endif
 template <int CW, int CH>
-__global__ void __launch_bounds__(KLT_WARPS * 32)
+__global__ void __launch_bounds__(KLT_WARPS * 32, YAVO_KLT_MIN_CTAS)
 klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
                  const float2 *__restrict__ prev_xy,                                  // explicit points, or
                  const int32_t *__restrict__ kp_row, const int32_t *__restrict__ kp_col,  // keypoints (row, col) per slot
@@ -195,9 +198,13 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
     uint8_t *base = klt_smem + (size_t)warp * klt_smem_per_warp(ww, wh);
     int16_t *sI = reinterpret_cast<int16_t *>(base), *sIx = reinterpret_cast<int16_t *>(base + plane),
             *sIy = reinterpret_cast<int16_t *>(base + 2 * plane);
-    float *sT = reinterpret_cast<float *>(base + 3 * plane);   // T11 | T12 | T22
-    int *sQ = reinterpret_cast<int *>(sT);                      // Q1 | Q2 (after the gradient matrix is done)
-    uint8_t *sR = base + 3 * plane + 12 * (size_t)area;
+    const size_t planes = (3 * plane + 15) & ~size_t(15);
+    float *sT = reinterpret_cast<float *>(base + planes);      // T11 | T12 | T22, later the mismatch term lists (16-byte aligned)
+    const int G = ww >> 3, vec = G * 8, tw = ww - vec;          // column groups of 8, tail columns
+    const int LV = klt_list_v(ww, wh), LT = klt_list_t(ww, wh);
+    const int NVI = wh * G * 4, NTI = wh * tw;                  // pair items, tail items of one iteration
+    const size_t lists = 4 * (size_t)(8 * LV + 2 * LT);
+    uint8_t *sR = base + planes + (((12 * (size_t)area > lists ? 12 * (size_t)area : lists) + 15) & ~size_t(15));
     short2 *sG = reinterpret_cast<short2 *>(sR + (((size_t)rw * (wh + 3) + 3) & ~size_t(3)));
 
     const size_t o = (size_t)pair * pts_stride + pt;
@@ -312,17 +319,28 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
             __syncwarp();
             klt_stage_patch(sR, J, pitch, H, W, jy, jx, wh + 1, gw, lane);
             __syncwarp();
+            // work items in accumulation order: pair items (row y, group g, k < 4) = columns 8g+k and 8g+k+4 of one
+            // row, then the tail pixels; each writes its finished float term into its accumulator's list
 #pragma unroll
-            for (int p = lane; p < area; p += 32) {
-                const int y = p / ww, x = p - y * ww;
-                const int d = klt_diff(sR + y * gw + x, gw, w, sI[p]);
-                sQ[p] = d * sIx[p];
-                sQ[area + p] = d * sIy[p];
+            for (int i = lane; i < NVI + NTI; i += 32) {
+                if (i < NVI) {
+                    const int y = i / (4 * G), rem = i - y * 4 * G, g = rem >> 2, k = rem & 3;
+                    const int pa = y * ww + 8 * g + k, pb = pa + 4;
+                    const int da = klt_diff(sR + y * gw + 8 * g + k, gw, w, sI[pa]);
+                    const int db = klt_diff(sR + y * gw + 8 * g + k + 4, gw, w, sI[pb]);
+                    sT[k * LV + y * G + g] = __int2float_rn(da * sIx[pa] + db * sIx[pb]);
+                    sT[(4 + k) * LV + y * G + g] = __int2float_rn(da * sIy[pa] + db * sIy[pb]);
+                } else {
+                    const int t = i - NVI, y = t / tw, x = vec + t - y * tw, pa = y * ww + x;
+                    const int da = klt_diff(sR + y * gw + x, gw, w, sI[pa]);
+                    sT[8 * LV + t] = __int2float_rn(da * sIx[pa]);
+                    sT[8 * LV + LT + t] = __int2float_rn(da * sIy[pa]);
+                }
             }
             __syncwarp();
             float u = 0.f;
-            if (lane < 8) u = klt_chain_i(sQ + (lane >> 2) * area, ww, wh, lane & 3);
-            else if (lane < 10) u = klt_chain_i(sQ + (lane - 8) * area, ww, wh, 4);
+            if (lane < 8) u = klt_chain_list(sT + lane * LV, wh * G);
+            else if (lane < 10) u = klt_chain_list(sT + 8 * LV + (lane - 8) * LT, NTI);
             const float b1 = __fmul_rn(klt_combine(u, 0, 8), FLT_SCALE), b2 = __fmul_rn(klt_combine(u, 4, 9), FLT_SCALE);
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);

@@ -446,7 +446,7 @@ KltLevels klt_levels_struct(yavo_ctx *ctx, int H, int W, int top) {
     return L;
 }
 
-// one launch of K8; the reference's 11 x 11 window (and OpenCV's default 21 x 21) run the specialised instances
+// one launch of K8; the reference's 11 x 11 window runs the specialised instance
 int launch_klt(yavo_ctx *ctx, dim3 grid, const KltLevels &L, const KltParams &P, int prev_slot0, int next_slot0,
                const float2 *prev_xy, const int32_t *kp_row, const int32_t *kp_col, const int *n_all, int n_fixed,
                int pts_stride, const float2 *init_xy, float2 *next_xy, uint8_t *status, float *err) {
@@ -460,7 +460,6 @@ int launch_klt(yavo_ctx *ctx, dim3 grid, const KltLevels &L, const KltParams &P,
                          next_xy, status, err));                                                                        \
     } while (0)
     if (P.ww == 11 && P.wh == 11) KLT_LAUNCH(11, 11);
-    else if (P.ww == 21 && P.wh == 21) KLT_LAUNCH(21, 21);
     else KLT_LAUNCH(0, 0);
 #undef KLT_LAUNCH
     CK_LAUNCH();
