@@ -387,4 +387,337 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K8, compile-time window (the reference's 11 x 11).  Same arithmetic as klt_track_kernel; what changes is where the
+// per-step work lives:
+//   * patches are staged as aligned 32-bit words (2-3 loads per lane instead of 5-7 byte loads); a byte shift
+//     (origin column & 3) locates the pixels inside the staged rows;
+//   * every lane owns up to NSLOT fixed work items of a Newton step — a pair item (columns x and x+4 of one row, whose
+//     int32 products OpenCV adds before converting to float) or a tail pixel — with their staged-patch offsets,
+//     term-list positions and the previous frame's I / Ix / Iy samples held in registers for the whole level;
+//   * the ten accumulation chains read their terms as 128-bit loads from contiguous lists; the first CNTV terms are
+//     added by all chain lanes in one instruction stream, only the two tails continue.
+// ------------------------------------------------------------------------------------------------
+template <int WW, int WH>
+struct KltFixed {
+    static constexpr int AREA = WW * WH, G = WW / 8, VEC = G * 8, TW = WW - VEC;
+    static constexpr int CNTV = WH * G, CNTT = WH * TW;                    // terms per lane accumulator / per tail
+    static constexpr int LV = (CNTV + 3) & ~3, LT = (CNTT + 3) & ~3;       // padded list lengths (floats)
+    static constexpr int NVI = CNTV * 4, NTI = CNTT, NIT = NVI + NTI, NSLOT = (NIT + 31) / 32;
+    static constexpr int JW = (WW + 1 + 3 + 3) / 4, RS = 4 * JW;           // next-frame patch: words / bytes per staged row
+    static constexpr int IW = (WW + 3 + 3 + 3) / 4, RS1 = 4 * IW;          // raw previous-frame patch
+    static constexpr int PLANE = (AREA * 2 + 3) & ~3, PLANES = (3 * PLANE + 15) & ~15;
+    static constexpr int LISTS = 4 * (8 * LV + 2 * LT);
+    static constexpr int TERMS = ((12 * AREA > LISTS ? 12 * AREA : LISTS) + 15) & ~15;
+    static constexpr int PATCH = (((WH + 3) * RS1 > (WH + 1) * RS ? (WH + 3) * RS1 : (WH + 1) * RS) + 15) & ~15;
+    static constexpr int DERIV = (WW + 1) * (WH + 1) * 4;
+    static constexpr int SMEM = (PLANES + TERMS + PATCH + DERIV + 15) & ~15;
+    static_assert(CNTT >= CNTV && G >= 1, "window shape not covered by the fixed kernel");
+};
+
+// ROWS x WORDS aligned words starting at row oy, byte column c0 (multiple of 4); all rows inside the image
+template <int ROWS, int WORDS>
+__device__ __forceinline__ void klt_stage_words(uint32_t *dst, const uint8_t *__restrict__ im, int pitch, int oy, int c0, int lane) {
+    const uint8_t *src = im + (size_t)oy * pitch + c0;
+#pragma unroll
+    for (int p = lane; p < ROWS * WORDS; p += 32) {
+        const int r = p / WORDS, wd = p - r * WORDS;
+        dst[p] = (c0 + 4 * wd < pitch) ? __ldg(reinterpret_cast<const uint32_t *>(src + r * pitch + 4 * wd)) : 0u;
+    }
+}
+// the same patch through REFLECT_101 (window reaches outside the image), byte by byte, shift 0
+template <int ROWS, int COLS, int RSB>
+__device__ __forceinline__ void klt_stage_reflect(uint8_t *dst, const uint8_t *__restrict__ im, int pitch, int H, int W, int oy, int ox,
+                                                  int lane) {
+#pragma unroll
+    for (int p = lane; p < ROWS * COLS; p += 32) {
+        const int r = p / COLS, c = p - r * COLS;
+        dst[r * RSB + c] = __ldg(im + (size_t)klt_refl(oy + r, H) * pitch + klt_refl(ox + c, W));
+    }
+}
+
+template <int RSB>
+__device__ __forceinline__ int klt_bilin(const uint8_t *q, const KltW &w) {
+    return (q[0] * w.w00 + q[1] * w.w01 + q[RSB] * w.w10 + q[RSB + 1] * w.w11 + (1 << 8)) >> 9;
+}
+
+template <int WW, int WH>
+__global__ void __launch_bounds__(KLT_WARPS * 32, YAVO_KLT_MIN_CTAS)
+klt_track_fixed_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0, const float2 *__restrict__ prev_xy,
+                       const int32_t *__restrict__ kp_row, const int32_t *__restrict__ kp_col, const int *__restrict__ n_all,
+                       int n_fixed, int pts_stride, const float2 *__restrict__ init_xy, float2 *__restrict__ next_xy,
+                       uint8_t *__restrict__ status, float *__restrict__ err) {
+    using F = KltFixed<WW, WH>;
+    extern __shared__ __align__(16) uint8_t klt_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.y;
+    const int pt = blockIdx.x * KLT_WARPS + warp;
+    const int n = n_all ? n_all[prev_slot0 + pair] : n_fixed;
+    if (pt >= n) return;
+    constexpr int ww = WW, wh = WH, area = F::AREA, gw = WW + 1;
+    uint8_t *base = klt_smem + (size_t)warp * F::SMEM;
+    int16_t *sI = reinterpret_cast<int16_t *>(base), *sIx = reinterpret_cast<int16_t *>(base + F::PLANE),
+            *sIy = reinterpret_cast<int16_t *>(base + 2 * F::PLANE);
+    float *sT = reinterpret_cast<float *>(base + F::PLANES);
+    uint8_t *sR = base + F::PLANES + F::TERMS;
+    short2 *sG = reinterpret_cast<short2 *>(sR + F::PATCH);
+
+    // ---- this lane's work items of a Newton step (fixed for the whole kernel) ------------------------------
+    int offA[F::NSLOT], offB[F::NSLOT], lpos[F::NSLOT], ldel[F::NSLOT], pixA[F::NSLOT], pixB[F::NSLOT];
+    bool valid[F::NSLOT], ispair[F::NSLOT];
+#pragma unroll
+    for (int m = 0; m < F::NSLOT; m++) {
+        const int i = lane + 32 * m;
+        valid[m] = i < F::NIT;
+        ispair[m] = i < F::NVI;
+        int y, xa, xb;
+        if (ispair[m]) {
+            y = i / (4 * F::G);
+            const int rem = i - y * 4 * F::G, g = rem >> 2, k = rem & 3;
+            xa = 8 * g + k;
+            xb = xa + 4;
+            lpos[m] = k * F::LV + y * F::G + g;
+            ldel[m] = 4 * F::LV;
+        } else {
+            const int t = valid[m] ? i - F::NVI : 0;
+            y = t / F::TW;
+            xa = F::VEC + t - y * F::TW;
+            xb = xa;
+            lpos[m] = 8 * F::LV + t;
+            ldel[m] = F::LT;
+        }
+        offA[m] = y * F::RS + xa;
+        offB[m] = y * F::RS + xb;
+        pixA[m] = y * ww + xa;
+        pixB[m] = y * ww + xb;
+    }
+    const float *chain = sT + (lane < 8 ? lane * F::LV : 8 * F::LV + (lane & 1) * F::LT);  // lanes 8, 9: the tails
+
+    const size_t o = (size_t)pair * pts_stride + pt;
+    float2 p0;
+    if (prev_xy) p0 = prev_xy[o];
+    else p0 = make_float2((float)kp_col[(size_t)(prev_slot0 + pair) * pts_stride + pt],
+                          (float)kp_row[(size_t)(prev_slot0 + pair) * pts_stride + pt]);
+    const float halfx = __fmul_rn((float)(ww - 1), 0.5f), halfy = __fmul_rn((float)(wh - 1), 0.5f);
+    const bool use_initial = (P.flags & 4) != 0, get_min_eig = (P.flags & 8) != 0;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    float outx = 0.f, outy = 0.f, ev = 0.f;
+    bool st = true;
+
+    for (int level = L.top; level >= 0; level--) {
+        const int H = L.H[level], W = L.W[level], pitch = L.pitch[level];
+        const uint8_t *I = L.img[level] + (size_t)(prev_slot0 + pair) * L.slot_stride[level];
+        const uint8_t *J = L.img[level] + (size_t)(next_slot0 + pair) * L.slot_stride[level];
+        const float sc = __int_as_float((127 - level) << 23);  // 1 / (1 << level)
+        float px = __fmul_rn(p0.x, sc), py = __fmul_rn(p0.y, sc);
+        float nx, ny;
+        if (level == L.top) {
+            if (use_initial) {
+                const float2 q = init_xy[o];
+                nx = __fmul_rn(q.x, sc);
+                ny = __fmul_rn(q.y, sc);
+            } else {
+                nx = px;
+                ny = py;
+            }
+        } else {
+            nx = __fmul_rn(outx, 2.f);
+            ny = __fmul_rn(outy, 2.f);
+        }
+        outx = nx;
+        outy = ny;
+        px = __fsub_rn(px, halfx);
+        py = __fsub_rn(py, halfy);
+        const int ix = __float2int_rd(px), iy = __float2int_rd(py);
+        if (ix < -ww || ix >= W || iy < -wh || iy >= H) {
+            if (level == 0) {
+                st = false;
+                ev = 0.f;
+            }
+            continue;
+        }
+        KltW w = klt_weights(__fsub_rn(px, (float)ix), __fsub_rn(py, (float)iy));
+
+        // ---- raw patch rows iy-1 .. iy+wh+1, cols ix-1 .. ix+ww+1 of the previous frame ----------------
+        __syncwarp();
+        const bool raw_in = iy >= 1 && ix >= 1 && iy + wh + 2 <= H && ix + ww + 2 <= W;
+        int sh = 0;
+        if (raw_in) {
+            sh = (ix - 1) & 3;
+            klt_stage_words<WH + 3, F::IW>(reinterpret_cast<uint32_t *>(sR), I, pitch, iy - 1, (ix - 1) & ~3, lane);
+        } else {
+            klt_stage_reflect<WH + 3, WW + 3, F::RS1>(sR, I, pitch, H, W, iy - 1, ix - 1, lane);
+        }
+        __syncwarp();
+        const uint8_t *R = sR + sh;
+        // Scharr (dx, dy) at window positions (iy + r, ix + c), r <= wh, c <= ww; zero outside the image
+#pragma unroll
+        for (int p = lane; p < (wh + 1) * gw; p += 32) {
+            const int r = p / gw, c = p - r * gw;
+            short2 g = make_short2(0, 0);
+            if (raw_in || (iy + r >= 0 && iy + r < H && ix + c >= 0 && ix + c < W)) {
+                const uint8_t *q0 = R + r * F::RS1 + c, *q1 = q0 + F::RS1, *q2 = q1 + F::RS1;
+                const int t0a = (q0[0] + q2[0]) * 3 + q1[0] * 10, t0c = (q0[2] + q2[2]) * 3 + q1[2] * 10;
+                const int t1a = q2[0] - q0[0], t1b = q2[1] - q0[1], t1c = q2[2] - q0[2];
+                g.x = (short)(t0c - t0a);
+                g.y = (short)((t1c + t1a) * 3 + t1b * 10);
+            }
+            sG[p] = g;
+        }
+        __syncwarp();
+        // bilinear samples of the patch and its derivatives; float terms of the gradient matrix
+#pragma unroll
+        for (int p = lane; p < area; p += 32) {
+            const int y = p / ww, x = p - y * ww;
+            const int iv = klt_bilin<F::RS1>(R + (y + 1) * F::RS1 + (x + 1), w);
+            const short2 g00 = sG[y * gw + x], g01 = sG[y * gw + x + 1], g10 = sG[(y + 1) * gw + x], g11 = sG[(y + 1) * gw + x + 1];
+            const int gx = (g00.x * w.w00 + g01.x * w.w01 + g10.x * w.w10 + g11.x * w.w11 + (1 << 13)) >> 14;
+            const int gy = (g00.y * w.w00 + g01.y * w.w01 + g10.y * w.w10 + g11.y * w.w11 + (1 << 13)) >> 14;
+            sI[p] = (int16_t)iv;
+            sIx[p] = (int16_t)gx;
+            sIy[p] = (int16_t)gy;
+            const float fx = (float)gx, fy = (float)gy;
+            sT[p] = __fmul_rn(fx, fx);
+            sT[area + p] = __fmul_rn(fx, fy);
+            sT[2 * area + p] = __fmul_rn(fy, fy);
+        }
+        __syncwarp();
+        // gradient matrix: lanes 0-3 A11, 4-7 A12, 8-11 A22 lane accumulators; 12-14 their tails
+        float v = 0.f;
+        if (lane < 12) v = klt_chain_f(sT + (lane >> 2) * area, ww, wh, lane & 3);
+        else if (lane < 15) v = klt_chain_f(sT + (lane - 12) * area, ww, wh, 4);
+        // this lane's samples of the previous frame, kept in registers for the Newton steps of this level
+        int IvA[F::NSLOT], IxA[F::NSLOT], IyA[F::NSLOT], IvB[F::NSLOT], IxB[F::NSLOT], IyB[F::NSLOT];
+#pragma unroll
+        for (int m = 0; m < F::NSLOT; m++) {
+            IvA[m] = sI[pixA[m]];
+            IxA[m] = sIx[pixA[m]];
+            IyA[m] = sIy[pixA[m]];
+            IvB[m] = sI[pixB[m]];
+            IxB[m] = ispair[m] ? sIx[pixB[m]] : 0;   // a tail item's second pixel contributes nothing
+            IyB[m] = ispair[m] ? sIy[pixB[m]] : 0;
+        }
+        const float A11 = __fmul_rn(klt_combine(v, 0, 12), FLT_SCALE), A12 = __fmul_rn(klt_combine(v, 4, 13), FLT_SCALE),
+                    A22 = __fmul_rn(klt_combine(v, 8, 14), FLT_SCALE);
+        float D = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
+        const float dd = __fsub_rn(A11, A22);
+        const float rad = __fadd_rn(__fmul_rn(dd, dd), __fmul_rn(__fmul_rn(4.f, A12), A12));
+        const float minEig = __fdiv_rn(__fsub_rn(__fadd_rn(A22, A11), __fsqrt_rn(rad)), (float)(2 * ww * wh));
+        if (get_min_eig) ev = minEig;
+        if (minEig < P.min_eig || D < 1.1920928955078125e-07f) {
+            if (level == 0) st = false;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+        nx = __fsub_rn(nx, halfx);
+        ny = __fsub_rn(ny, halfy);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < P.max_count; j++) {
+            const int jx = __float2int_rd(nx), jy = __float2int_rd(ny);
+            if (jx < -ww || jx >= W || jy < -wh || jy >= H) {
+                if (level == 0) st = false;
+                break;
+            }
+            w = klt_weights(__fsub_rn(nx, (float)jx), __fsub_rn(ny, (float)jy));
+            __syncwarp();
+            int js = 0;
+            if (jy >= 0 && jx >= 0 && jy + wh + 1 <= H && jx + ww + 1 <= W) {
+                js = jx & 3;
+                klt_stage_words<WH + 1, F::JW>(reinterpret_cast<uint32_t *>(sR), J, pitch, jy, jx & ~3, lane);
+            } else {
+                klt_stage_reflect<WH + 1, WW + 1, F::RS>(sR, J, pitch, H, W, jy, jx, lane);
+            }
+            __syncwarp();
+            const uint8_t *Q = sR + js;
+#pragma unroll
+            for (int m = 0; m < F::NSLOT; m++) {
+                if (valid[m]) {
+                    const int da = klt_bilin<F::RS>(Q + offA[m], w) - IvA[m];
+                    int t1 = da * IxA[m], t2 = da * IyA[m];
+                    if (32 * m < F::NVI) {  // this slot holds pair items (for its tail lanes IxB = IyB = 0)
+                        const int db = klt_bilin<F::RS>(Q + offB[m], w) - IvB[m];
+                        t1 += db * IxB[m];
+                        t2 += db * IyB[m];
+                    }
+                    sT[lpos[m]] = __int2float_rn(t1);
+                    sT[lpos[m] + ldel[m]] = __int2float_rn(t2);
+                }
+            }
+            __syncwarp();
+            // chains: lanes 0-3 b1 accumulators, 4-7 b2 accumulators, 8 / 9 the b1 / b2 tails
+            float u = 0.f;
+#pragma unroll
+            for (int i = 0; i < F::CNTV; i += 4) {
+                const float4 t = *reinterpret_cast<const float4 *>(chain + i);
+                u = __fadd_rn(u, t.x);
+                if (i + 1 < F::CNTV) u = __fadd_rn(u, t.y);
+                if (i + 2 < F::CNTV) u = __fadd_rn(u, t.z);
+                if (i + 3 < F::CNTV) u = __fadd_rn(u, t.w);
+            }
+            if ((lane >> 1) == 4) {
+#pragma unroll
+                for (int i = F::CNTV & ~3; i < F::CNTT; i += 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(chain + i);
+                    if (i >= F::CNTV) u = __fadd_rn(u, t.x);
+                    if (i + 1 >= F::CNTV && i + 1 < F::CNTT) u = __fadd_rn(u, t.y);
+                    if (i + 2 >= F::CNTV && i + 2 < F::CNTT) u = __fadd_rn(u, t.z);
+                    if (i + 3 >= F::CNTV && i + 3 < F::CNTT) u = __fadd_rn(u, t.w);
+                }
+            }
+            const float b1 = __fmul_rn(klt_combine(u, 0, 8), FLT_SCALE), b2 = __fmul_rn(klt_combine(u, 4, 9), FLT_SCALE);
+            const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
+            const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
+            nx = __fadd_rn(nx, ddx);
+            ny = __fadd_rn(ny, ddy);
+            outx = __fadd_rn(nx, halfx);
+            outy = __fadd_rn(ny, halfy);
+            if (__dadd_rn(__dmul_rn((double)ddx, (double)ddx), __dmul_rn((double)ddy, (double)ddy)) <= P.eps2) break;
+            // |float| < 0.01 (double)  <=>  |float| <= 0.01f: 0.01f is the largest float below the double 0.01
+            if (j > 0 && fabsf(__fadd_rn(ddx, pdx)) <= 0.01f && fabsf(__fadd_rn(ddy, pdy)) <= 0.01f) {
+                outx = __fsub_rn(outx, __fmul_rn(ddx, 0.5f));
+                outy = __fsub_rn(outy, __fmul_rn(ddy, 0.5f));
+                break;
+            }
+            pdx = ddx;
+            pdy = ddy;
+        }
+        if (st && level == 0 && !get_min_eig) {
+            // err = mean absolute difference of the patch at the final position (5 fractional bits removed)
+            const float qx = __fsub_rn(outx, halfx), qy = __fsub_rn(outy, halfy);
+            const int jx = __float2int_rd(qx), jy = __float2int_rd(qy);
+            if (jx < -ww || jx >= W || jy < -wh || jy >= H) {
+                st = false;
+                continue;
+            }
+            w = klt_weights(__fsub_rn(qx, (float)jx), __fsub_rn(qy, (float)jy));
+            __syncwarp();
+            int js = 0;
+            if (jy >= 0 && jx >= 0 && jy + wh + 1 <= H && jx + ww + 1 <= W) {
+                js = jx & 3;
+                klt_stage_words<WH + 1, F::JW>(reinterpret_cast<uint32_t *>(sR), J, pitch, jy, jx & ~3, lane);
+            } else {
+                klt_stage_reflect<WH + 1, WW + 1, F::RS>(sR, J, pitch, H, W, jy, jx, lane);
+            }
+            __syncwarp();
+            const uint8_t *Q = sR + js;
+            int e = 0;
+#pragma unroll
+            for (int m = 0; m < F::NSLOT; m++) {
+                if (valid[m]) {
+                    e += abs(klt_bilin<F::RS>(Q + offA[m], w) - IvA[m]);
+                    if (ispair[m]) e += abs(klt_bilin<F::RS>(Q + offB[m], w) - IvB[m]);
+                }
+            }
+#pragma unroll
+            for (int s = 16; s; s >>= 1) e += __shfl_xor_sync(0xffffffffu, e, s);
+            ev = __fdiv_rn(__fmul_rn((float)e, 1.f), (float)(32 * ww * wh));  // integer partial sums: order-free
+        }
+    }
+    if (lane == 0) {
+        next_xy[o] = make_float2(outx, outy);
+        status[o] = st ? 1 : 0;
+        err[o] = ev;
+    }
+}
+
 }  // namespace yavo

@@ -450,6 +450,14 @@ KltLevels klt_levels_struct(yavo_ctx *ctx, int H, int W, int top) {
 int launch_klt(yavo_ctx *ctx, dim3 grid, const KltLevels &L, const KltParams &P, int prev_slot0, int next_slot0,
                const float2 *prev_xy, const int32_t *kp_row, const int32_t *kp_col, const int *n_all, int n_fixed,
                int pts_stride, const float2 *init_xy, float2 *next_xy, uint8_t *status, float *err) {
+    if (P.ww == 11 && P.wh == 11) {
+        const size_t smem = (size_t)KltFixed<11, 11>::SMEM * KLT_WARPS;
+        PROF(KC_KLT, klt_track_fixed_kernel<11, 11><<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(
+                         L, P, prev_slot0, next_slot0, prev_xy, kp_row, kp_col, n_all, n_fixed, pts_stride, init_xy,
+                         next_xy, status, err));
+        CK_LAUNCH();
+        return 0;
+    }
     const size_t smem = klt_smem_per_warp(P.ww, P.wh) * KLT_WARPS;
 #define KLT_LAUNCH(CW, CH)                                                                                              \
     do {                                                                                                                \
@@ -459,8 +467,7 @@ int launch_klt(yavo_ctx *ctx, dim3 grid, const KltLevels &L, const KltParams &P,
                          L, P, prev_slot0, next_slot0, prev_xy, kp_row, kp_col, n_all, n_fixed, pts_stride, init_xy,    \
                          next_xy, status, err));                                                                        \
     } while (0)
-    if (P.ww == 11 && P.wh == 11) KLT_LAUNCH(11, 11);
-    else KLT_LAUNCH(0, 0);
+    KLT_LAUNCH(0, 0);
 #undef KLT_LAUNCH
     CK_LAUNCH();
     return 0;
