@@ -228,6 +228,18 @@ int yavo_klt_track_batch(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, 
  * slot0+f's keypoints into slot slot0+f+1; the last row of the batch is unused. */
 int yavo_klt_fetch(yavo_ctx *ctx, int slot0, int n, float *next_xy, uint8_t *status, float *err);
 
+/* ---- inlier count of the F-matrix RANSAC: _3DHandler::getFRANSAC (src/3DHandler.cc:145-195) ------
+ * The reference fits a fundamental matrix to 8 random matches per iteration (cv::SVD; stays on the host) and counts,
+ * over all matches, those with fabs(p2.t() * F * p1) < threshold, p = (pt.x, pt.y, 1) (:163-186); the matrix with the
+ * first maximal count wins (:187-190).  This entry point evaluates m candidate matrices against n matches in one
+ * launch: F [m x 9] row-major doubles, x1/y1/x2/y2 [n] the matches' pt1.x, pt1.y, pt2.x, pt2.y (integer keypoint
+ * coordinates, as the reference reads them).  counts [m]; *best = index of the first maximum, *best_count its count
+ * (m == 0: -1, INT_MIN, the reference's initial value); residuals [m x n] optional (NULL to skip).  Doubles are
+ * summed in OpenCV's order: results are bit-identical to cv::gemm (tests/golden/epipolar_golden.npz). */
+int yavo_epipolar_inliers(yavo_ctx *ctx, const double *F, int m, const int32_t *x1, const int32_t *y1,
+                          const int32_t *x2, const int32_t *y2, int n, double threshold, int32_t *counts,
+                          int32_t *best, int32_t *best_count, double *residuals);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,7 +16,7 @@ INT_MAX = 2**31 - 1
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("yavo_oracle.cpp", "yavo_oracle_klt.cpp", "yavo_oracle.h")]
+    src = [os.path.join(_HERE, f) for f in ("yavo_oracle.cpp", "yavo_oracle_klt.cpp", "yavo_oracle_geom.cpp", "yavo_oracle.h")]
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src)
     if force or stale:
@@ -252,3 +252,19 @@ def klt_track(prev, nxt, prev_pts, win=(11, 11), max_level=3, crit_type=3, max_c
     f(_p(prev), _p(nxt), H, W, _p(pp), n, _p(nx), _p(st), _p(er), int(win[0]), int(win[1]), int(max_level),
       int(crit_type), int(max_count), float(epsilon), int(flags), float(min_eig))
     return nx, st, er
+
+
+# ---- inlier count of the reference's F-matrix RANSAC -------------------------------------------
+def epipolar_inliers(F, x1, y1, x2, y2, threshold=0.1, residuals=False):
+    """src/3DHandler.cc:163-188.  F: (m, 3, 3) float64; x1, y1, x2, y2: int32 (n,), the Matches' pt1.x, pt1.y, pt2.x,
+    pt2.y as the reference reads them.  Returns counts (m,), best index, best count[, residuals (m, n)]."""
+    F = np.ascontiguousarray(F, np.float64).reshape(-1, 9)
+    a = [np.ascontiguousarray(v, np.int32) for v in (x1, y1, x2, y2)]
+    m, n = F.shape[0], a[0].size
+    counts = np.zeros(m, np.int32)
+    res = np.zeros((m, n), np.float64) if residuals else None
+    best, bc = C.c_int32(), C.c_int32()
+    f = lib().yavo_oracle_epipolar_inliers
+    f.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 4 + [C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    f(_p(F), m, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), n, float(threshold), _p(counts), _p(res), C.byref(best), C.byref(bc))
+    return (counts, best.value, bc.value, res) if residuals else (counts, best.value, bc.value)

@@ -105,6 +105,14 @@ int yavo_oracle_klt(const uint8_t *prev, const uint8_t *next, int H, int W, cons
                     uint8_t *status, float *err, int win_w, int win_h, int max_level, int crit_type, int max_count,
                     double epsilon, int flags, double min_eig_threshold);
 
+/* ---- inlier count of the reference's F-matrix RANSAC (yavo_oracle_geom.cpp) ---------------------
+ * src/3DHandler.cc:163-188: residual = p2.t() * F * p1 with p = (x, y, 1) from the integer keypoint coordinates,
+ * inlier iff fabs(residual) < threshold, first maximum over the m candidate matrices wins.  F: m x 9 row-major. */
+double yavo_oracle_epipolar_residual(const double *F, int x1, int y1, int x2, int y2);
+void yavo_oracle_epipolar_inliers(const double *F, int m, const int32_t *x1, const int32_t *y1, const int32_t *x2,
+                                  const int32_t *y2, int n, double threshold, int32_t *counts, double *residuals,
+                                  int32_t *best, int32_t *best_count);
+
 #ifdef __cplusplus
 }
 #endif

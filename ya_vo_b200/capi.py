@@ -26,7 +26,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
-    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers",
 ]
 
 
@@ -128,7 +128,7 @@ class Context:
         return int(self._L.yavo_get_stream(self._h) or 0)
 
     KERNEL_CLASSES = ("repitch", "detect_blur", "compact_score", "select_topk", "brief", "match_partial", "match_reduce",
-                      "filter_pairs", "pyr_down", "klt_track")
+                      "filter_pairs", "pyr_down", "klt_track", "epipolar_inliers")
 
     def set_profiling(self, on):
         self._ck(self._L.yavo_set_profiling(self._h, int(bool(on))))
@@ -329,6 +329,18 @@ class Context:
         er = np.zeros((n, K), np.float32)
         self._ck(self._L.yavo_klt_fetch(self._h, int(slot0), int(n), _p(xy), _p(st), _p(er)))
         return xy, st, er
+
+    # ---- inlier count of the F-matrix RANSAC (src/3DHandler.cc:163-190) ----
+    def epipolar_inliers(self, F, x1, y1, x2, y2, threshold=0.1, residuals=False):
+        F = np.ascontiguousarray(F, np.float64).reshape(-1, 9)
+        a = [np.ascontiguousarray(v, np.int32) for v in (x1, y1, x2, y2)]
+        m, n = F.shape[0], a[0].size
+        counts = np.zeros(m, np.int32)
+        res = np.zeros((m, n), np.float64) if residuals else None
+        best, bc = C.c_int32(), C.c_int32()
+        self._ck(self._L.yavo_epipolar_inliers(self._h, _p(F), m, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), n,
+                                               C.c_double(threshold), _p(counts), C.byref(best), C.byref(bc), _p(res)))
+        return (counts, best.value, bc.value, res) if residuals else (counts, best.value, bc.value)
 
 
 def ring_points(xc, yc):

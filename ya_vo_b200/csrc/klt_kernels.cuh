@@ -15,6 +15,7 @@
 // Float arithmetic uses the _rn intrinsics: nothing may be contracted to FMA or reassociated.
 #pragma once
 #include <cuda_runtime.h>
+#include <limits.h>
 #include <stdint.h>
 
 namespace yavo {
@@ -717,6 +718,69 @@ klt_track_fixed_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
         next_xy[o] = make_float2(outx, outy);
         status[o] = st ? 1 : 0;
         err[o] = ev;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9  inlier count of the reference's fundamental-matrix RANSAC (src/3DHandler.cc:163-188).
+// One CTA per candidate matrix F (the 8-point fits with cv::SVD stay on the host), threads stride over the
+// matches: residual = p2.t() * F * p1 in double with OpenCV's left-to-right sums, inlier iff |residual| < threshold.
+// A second tiny kernel picks the first maximum, the reference's `inlierCount > maxInliers` rule.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double epi_residual(const double *__restrict__ F, int x1, int y1, int x2, int y2) {
+    const double a0 = (double)x2, a1 = (double)y2, b0 = (double)x1, b1 = (double)y1;
+    const double r0 = __dadd_rn(__dadd_rn(__dmul_rn(a0, F[0]), __dmul_rn(a1, F[3])), F[6]);   // a2 = 1: 1 * F = F exactly
+    const double r1 = __dadd_rn(__dadd_rn(__dmul_rn(a0, F[1]), __dmul_rn(a1, F[4])), F[7]);
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(a0, F[2]), __dmul_rn(a1, F[5])), F[8]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(r0, b0), __dmul_rn(r1, b1)), r2);
+}
+
+__global__ void __launch_bounds__(256)
+epipolar_inliers_kernel(const double *__restrict__ Fs, const int32_t *__restrict__ x1, const int32_t *__restrict__ y1,
+                        const int32_t *__restrict__ x2, const int32_t *__restrict__ y2, int n, double threshold,
+                        int32_t *__restrict__ counts, double *__restrict__ residuals) {
+    __shared__ double F[9];
+    __shared__ int red[8];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    if (tid < 9) F[tid] = Fs[9 * (size_t)i + tid];
+    __syncthreads();
+    int c = 0;
+    for (int k = tid; k < n; k += 256) {
+        const double e = epi_residual(F, x1[k], y1[k], x2[k], y2[k]);
+        if (residuals) residuals[(size_t)i * n + k] = e;
+        c += fabs(e) < threshold;
+    }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) c += __shfl_xor_sync(0xffffffffu, c, s);
+    if ((tid & 31) == 0) red[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; w++) t += red[w];
+        counts[i] = t;
+    }
+}
+
+__global__ void first_max_kernel(const int32_t *__restrict__ counts, int m, int32_t *__restrict__ best) {
+    // one warp: lane-strided scan keeps the lowest index among equal maxima, then a shuffle reduction does the same
+    const int lane = threadIdx.x;
+    int bc = INT_MIN, bi = -1;
+    for (int i = lane; i < m; i += 32)
+        if (counts[i] > bc) {
+            bc = counts[i];
+            bi = i;
+        }
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, s), oi = __shfl_xor_sync(0xffffffffu, bi, s);
+        if (oi >= 0 && (oc > bc || (oc == bc && (bi < 0 || oi < bi)))) {
+            bc = oc;
+            bi = oi;
+        }
+    }
+    if (lane == 0) {
+        best[0] = bi;
+        best[1] = bc;
     }
 }
 

@@ -103,7 +103,7 @@ struct yavo_ctx {
     std::string err;
 };
 
-enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_PYR, KC_KLT, KC_COUNT };
+enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_PYR, KC_KLT, KC_EPI, KC_COUNT };
 
 namespace {
 
@@ -1274,6 +1274,62 @@ int yavo_klt_fetch(yavo_ctx *ctx, int slot0, int n, float *next_xy, uint8_t *sta
     if (status) CK(cudaMemcpyAsync(status, ctx->d_trk_status + o, cnt, cudaMemcpyDeviceToHost, ctx->stream));
     if (err) CK(cudaMemcpyAsync(err, ctx->d_trk_err + o, sizeof(float) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+// ---- inlier count of the F-matrix RANSAC (src/3DHandler.cc:163-190) -----------------------------------------
+
+int yavo_epipolar_inliers(yavo_ctx *ctx, const double *F, int m, const int32_t *x1, const int32_t *y1,
+                          const int32_t *x2, const int32_t *y2, int n, double threshold, int32_t *counts,
+                          int32_t *best, int32_t *best_count, double *residuals) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    if (m < 0 || n < 0 || (m > 0 && (!F || !counts)) || (n > 0 && (!x1 || !y1 || !x2 || !y2)))
+        return fail(ctx, YAVO_ERR_INVALID, "bad arguments (m=%d, n=%d)", m, n);
+    if (best) *best = -1;
+    if (best_count) *best_count = INT_MIN;
+    if (m == 0) return 0;
+    CK(cudaSetDevice(ctx->device));
+    double *dF = nullptr, *dres = nullptr;
+    int32_t *dpts = nullptr, *dcnt = nullptr;
+    // small, call-scoped buffers: the reference calls this once per (re)initialisation (src/LoopHandler.cc:225,567)
+    cudaError_t e = cudaSuccess;
+    auto cleanup = [&]() {
+        if (dF) cudaFree(dF);
+        if (dres) cudaFree(dres);
+        if (dpts) cudaFree(dpts);
+        if (dcnt) cudaFree(dcnt);
+    };
+#define CKE(call)                                                                                          \
+    do {                                                                                                   \
+        e = (call);                                                                                        \
+        if (e != cudaSuccess) {                                                                            \
+            cleanup();                                                                                     \
+            return fail(ctx, YAVO_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e));               \
+        }                                                                                                  \
+    } while (0)
+    CKE(dalloc(&dF, (size_t)m * 9));
+    CKE(dalloc(&dpts, (size_t)std::max(n, 1) * 4));
+    CKE(dalloc(&dcnt, (size_t)m + 2));
+    if (residuals && n > 0) CKE(dalloc(&dres, (size_t)m * n));
+    CKE(cudaMemcpyAsync(dF, F, sizeof(double) * 9 * m, cudaMemcpyHostToDevice, ctx->stream));
+    const int32_t *src[4] = {x1, y1, x2, y2};
+    for (int k = 0; k < 4 && n > 0; k++)
+        CKE(cudaMemcpyAsync(dpts + (size_t)k * n, src[k], sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    PROF(KC_EPI, epipolar_inliers_kernel<<<m, 256, 0, ctx->stream>>>(dF, dpts, dpts + n, dpts + 2 * (size_t)n, dpts + 3 * (size_t)n, n,
+                                                                    threshold, dcnt, dres));
+    ctx->launches++;
+    first_max_kernel<<<1, 32, 0, ctx->stream>>>(dcnt, m, dcnt + m);
+    ctx->launches++;
+    CKE(cudaGetLastError());
+    std::vector<int32_t> h((size_t)m + 2);
+    CKE(cudaMemcpyAsync(h.data(), dcnt, sizeof(int32_t) * (m + 2), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dres) CKE(cudaMemcpyAsync(residuals, dres, sizeof(double) * (size_t)m * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CKE(cudaStreamSynchronize(ctx->stream));
+#undef CKE
+    cleanup();
+    memcpy(counts, h.data(), sizeof(int32_t) * m);
+    if (best) *best = h[m];
+    if (best_count) *best_count = h[m + 1];
     return 0;
 }
 
