@@ -120,7 +120,9 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
                          &tile_bar);
             }
         }
-        mbar_wait(&tile_bar, 0);
+        // only warp 0 polls the mbarrier; the other warps park at the CTA barrier below (a barrier stall issues
+        // nothing, a try_wait loop in every warp takes issue slots this issue-bound kernel needs)
+        if (tid < 32) mbar_wait(&tile_bar, 0);
     }
     const bool edge_cols = DO_BLUR && (x0 == 0 || x0 + TW + HALO > W);
     if (edge_cols) {
