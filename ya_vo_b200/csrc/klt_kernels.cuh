@@ -177,7 +177,7 @@ __device__ __forceinline__ int klt_diff(const uint8_t *q, int gw, const KltW &w,
 // CW x CH = compile-time window (0 = taken from P at run time): the reference's 11 x 11 gets constant trip counts,
 // divisions by constants and fully unrolled accumulation chains.
 #ifndef YAVO_KLT_MIN_CTAS
-#define YAVO_KLT_MIN_CTAS 4
+#define YAVO_KLT_MIN_CTAS 5
 #endif
 template <int CW, int CH>
 __global__ void __launch_bounds__(KLT_WARPS * 32, YAVO_KLT_MIN_CTAS)
