@@ -118,6 +118,35 @@ def test_batch_form_tracks_the_frontend_keypoints(ctx, oracle, offsets):
         assert np.array_equal(er[f, :k][ok].view(np.uint32), o_err[ok].view(np.uint32))
 
 
+def test_fullsize_batch_tracking_matches_oracle(cuda_lib, oracle, offsets, kitti):
+    """BASELINE frame size (1241x376), 2000 keypoints per frame, 5 frames resident: the KITTI fixture followed by
+    shifted / noisy successors and one unrelated frame (tracks that fail or wander must agree too)."""
+    from ya_vo_b200 import synth
+    frames = [kitti]
+    for f in range(3):
+        frames.append(synth.shifted_pair(frames[-1], 300 + f, drow=f - 1, dcol=2 * f + 1))
+    frames.append(synth.synth_frame("G30", 305, 376, 1241))
+    frames = np.stack(frames)
+    with cuda_lib.Context(device=0, n_slots=5, max_rows=376, max_cols=1241, max_kp=2000) as c:
+        c.set_brief_offsets(offsets)
+        c.upload_batch(0, frames)
+        c.frontend_batch(0, 5, False)
+        c.klt_track_batch(0, 5)
+        xy, st, er = c.klt_fetch(0, 5)
+    total = 0
+    for f in range(4):
+        r, col, s, nc = oracle.fast_detect(frames[f], 2000)
+        pts = np.stack([col, r], 1).astype(np.float32)
+        o_next, o_st, o_err = oracle.klt_track(frames[f], frames[f + 1], pts)
+        k = r.size
+        assert np.array_equal(st[f, :k], o_st), f
+        assert np.array_equal(xy[f, :k].view(np.uint32), o_next.view(np.uint32)), f
+        ok = o_st == 1
+        assert np.array_equal(er[f, :k][ok].view(np.uint32), o_err[ok].view(np.uint32)), f
+        total += k
+    assert total > 7000
+
+
 def test_identical_frames_leave_integer_keypoints_in_place(ctx, kitti):
     """Size-independent property at full frame size: with prev == next every mismatch sum is zero, so each accepted
     point stays exactly where it was and its err is 0."""

@@ -207,6 +207,17 @@ static int track(char **a) {
     std::vector<float> error;
     yavo::calcOpticalFlowPyrLK(lastFrame, currentFrame, lastFrameKpt, currFrameKpt, flowStatus, error, cv::Size(11, 11), 3,
                                cv::TermCriteria(cv::TermCriteria::COUNT + cv::TermCriteria::EPS, 30, 0.01), 0, 0.001);
+    {   // wall time of one call with both frames resident and their pyramids built (the steady state of the VO loop)
+        std::vector<cv::Point2f> tmp;
+        std::vector<uchar> st;
+        std::vector<float> er;
+        auto start = std::chrono::high_resolution_clock::now();
+        yavo::calcOpticalFlowPyrLK(lastFrame, currentFrame, lastFrameKpt, tmp, st, er, cv::Size(11, 11), 3,
+                                   cv::TermCriteria(cv::TermCriteria::COUNT + cv::TermCriteria::EPS, 30, 0.01), 0, 0.001);
+        auto stop = std::chrono::high_resolution_clock::now();
+        std::cout << "Time taken for calcOpticalFlowPyrLK (" << lastFrameKpt.size() << " points): "
+                  << std::chrono::duration_cast<std::chrono::microseconds>(stop - start).count() << " us" << std::endl;
+    }
     // the cv::Mat form (what the reference passes) must agree
     std::vector<cv::Point2f> again;
     std::vector<uchar> st2;
