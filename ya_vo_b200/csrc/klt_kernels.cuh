@@ -409,7 +409,7 @@ struct KltFixed {
     static constexpr int IW = (WW + 3 + 3 + 3) / 4, RS1 = 4 * IW;          // raw previous-frame patch
     static constexpr int PLANE = (AREA * 2 + 3) & ~3, PLANES = (3 * PLANE + 15) & ~15;
     static constexpr int LISTS = 4 * (8 * LV + 2 * LT);
-    static constexpr int TERMS = ((12 * AREA > LISTS ? 12 * AREA : LISTS) + 15) & ~15;
+    static constexpr int TERMS = ((12 * AREA > LISTS + 8 ? 12 * AREA : LISTS + 8) + 15) & ~15;   // + 2 scratch floats
     static constexpr int PATCH = (((WH + 3) * RS1 > (WH + 1) * RS ? (WH + 3) * RS1 : (WH + 1) * RS) + 15) & ~15;
     static constexpr int DERIV = (WW + 1) * (WH + 1) * 4;
     static constexpr int SMEM = (PLANES + TERMS + PATCH + DERIV + 15) & ~15;
@@ -484,8 +484,8 @@ klt_track_fixed_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
             y = t / F::TW;
             xa = F::VEC + t - y * F::TW;
             xb = xa;
-            lpos[m] = 8 * F::LV + t;
-            ldel[m] = F::LT;
+            lpos[m] = valid[m] ? 8 * F::LV + t : F::LISTS / 4;   // an idle lane of the last slot writes to scratch
+            ldel[m] = valid[m] ? F::LT : 1;
         }
         offA[m] = y * F::RS + xa;
         offB[m] = y * F::RS + xb;
@@ -631,18 +631,16 @@ klt_track_fixed_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
             __syncwarp();
             const uint8_t *Q = sR + js;
 #pragma unroll
-            for (int m = 0; m < F::NSLOT; m++) {
-                if (valid[m]) {
-                    const int da = klt_bilin<F::RS>(Q + offA[m], w) - IvA[m];
-                    int t1 = da * IxA[m], t2 = da * IyA[m];
-                    if (32 * m < F::NVI) {  // this slot holds pair items (for its tail lanes IxB = IyB = 0)
-                        const int db = klt_bilin<F::RS>(Q + offB[m], w) - IvB[m];
-                        t1 += db * IxB[m];
-                        t2 += db * IyB[m];
-                    }
-                    sT[lpos[m]] = __int2float_rn(t1);
-                    sT[lpos[m] + ldel[m]] = __int2float_rn(t2);
+            for (int m = 0; m < F::NSLOT; m++) {  // no branches: idle lanes compute pixel (0, VEC) again into scratch
+                const int da = klt_bilin<F::RS>(Q + offA[m], w) - IvA[m];
+                int t1 = da * IxA[m], t2 = da * IyA[m];
+                if (32 * m < F::NVI) {  // this slot holds pair items (for its tail lanes IxB = IyB = 0)
+                    const int db = klt_bilin<F::RS>(Q + offB[m], w) - IvB[m];
+                    t1 += db * IxB[m];
+                    t2 += db * IyB[m];
                 }
+                sT[lpos[m]] = __int2float_rn(t1);
+                sT[lpos[m] + ldel[m]] = __int2float_rn(t2);
             }
             __syncwarp();
             // chains: lanes 0-3 b1 accumulators, 4-7 b2 accumulators, 8 / 9 the b1 / b2 tails
@@ -665,7 +663,13 @@ klt_track_fixed_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
                     if (i + 3 >= F::CNTV && i + 3 < F::CNTT) u = __fadd_rn(u, t.w);
                 }
             }
-            const float b1 = __fmul_rn(klt_combine(u, 0, 8), FLT_SCALE), b2 = __fmul_rn(klt_combine(u, 4, 9), FLT_SCALE);
+            // tail + ((q0 + q2) + (q1 + q3)) for both sums at once: lanes k and k^2 add, then k and k^1, lanes 0 / 4 add
+            // their tail (lanes 8 / 9) and the two results are broadcast: 5 shuffles instead of 10
+            const float tl = __shfl_sync(0xffffffffu, u, 8 + ((lane >> 2) & 1));  // lanes 0-3: b1 tail, 4-7: b2 tail
+            float s1 = __fadd_rn(u, __shfl_xor_sync(0xffffffffu, u, 2));          // lanes 0,1 (4,5): q0+q2, q1+q3
+            s1 = __fadd_rn(s1, __shfl_xor_sync(0xffffffffu, s1, 1));              // lane 0 (4): (q0+q2)+(q1+q3)
+            const float sb = __fadd_rn(tl, s1);                                   // valid in lanes 0 and 4
+            const float b1 = __fmul_rn(__shfl_sync(0xffffffffu, sb, 0), FLT_SCALE), b2 = __fmul_rn(__shfl_sync(0xffffffffu, sb, 4), FLT_SCALE);
             const float ddx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float ddy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
             nx = __fadd_rn(nx, ddx);
