@@ -44,28 +44,82 @@ __device__ __forceinline__ int klt_refl(int p, int n) {  // BORDER_REFLECT_101
 }
 
 // ------------------------------------------------------------------------------------------------
-// K7: thread = one output pixel.  Horizontal [1 4 6 4 1] on five source rows, then vertical.
-// grid (ceil(ow/128), oh, slots)
+// K7  cv::pyrDown on 8-bit frames: separable [1 4 6 4 1], BORDER_REFLECT_101, (sum + 128) >> 8.
+// One CTA = a 64 x 16 output tile.  The 131 x 35 input region is staged in shared memory (aligned 128-bit loads for
+// tiles whose columns lie inside the frame, reflected byte loads at the left / right edge; rows are reflected per
+// row either way); the horizontal pass turns four staged words into four sums with two PRMT and four IDP.4A
+// (taps 1 4 6 4 in the dot product, the fifth tap added), stored transposed as u16 so that the vertical pass reads
+// row pairs as words: two IDP.2A (taps 1 4 | 6 4, rounding constant in the accumulator) + the fifth row; four
+// outputs are packed into one 32-bit store.  HBM traffic is the algorithmic one: every input byte read once
+// (tile halos overlap by 3 of 131 columns / 35 rows), every output byte written once.
+// grid (ceil(oW / 64), ceil(oH / 16), slots)
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int PD_TW = 64, PD_TH = 16;                 // output tile
+constexpr int PD_IW = 160, PD_IH = 2 * PD_TH + 3;     // staged bytes per row (cols 2x0-16 .. 2x0+143, 16-byte aligned), rows (35)
+constexpr int PD_HS = 38;                             // u16 per transposed column of horizontal sums (19 words: conflict-free)
+
+__global__ void __launch_bounds__(256)
 pyr_down_kernel(const uint8_t *__restrict__ src, size_t src_stride, int src_pitch, int sH, int sW,
-                uint8_t *__restrict__ dst, size_t dst_stride, int dst_pitch, int oW) {
-    const int x = blockIdx.x * 128 + threadIdx.x, y = blockIdx.y;
-    if (x >= oW) return;
+                uint8_t *__restrict__ dst, size_t dst_stride, int dst_pitch, int oH, int oW) {
+    __shared__ __align__(16) uint32_t tile[PD_IH][PD_IW / 4];
+    __shared__ __align__(4) uint16_t hT[PD_TW][PD_HS];
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * PD_TW, y0 = blockIdx.y * PD_TH;
     const uint8_t *s = src + (size_t)blockIdx.z * src_stride;
-    int c[5];
-    const bool inner = (2 * x - 2 >= 0) && (2 * x + 2 < sW);
-#pragma unroll
-    for (int k = 0; k < 5; k++) c[k] = inner ? 2 * x - 2 + k : klt_refl(2 * x - 2 + k, sW);
-    int acc = 0;
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const int r = klt_refl(2 * y - 2 + j, sH);
-        const uint8_t *row = s + (size_t)r * src_pitch;
-        const int h = __ldg(row + c[0]) + 4 * __ldg(row + c[1]) + 6 * __ldg(row + c[2]) + 4 * __ldg(row + c[3]) + __ldg(row + c[4]);
-        acc += h * ((j == 0 || j == 4) ? 1 : (j == 2 ? 6 : 4));
+    const int cbase = 2 * x0 - 16;  // frame column of staged byte 0 (a multiple of 16)
+    for (int i = tid; i < PD_IH * (PD_IW / 16); i += 256) {   // 350 x 16 bytes, rows reflected
+        const int r = i / (PD_IW / 16), q = i - r * (PD_IW / 16);
+        const int gr = klt_refl(2 * y0 - 2 + r, sH), c = cbase + 16 * q;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (c >= 0 && c + 16 <= src_pitch) v = __ldg(reinterpret_cast<const uint4 *>(s + (size_t)gr * src_pitch + c));
+        reinterpret_cast<uint4 *>(&tile[r][0])[q] = v;  // columns >= sW hold row padding here; the ones a kept output
+    }                                                   // can touch are replaced below
+    if (cbase < 0 || cbase + PD_IW > sW) {
+        // BORDER_REFLECT_101 columns: -2, -1 on the left; sW, sW+1, sW+2 on the right (outputs x < oW reach no further)
+        __syncthreads();
+        uint8_t *tb = reinterpret_cast<uint8_t *>(&tile[0][0]);
+        for (int i = tid; i < PD_IH * 5; i += 256) {
+            const int r = i / 5, j = i - r * 5;
+            const int c = j < 2 ? j - 2 : sW + j - 2, sc = c - cbase;
+            if (sc < 0 || sc >= PD_IW) continue;
+            const int gr = klt_refl(2 * y0 - 2 + r, sH);
+            tb[r * PD_IW + sc] = __ldg(s + (size_t)gr * src_pitch + klt_refl(c, sW));
+        }
     }
-    dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dst_pitch + x] = (uint8_t)((acc + 128) >> 8);
+    __syncthreads();
+    // horizontal: item = (staged row r, four outputs 4g .. 4g+3); output x's window starts at staged byte 2x + 14
+    for (int i = tid; i < PD_IH * (PD_TW / 4); i += 256) {
+        const int r = i >> 4, g = i & 15;
+        const uint32_t w3 = tile[r][2 * g + 3], w6 = tile[r][2 * g + 6];
+        const uint2 w45 = *reinterpret_cast<const uint2 *>(&tile[r][2 * g + 4]);
+        const uint32_t T = 0x04060401u;  // taps 1 4 6 4 on four consecutive bytes; the fifth tap (1) is added
+        const uint32_t h0 = __dp4a(__byte_perm(w3, w45.x, 0x5432), T, (w45.x >> 16) & 0xffu);
+        const uint32_t h1 = __dp4a(w45.x, T, w45.y & 0xffu);
+        const uint32_t h2 = __dp4a(__byte_perm(w45.x, w45.y, 0x5432), T, (w45.y >> 16) & 0xffu);
+        const uint32_t h3 = __dp4a(w45.y, T, w6 & 0xffu);
+        hT[4 * g][r] = (uint16_t)h0;
+        hT[4 * g + 1][r] = (uint16_t)h1;
+        hT[4 * g + 2][r] = (uint16_t)h2;
+        hT[4 * g + 3][r] = (uint16_t)h3;
+    }
+    __syncthreads();
+    // vertical: thread = (output row y, four consecutive output columns)
+    {
+        const int y = tid >> 4, xq = (tid & 15) * 4;
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t *col = reinterpret_cast<const uint32_t *>(&hT[xq + q][0]) + y;   // u16 index 2y
+            uint32_t v = __dp2a_lo(col[0], 0x0401u, 128u);  // h[2y] + 4 h[2y+1] + rounding
+            v = __dp2a_lo(col[1], 0x0406u, v);              // 6 h[2y+2] + 4 h[2y+3]
+            v += col[2] & 0xffffu;                          // h[2y+4]
+            o[q] = v >> 8;
+        }
+        const int gy = y0 + y, gx = x0 + xq;
+        if (gy < oH && gx < oW)  // dst_pitch is a multiple of 16: the word may run past oW into the row padding
+            *reinterpret_cast<uint32_t *>(dst + (size_t)blockIdx.z * dst_stride + (size_t)gy * dst_pitch + gx) =
+                o[0] | (o[1] << 8) | (o[2] << 16) | (o[3] << 24);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -400,10 +400,10 @@ int launch_pyramid(yavo_ctx *ctx, int slot0, int n, int levels) {
             const uint8_t *src = l == 1 ? ctx->d_frames + ctx->frame_stride * s : ctx->d_pyr + ctx->pyr_slot_stride * s + ctx->pyr_off[l - 1];
             const size_t sstride = l == 1 ? ctx->frame_stride : ctx->pyr_slot_stride;
             const int spitch = l == 1 ? ctx->pitch : ctx->pyr_pitch[l - 1];
-            dim3 grid((ow + 127) / 128, oh, e - s);
-            PROF(KC_PYR, pyr_down_kernel<<<grid, 128, 0, ctx->stream>>>(src, sstride, spitch, sh, sw,
+            dim3 grid((ow + PD_TW - 1) / PD_TW, (oh + PD_TH - 1) / PD_TH, e - s);
+            PROF(KC_PYR, pyr_down_kernel<<<grid, 256, 0, ctx->stream>>>(src, sstride, spitch, sh, sw,
                                                                          ctx->d_pyr + ctx->pyr_slot_stride * s + ctx->pyr_off[l],
-                                                                         ctx->pyr_slot_stride, ctx->pyr_pitch[l], ow));
+                                                                         ctx->pyr_slot_stride, ctx->pyr_pitch[l], oh, ow));
             CK_LAUNCH();
         }
         for (int k = s; k < e; k++) ctx->slot_pyr[k] = levels;
