@@ -12,6 +12,9 @@
 //                      and the float sums are accumulated in the ORDER of OpenCV's 128-bit SIMD loops (lane
 //                      accumulators over groups of 8 columns + a scalar tail), which makes positions, status
 //                      and err bit-identical to cv2 4.13 (tests/golden/klt_golden.npz).
+//                      klt_track_fixed_kernel<11,11> is the same algorithm with the reference's window size
+//                      known at compile time; klt_track_kernel takes any window up to 31 x 31.
+// K9 epipolar_inliers_kernel  inlier count of the fundamental-matrix RANSAC (src/3DHandler.cc:163-190).
 // Float arithmetic uses the _rn intrinsics: nothing may be contracted to FMA or reassociated.
 #pragma once
 #include <cuda_runtime.h>
@@ -228,12 +231,11 @@ __device__ __forceinline__ int klt_diff(const uint8_t *q, int gw, const KltW &w,
     return ((q[0] * w.w00 + q[1] * w.w01 + q[gw] * w.w10 + q[gw + 1] * w.w11 + (1 << 8)) >> 9) - iv;
 }
 
-// CW x CH = compile-time window (0 = taken from P at run time): the reference's 11 x 11 gets constant trip counts,
-// divisions by constants and fully unrolled accumulation chains.
+// K8, any window up to KLT_MAX_WIN x KLT_MAX_WIN (window size taken from P at run time).  The reference's 11 x 11
+// window runs klt_track_fixed_kernel below instead.
 #ifndef YAVO_KLT_MIN_CTAS
 #define YAVO_KLT_MIN_CTAS 5
 #endif
-template <int CW, int CH>
 __global__ void __launch_bounds__(KLT_WARPS * 32, YAVO_KLT_MIN_CTAS)
 klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
                  const float2 *__restrict__ prev_xy,                                  // explicit points, or
@@ -247,7 +249,7 @@ klt_track_kernel(KltLevels L, KltParams P, int prev_slot0, int next_slot0,
     const int pt = blockIdx.x * KLT_WARPS + warp;
     const int n = n_all ? n_all[prev_slot0 + pair] : n_fixed;
     if (pt >= n) return;
-    const int ww = CW ? CW : P.ww, wh = CH ? CH : P.wh, area = ww * wh;
+    const int ww = P.ww, wh = P.wh, area = ww * wh;
     const int rw = ww + 3, gw = ww + 1;
     const size_t plane = ((size_t)area * 2 + 3) & ~size_t(3);
     uint8_t *base = klt_smem + (size_t)warp * klt_smem_per_warp(ww, wh);

@@ -459,16 +459,11 @@ int launch_klt(yavo_ctx *ctx, dim3 grid, const KltLevels &L, const KltParams &P,
         return 0;
     }
     const size_t smem = klt_smem_per_warp(P.ww, P.wh) * KLT_WARPS;
-#define KLT_LAUNCH(CW, CH)                                                                                              \
-    do {                                                                                                                \
-        if (smem > 48 * 1024)                                                                                           \
-            CK(cudaFuncSetAttribute(klt_track_kernel<CW, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        PROF(KC_KLT, klt_track_kernel<CW, CH><<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(                             \
-                         L, P, prev_slot0, next_slot0, prev_xy, kp_row, kp_col, n_all, n_fixed, pts_stride, init_xy,    \
-                         next_xy, status, err));                                                                        \
-    } while (0)
-    KLT_LAUNCH(0, 0);
-#undef KLT_LAUNCH
+    if (smem > 48 * 1024)
+        CK(cudaFuncSetAttribute(klt_track_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PROF(KC_KLT, klt_track_kernel<<<grid, KLT_WARPS * 32, smem, ctx->stream>>>(
+                     L, P, prev_slot0, next_slot0, prev_xy, kp_row, kp_col, n_all, n_fixed, pts_stride, init_xy,
+                     next_xy, status, err));
     CK_LAUNCH();
     return 0;
 }
