@@ -200,7 +200,7 @@ int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int row
  * These entry points run that call on device-resident frame slots.  Unlike the rest of this header, points here
  * are OpenCV's: interleaved float (x = column, y = row), exactly what the reference hands to OpenCV
  * (it swaps its (row, col) keypoints at :343-347).  crit_type: 1 = COUNT, 2 = EPS (cv::TermCriteria::Type);
- * flags: 4 = OPTFLOW_USE_INITIAL_FLOW (next_xy is read), 8 = OPTFLOW_LK_GET_MIN_EIGENVALS.  Window sides 1..31.
+ * flags: 4 = OPTFLOW_USE_INITIAL_FLOW (next_xy is read), 8 = OPTFLOW_LK_GET_MIN_EIGENVALS.  Window sides 3..31 (OpenCV rejects smaller ones).
  * Results are bit-identical to cv2 4.13 (tests/golden/klt_golden.npz); err is defined where status == 1
  * (OpenCV leaves it uninitialised elsewhere; here it is 0 or the last minimum eigenvalue). */
 #define YAVO_KLT_MAX_LEVEL 7

@@ -6,7 +6,7 @@ import hashlib
 import numpy as np
 import pytest
 
-from test_klt_golden import GOLDEN, case_args, check_case
+from test_klt_golden import GOLDEN, case_args, check_case, live_opencv, random_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -50,7 +50,7 @@ def test_cuda_pyramid_matches_opencv(ctx, gold, images, oracle):
     for shape in ((9, 13), (8, 8), (5, 64), (33, 7)):
         im = rng.integers(0, 256, shape, dtype=np.uint8)
         ctx.upload(1, im)
-        n = ctx.build_pyramid(1, 1, (1, 1), 2)
+        n = ctx.build_pyramid(1, 1, (3, 3), 2)
         cur = im
         for k in range(1, n + 1):
             cur = oracle.pyr_down(cur)
@@ -93,6 +93,21 @@ def test_cuda_matches_oracle_on_seeded_frames(ctx, oracle, kind, seed, shape):
         ok = o_st == 1
         assert np.array_equal(g_err[ok].view(np.uint32), o_err[ok].view(np.uint32)), (win, lv)
         assert 0 < ok.sum() < pts.shape[0]
+
+
+def test_cuda_matches_live_opencv_on_random_configurations(ctx):
+    """The CUDA path against the live cv2.calcOpticalFlowPyrLK of this image (the GPU box has the same cv2 4.13):
+    seeded random frame sizes, windows 3..31, 0-4 levels, criteria and flags — bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    for a, b, pts, init, kw in random_cases(n_trials=32, seed=777):
+        ctx.upload(2, a)
+        ctx.upload(3, b)
+        c_next, c_st, c_err = live_opencv(cv2, a, b, pts, init, kw)
+        g_next, g_st, g_err = ctx.klt_track(2, 3, pts, init_pts=init, **kw)
+        assert np.array_equal(g_st, c_st), kw
+        assert np.array_equal(g_next.view(np.uint32), c_next.view(np.uint32)), kw
+        ok = c_st == 1
+        assert np.array_equal(g_err[ok].view(np.uint32), c_err[ok].view(np.uint32)), kw
 
 
 def test_batch_form_tracks_the_frontend_keypoints(ctx, oracle, offsets):
@@ -188,6 +203,8 @@ def test_argument_errors(ctx, cuda_lib, kitti):
     ctx.upload(1, kitti)
     with pytest.raises(cuda_lib.YavoError):
         ctx.klt_track(0, 1, p, win=(33, 11))        # window too large
+    with pytest.raises(cuda_lib.YavoError):
+        ctx.klt_track(0, 1, p, win=(2, 11))         # OpenCV asserts sides > 2
     with pytest.raises(cuda_lib.YavoError):
         ctx.klt_track(0, 1, p, flags=1)             # unknown flag
     with pytest.raises(cuda_lib.YavoError):

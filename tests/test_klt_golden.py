@@ -88,3 +88,44 @@ def test_oracle_pyramid_depth_rule(oracle):
 def test_empty_point_list(oracle, gold):
     nxt, st, er = oracle.klt_track(gold["small1"], gold["small2"], np.zeros((0, 2), np.float32))
     assert nxt.shape == (0, 2) and st.size == 0 and er.size == 0
+
+
+def random_cases(n_trials=24, seed=4242):
+    """Seeded random frames, windows (3..31), depths, criteria and flags for the live comparisons with cv2."""
+    from ya_vo_b200 import synth
+    rng = np.random.default_rng(seed)
+    for trial in range(n_trials):
+        H, W = int(rng.integers(24, 200)), int(rng.integers(24, 260))
+        kind = ("U", "G30", "B4")[trial % 3]
+        a = synth.synth_frame(kind, 9000 + trial, H, W)
+        b = synth.shifted_pair(a, 9100 + trial, drow=int(rng.integers(-2, 3)), dcol=int(rng.integers(-3, 4)))
+        win = (int(rng.integers(1, 16)) * 2 + 1 if trial % 4 else int(rng.integers(3, 32)), int(rng.integers(3, 32)))
+        lv = int(rng.integers(0, 5))
+        ct = int(rng.integers(1, 4))
+        mc, eps = int(rng.integers(0, 40)), float(rng.choice([0.0, 0.001, 0.01, 0.03, 0.3]))
+        flags = int(rng.choice([0, 4, 8, 12]))
+        me = float(rng.choice([1e-4, 1e-3, 1e-2]))
+        n = 150
+        pts = np.stack([rng.uniform(-10, W + 10, n), rng.uniform(-10, H + 10, n)], 1).astype(np.float32)
+        init = (pts + rng.normal(0, 1.0, pts.shape)).astype(np.float32) if flags & 4 else None
+        yield a, b, pts, init, dict(win=win, max_level=lv, crit_type=ct, max_count=mc, epsilon=eps, flags=flags, min_eig=me)
+
+
+def live_opencv(cv2, a, b, pts, init, kw):
+    nxt, st, er = cv2.calcOpticalFlowPyrLK(a, b, pts.copy(), None if init is None else init.copy(), winSize=kw["win"],
+                                           maxLevel=kw["max_level"], criteria=(kw["crit_type"], kw["max_count"], kw["epsilon"]),
+                                           flags=kw["flags"], minEigThreshold=kw["min_eig"])
+    return nxt.astype(np.float32), st.ravel(), er.ravel()
+
+
+def test_oracle_matches_live_opencv_on_random_configurations(oracle):
+    """Where cv2 imports (this image and the GPU box's), the oracle is also compared with the live
+    cv2.calcOpticalFlowPyrLK on seeded random frames, windows, depths, criteria and flags: bit for bit."""
+    cv2 = pytest.importorskip("cv2")
+    for a, b, pts, init, kw in random_cases():
+        c_next, c_st, c_err = live_opencv(cv2, a, b, pts, init, kw)
+        o_next, o_st, o_err = oracle.klt_track(a, b, pts, init_pts=init, **kw)
+        assert np.array_equal(o_st, c_st), kw
+        assert np.array_equal(o_next.view(np.uint32), c_next.view(np.uint32)), kw
+        ok = o_st == 1
+        assert np.array_equal(o_err[ok].view(np.uint32), c_err[ok].view(np.uint32)), kw

@@ -413,8 +413,9 @@ int launch_pyramid(yavo_ctx *ctx, int slot0, int n, int levels) {
 }
 
 int klt_check_params(yavo_ctx *ctx, int ww, int wh, int max_level, int flags) {
-    if (ww < 1 || wh < 1 || ww > KLT_MAX_WIN || wh > KLT_MAX_WIN)
-        return fail(ctx, YAVO_ERR_INVALID, "window %dx%d outside 1..%d", ww, wh, KLT_MAX_WIN);
+    // OpenCV asserts winSize.width > 2 && winSize.height > 2 (lkpyramid.cpp, SparsePyrLKOpticalFlowImpl::calc)
+    if (ww < 3 || wh < 3 || ww > KLT_MAX_WIN || wh > KLT_MAX_WIN)
+        return fail(ctx, YAVO_ERR_INVALID, "window %dx%d outside 3..%d", ww, wh, KLT_MAX_WIN);
     if (max_level < 0) return fail(ctx, YAVO_ERR_INVALID, "max_level %d < 0", max_level);
     if (flags & ~(4 | 8)) return fail(ctx, YAVO_ERR_INVALID, "unsupported flags 0x%x (4 = USE_INITIAL_FLOW, 8 = GET_MIN_EIGENVALS)", flags);
     return 0;
