@@ -228,6 +228,17 @@ int yavo_klt_track_batch(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, 
  * slot0+f's keypoints into slot slot0+f+1; the last row of the batch is unused. */
 int yavo_klt_fetch(yavo_ctx *ctx, int slot0, int n, float *next_xy, uint8_t *status, float *err);
 
+/* Tracking inside the streaming path (the steady state of LoopHandler::takeVOStep: FAST + BRIEF on the new frame, then
+ * calcOpticalFlowPyrLK from the last frame, src/LoopHandler.cc:453-464,372-375).  Once enabled, every
+ * yavo_submit_host_batch / yavo_process_host_batch on pinned frames also builds the pyramids and tracks the top-K
+ * keypoints of frame f into frame f+1 for all f, f+1 of the batch, stage by stage in the same copy / compute pipeline,
+ * and copies the tracks into the host arrays registered with yavo_stream_track_outputs BEFORE that submit
+ * (rows f of [n x max_kp x 2] / [n x max_kp] / [n x max_kp]; the last row unused; status / err may be NULL; the arrays
+ * must stay valid until the batch has been waited for).  enable = 0 switches tracking off (the default). */
+int yavo_stream_tracking(yavo_ctx *ctx, int enable, int win_w, int win_h, int max_level, int crit_type, int max_count,
+                         double epsilon, int flags, double min_eig_threshold);
+int yavo_stream_track_outputs(yavo_ctx *ctx, float *next_xy, uint8_t *status, float *err);
+
 /* ---- inlier count of the F-matrix RANSAC: _3DHandler::getFRANSAC (src/3DHandler.cc:145-195) ------
  * The reference fits a fundamental matrix to 8 random matches per iteration (cv::SVD; stays on the host) and counts,
  * over all matches, those with fabs(p2.t() * F * p1) < threshold, p = (pt.x, pt.y, 1) (:163-186); the matrix with the

@@ -70,3 +70,37 @@ def test_run_sequence_matches_oracle(cuda_lib, oracle, offsets, tmp_path):
             assert np.array_equal(got[f][4], exp["match_idx"][f, :kq]) and np.array_equal(got[f][5], exp["match_dist"][f, :kq])
         else:
             assert got[f][4] is None
+
+
+@pytest.mark.gpu
+def test_run_sequence_with_tracking_matches_oracle(cuda_lib, oracle, offsets):
+    """The steady-state loop of the reference (FAST + BRIEF on the new frame, then calcOpticalFlowPyrLK from the last one)
+    in one pipeline: tracks delivered per frame equal the oracle's, across stage and batch seams."""
+    F, H, W = 11, 200, 320
+    frames = np.empty((F, H, W), np.uint8)
+    frames[0] = synth.synth_frame("B4", 60, H, W)
+    for f in range(1, F):
+        frames[f] = synth.shifted_pair(frames[f - 1], 60 + f)
+    tracks = {}
+
+    def on_tracks(f, xy, st, er):
+        tracks[f] = (xy.copy(), st.copy(), er.copy())
+
+    import torch
+    pinned = [torch.empty((4, H, W), dtype=torch.uint8).pin_memory() for _ in range(4)]
+    with cuda_lib.Context(device=0, n_slots=4, max_rows=H, max_cols=W, max_kp=2000) as ctx:
+        ctx.set_brief_offsets(offsets)
+        ctx.set_pipeline_chunk(3)  # several copy/compute stages per batch: pairs across stage seams
+        s = stream.FrameStream(F, lambda i: frames[i], batch=4, shape=(H, W), prefetch=2, buffers=[t.numpy() for t in pinned])
+        n = stream.run_sequence(ctx, s, False, None, on_tracks)
+    assert n == F and sorted(tracks) == list(range(1, F))
+    for f in range(1, F):
+        r, c, sc, nc = oracle.fast_detect(frames[f - 1], 2000)
+        pts = np.stack([c, r], 1).astype(np.float32)
+        o_next, o_st, o_err = oracle.klt_track(frames[f - 1], frames[f], pts)
+        k = r.size
+        xy, st, er = tracks[f]
+        assert np.array_equal(st[:k], o_st), f
+        assert np.array_equal(xy[:k].view(np.uint32), o_next.view(np.uint32)), f
+        ok = o_st == 1
+        assert np.array_equal(er[:k][ok].view(np.uint32), o_err[ok].view(np.uint32)), f

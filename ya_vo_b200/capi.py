@@ -26,7 +26,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
-    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs",
 ]
 
 
@@ -329,6 +329,24 @@ class Context:
         er = np.zeros((n, K), np.float32)
         self._ck(self._L.yavo_klt_fetch(self._h, int(slot0), int(n), _p(xy), _p(st), _p(er)))
         return xy, st, er
+
+    def stream_tracking(self, enable=True, win=(11, 11), max_level=3, crit_type=3, max_count=30, epsilon=0.01, flags=0,
+                        min_eig=1e-3):
+        """Tracking inside submit_host_batch / process_host_batch (pinned frames): see yavo_stream_tracking."""
+        self._ck(self._L.yavo_stream_tracking(self._h, int(bool(enable)), int(win[0]), int(win[1]), int(max_level),
+                                              int(crit_type), int(max_count), C.c_double(epsilon), int(flags),
+                                              C.c_double(min_eig)))
+
+    def alloc_track_outputs(self, n):
+        K = self.max_kp
+        return dict(xy=np.zeros((n, K, 2), np.float32), status=np.zeros((n, K), np.uint8), err=np.zeros((n, K), np.float32))
+
+    def stream_track_outputs(self, tracks):
+        """Host arrays (alloc_track_outputs) the NEXT submit writes its tracks to; None detaches them."""
+        if tracks is None:
+            self._ck(self._L.yavo_stream_track_outputs(self._h, None, None, None))
+        else:
+            self._ck(self._L.yavo_stream_track_outputs(self._h, _p(tracks["xy"]), _p(tracks["status"]), _p(tracks["err"])))
 
     # ---- inlier count of the F-matrix RANSAC (src/3DHandler.cc:163-190) ----
     def epipolar_inliers(self, F, x1, y1, x2, y2, threshold=0.1, residuals=False):

@@ -92,6 +92,13 @@ struct yavo_ctx {
     uint8_t *d_klt_status = nullptr;
     float *d_klt_err = nullptr;
     int klt_cap = 0;
+    // tracking inside the streaming path (yavo_stream_tracking): parameters and the host arrays of the next submit
+    bool strk_on = false;
+    KltParams strk_P = {};
+    int strk_max_level = 0;
+    float *strk_xy = nullptr;
+    uint8_t *strk_status = nullptr;
+    float *strk_err = nullptr;
     float2 *d_trk_xy = nullptr;  // batch results, per slot max_kp
     uint8_t *d_trk_status = nullptr;
     float *d_trk_err = nullptr;
@@ -445,6 +452,15 @@ KltLevels klt_levels_struct(yavo_ctx *ctx, int H, int W, int top) {
         L.pitch[l] = l == 0 ? ctx->pitch : ctx->pyr_pitch[l];
     }
     return L;
+}
+
+int ensure_track_buffers(yavo_ctx *ctx) {
+    if (ctx->d_trk_xy) return 0;
+    const size_t S = (size_t)ctx->n_slots * ctx->max_kp;
+    CK(dalloc(&ctx->d_trk_xy, S));
+    CK(dalloc(&ctx->d_trk_status, S));
+    CK(dalloc(&ctx->d_trk_err, S));
+    return 0;
 }
 
 // one launch of K8; the reference's 11 x 11 window runs the specialised instance
@@ -1039,6 +1055,13 @@ int yavo_submit_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows
                 ctx->fetched_valid[c] = 0;
             }
     ctx->fetched_C = C;
+    const bool track = ctx->strk_on && ctx->strk_xy != nullptr;
+    int top = 0;
+    if (track) {
+        top = klt_levels_for(rows, cols, ctx->strk_P.ww, ctx->strk_P.wh, ctx->strk_max_level);
+        if (int r = ensure_pyramid_alloc(ctx)) return r;
+        if (int r = ensure_track_buffers(ctx)) return r;
+    }
     for (int c = 0; c < nchunks; c++) {
         const int buf = c & 1, s0 = c * C, nc = std::min(C, n - s0);
         uint8_t *raw = ctx->d_raw + (size_t)buf * C * fbytes;
@@ -1052,10 +1075,32 @@ int yavo_submit_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows
         CK(cudaEventRecord(ctx->ev_repitched[buf], ctx->stream));
         ctx->raw_used[buf] = 1;
         if (int r = frontend_range(ctx, s0, nc, do_match != 0, c > 0)) return r;
+        // streaming tracking: the keypoints of frame f tracked into f+1 for the pairs that END in this chunk (the
+        // pair across the chunk seam uses the previous chunk's keypoints and pyramid, still in place)
+        const int p0 = c > 0 ? s0 - 1 : s0, tpairs = track ? s0 + nc - 1 - p0 : 0;
+        if (track) {
+            if (top > 0) {
+                if (int r = launch_pyramid(ctx, s0, nc, top)) return r;
+            }
+            if (tpairs > 0) {
+                dim3 grid((ctx->max_kp + KLT_WARPS - 1) / KLT_WARPS, tpairs);
+                const size_t o = (size_t)p0 * ctx->max_kp;
+                if (int r = launch_klt(ctx, grid, klt_levels_struct(ctx, rows, cols, top), ctx->strk_P, p0, p0 + 1, nullptr,
+                                       ctx->d_kp_row, ctx->d_kp_col, ctx->d_nkp, 0, ctx->max_kp, nullptr, ctx->d_trk_xy + o,
+                                       ctx->d_trk_status + o, ctx->d_trk_err + o))
+                    return r;
+            }
+        }
         CK(cudaEventRecord(ctx->ev_done[c], ctx->stream));
         CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[c], 0));
         if (int r = fetch_async(ctx, ctx->s_d2h, 0, s0, nc, n_kp, out_rows, out_cols, scores, desc, match_idx, match_dist))
             return r;
+        if (tpairs > 0) {
+            const size_t o = (size_t)p0 * ctx->max_kp, cnt = (size_t)tpairs * ctx->max_kp;
+            CK(cudaMemcpyAsync(ctx->strk_xy + 2 * o, ctx->d_trk_xy + o, sizeof(float2) * cnt, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (ctx->strk_status) CK(cudaMemcpyAsync(ctx->strk_status + o, ctx->d_trk_status + o, cnt, cudaMemcpyDeviceToHost, ctx->s_d2h));
+            if (ctx->strk_err) CK(cudaMemcpyAsync(ctx->strk_err + o, ctx->d_trk_err + o, sizeof(float) * cnt, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        }
         CK(cudaEventRecord(ctx->ev_fetched[c], ctx->s_d2h));
         ctx->fetched_valid[c] = 1;
     }
@@ -1245,12 +1290,7 @@ int yavo_klt_track_batch(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, 
     if (top > 0) {
         if (int r = launch_pyramid(ctx, slot0, n, top)) return r;
     } else if (int r = ensure_pyramid_alloc(ctx)) return r;
-    if (!ctx->d_trk_xy) {
-        const size_t S = (size_t)ctx->n_slots * ctx->max_kp;
-        CK(dalloc(&ctx->d_trk_xy, S));
-        CK(dalloc(&ctx->d_trk_status, S));
-        CK(dalloc(&ctx->d_trk_err, S));
-    }
+    if (int r = ensure_track_buffers(ctx)) return r;
     const KltParams P = klt_params(win_w, win_h, crit_type, max_count, epsilon, flags, min_eig_threshold);
     const KltLevels L = klt_levels_struct(ctx, H, W, top);
     dim3 grid((ctx->max_kp + KLT_WARPS - 1) / KLT_WARPS, n - 1);
@@ -1258,6 +1298,29 @@ int yavo_klt_track_batch(yavo_ctx *ctx, int slot0, int n, int win_w, int win_h, 
     // keypoint arrays and counts are indexed by absolute slot inside the kernel; outputs by pair from `o`
     return launch_klt(ctx, grid, L, P, slot0, slot0 + 1, nullptr, ctx->d_kp_row, ctx->d_kp_col, ctx->d_nkp, 0, ctx->max_kp,
                       nullptr, ctx->d_trk_xy + o, ctx->d_trk_status + o, ctx->d_trk_err + o);
+}
+
+int yavo_stream_tracking(yavo_ctx *ctx, int enable, int win_w, int win_h, int max_level, int crit_type, int max_count,
+                         double epsilon, int flags, double min_eig_threshold) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    if (!enable) {
+        ctx->strk_on = false;
+        return 0;
+    }
+    if (int r = klt_check_params(ctx, win_w, win_h, max_level, flags)) return r;
+    if (flags & 4) return fail(ctx, YAVO_ERR_INVALID, "streaming tracking starts from the keypoints themselves (no OPTFLOW_USE_INITIAL_FLOW)");
+    ctx->strk_P = klt_params(win_w, win_h, crit_type, max_count, epsilon, flags, min_eig_threshold);
+    ctx->strk_max_level = max_level;
+    ctx->strk_on = true;
+    return 0;
+}
+
+int yavo_stream_track_outputs(yavo_ctx *ctx, float *next_xy, uint8_t *status, float *err) {
+    if (!ctx) return YAVO_ERR_INVALID;
+    ctx->strk_xy = next_xy;
+    ctx->strk_status = status;
+    ctx->strk_err = err;
+    return 0;
 }
 
 int yavo_klt_fetch(yavo_ctx *ctx, int slot0, int n, float *next_xy, uint8_t *status, float *err) {

@@ -99,16 +99,23 @@ class FrameStream:
         self._free.put(bi)
 
 
-def run_sequence(ctx, stream, do_match=True, on_frame=None):
+def run_sequence(ctx, stream, do_match=True, on_frame=None, on_tracks=None, track_params=None):
     """Pushes a FrameStream through the front end with one batch in flight ahead of the one being consumed.
 
     on_frame(f, n_kp, rows, cols, scores, desc, match_idx, match_dist) is called once per frame in order (match_* are
     None for frame 0; they describe the pair (f-1, f) and index frame f-1's / frame f's keypoints).
+    on_tracks(f, next_xy, status, err), if given, switches on the tracking step of the reference's steady-state loop
+    (cv::calcOpticalFlowPyrLK, src/LoopHandler.cc:372-375) inside the same pipeline: frame f-1's top-K FAST keypoints
+    (before checkBoundry, (x, y) = (col, row)) tracked into frame f, called once per f >= 1 after on_frame(f, ...);
+    track_params are keyword arguments of Context.stream_tracking (default: the reference's 11x11 / 3 levels / 30 / 0.01).
     Returns the number of frames delivered."""
-    pending = None  # (a, b, out, ticket, buffer index)
+    pending = None  # (a, b, out, tracks, ticket, buffer index)
     delivered = 0
+    tracking = on_tracks is not None
+    if tracking:
+        ctx.stream_tracking(True, **(track_params or {}))
 
-    def deliver(a, b, out):
+    def deliver(a, b, out, trk):
         nonlocal delivered
         for i in range(b - a):
             f = a + i
@@ -121,22 +128,33 @@ def run_sequence(ctx, stream, do_match=True, on_frame=None):
                     kq = int(out["n_kp"][i - 1])
                     mi, md = out["match_idx"][i, :kq], out["match_dist"][i, :kq]
                 on_frame(f, k, out["rows"][i, :k], out["cols"][i, :k], out["scores"][i, :k], out["desc"][i, :k], mi, md)
+            if tracking and i > 0:
+                on_tracks(f, trk["xy"][i - 1], trk["status"][i - 1], trk["err"][i - 1])
             delivered += 1
 
     outs = [ctx.alloc_batch_outputs(stream.batch), ctx.alloc_batch_outputs(stream.batch)]
+    trks = [ctx.alloc_track_outputs(stream.batch), ctx.alloc_track_outputs(stream.batch)] if tracking else [None, None]
     turn = 0
-    for a, b, frames, bi in stream:
-        out, ticket = ctx.submit_host_batch(frames, do_match, outs[turn])
+    try:
+        for a, b, frames, bi in stream:
+            if tracking:
+                ctx.stream_track_outputs(trks[turn])
+            out, ticket = ctx.submit_host_batch(frames, do_match, outs[turn])
+            if pending is not None:
+                pa, pb, pout, ptrk, pt, pbi = pending
+                ctx.wait_batch(pt)
+                stream.release(pbi)
+                deliver(pa, pb, pout, ptrk)
+            pending = (a, b, out, trks[turn], ticket, bi)
+            turn ^= 1
         if pending is not None:
-            pa, pb, pout, pt, pbi = pending
-            ctx.wait_batch(pt)
+            pa, pb, pout, ptrk, pt, pbi = pending
+            ctx.wait()
             stream.release(pbi)
-            deliver(pa, pb, pout)
-        pending = (a, b, out, ticket, bi)
-        turn ^= 1
-    if pending is not None:
-        pa, pb, pout, pt, pbi = pending
-        ctx.wait()
-        stream.release(pbi)
-        deliver(pa, pb, pout)
+            deliver(pa, pb, pout, ptrk)
+    finally:
+        if tracking:
+            ctx.wait()
+            ctx.stream_track_outputs(None)
+            ctx.stream_tracking(False)
     return delivered
