@@ -29,7 +29,11 @@ def main():
     if os.environ.get("YAVO_REBUILD"):
         capi.build(force=True)  # tuning runs: YAVO_NVCC_EXTRA=-D... YAVO_REBUILD=1
     frames = np.empty((B, H, W), np.uint8)
-    frames[0] = synth.synth_frame(args.kind, 500, H, W)
+    if args.kind == "K":  # the real KITTI-shaped frame of the reference's tests (tests/golden/kitti_frame.png)
+        import cv2
+        frames[0] = cv2.imread(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "kitti_frame.png"), 0)
+    else:
+        frames[0] = synth.synth_frame(args.kind, 500, H, W)
     for f in range(1, B):
         frames[f] = synth.shifted_pair(frames[f - 1], 500 + f)
     with capi.Context(device=0, n_slots=B, max_rows=H, max_cols=W, max_kp=2000, max_cand=65536) as ctx:
