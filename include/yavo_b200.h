@@ -251,6 +251,12 @@ int yavo_epipolar_inliers(yavo_ctx *ctx, const double *F, int m, const int32_t *
                           const int32_t *x2, const int32_t *y2, int n, double threshold, int32_t *counts,
                           int32_t *best, int32_t *best_count, double *residuals);
 
+/* Page-locked host memory for the frame and result arrays of the asynchronous entry points (yavo_submit_host_batch
+ * copies to and from them while the call has already returned; with pageable result arrays the driver stages the
+ * device-to-host copies and the submit blocks until they are done).  NULL on failure. */
+void *yavo_pinned_alloc(size_t bytes);
+void yavo_pinned_free(void *p);
+
 #ifdef __cplusplus
 }
 #endif

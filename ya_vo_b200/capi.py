@@ -26,7 +26,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
-    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free",
 ]
 
 
@@ -68,6 +68,10 @@ def lib():
         L.yavo_destroy.restype = None
         L.yavo_destroy.argtypes = [C.c_void_p]
         L.yavo_ring_points.restype = None
+        L.yavo_pinned_alloc.restype = C.c_void_p
+        L.yavo_pinned_alloc.argtypes = [C.c_size_t]
+        L.yavo_pinned_free.restype = None
+        L.yavo_pinned_free.argtypes = [C.c_void_p]
         L.yavo_get_stream.restype = C.c_void_p
         L.yavo_get_stream.argtypes = [C.c_void_p]
         L.yavo_upload_from_device.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_size_t]
@@ -231,10 +235,13 @@ class Context:
         self._ck(self._L.yavo_frontend_batch(self._h, int(slot0), int(n), int(do_match)))
 
     def alloc_batch_outputs(self, n, pinned=False):
+        """Result arrays of the batch entry points; pinned=True puts them in page-locked memory, which is what lets
+        submit_host_batch return before the device-to-host copies have run."""
         K = self.max_kp
-        return dict(n_kp=np.zeros(n, np.int32), rows=np.zeros((n, K), np.int32), cols=np.zeros((n, K), np.int32),
-                    scores=np.zeros((n, K), np.float32), desc=np.zeros((n, K, 32), np.uint8),
-                    match_idx=np.zeros((n, K), np.int32), match_dist=np.zeros((n, K), np.int32))
+        z = pinned_zeros if pinned else np.zeros
+        return dict(n_kp=z(n, np.int32), rows=z((n, K), np.int32), cols=z((n, K), np.int32),
+                    scores=z((n, K), np.float32), desc=z((n, K, 32), np.uint8),
+                    match_idx=z((n, K), np.int32), match_dist=z((n, K), np.int32))
 
     def fetch_batch(self, slot0, n, out=None):
         out = out or self.alloc_batch_outputs(n)
@@ -337,9 +344,10 @@ class Context:
                                               int(crit_type), int(max_count), C.c_double(epsilon), int(flags),
                                               C.c_double(min_eig)))
 
-    def alloc_track_outputs(self, n):
+    def alloc_track_outputs(self, n, pinned=False):
         K = self.max_kp
-        return dict(xy=np.zeros((n, K, 2), np.float32), status=np.zeros((n, K), np.uint8), err=np.zeros((n, K), np.float32))
+        z = pinned_zeros if pinned else np.zeros
+        return dict(xy=z((n, K, 2), np.float32), status=z((n, K), np.uint8), err=z((n, K), np.float32))
 
     def stream_track_outputs(self, tracks):
         """Host arrays (alloc_track_outputs) the NEXT submit writes its tracks to; None detaches them."""
@@ -359,6 +367,41 @@ class Context:
         self._ck(self._L.yavo_epipolar_inliers(self._h, _p(F), m, _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), n,
                                                C.c_double(threshold), _p(counts), C.byref(best), C.byref(bc), _p(res)))
         return (counts, best.value, bc.value, res) if residuals else (counts, best.value, bc.value)
+
+
+class _PinnedBlock:
+    """Owner of one yavo_pinned_alloc block; freed when the last numpy view of it is collected."""
+
+    def __init__(self, nbytes):
+        self.ptr = lib().yavo_pinned_alloc(max(int(nbytes), 1))
+        if not self.ptr:
+            raise YavoError("yavo_pinned_alloc(%d) failed" % nbytes)
+        self.buf = (C.c_uint8 * max(int(nbytes), 1)).from_address(self.ptr)
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                lib().yavo_pinned_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
+
+
+def pinned_zeros(shape, dtype=np.uint8):
+    """numpy array in page-locked host memory (cudaMallocHost through the C ABI), zero-filled."""
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    blk = _PinnedBlock(n)
+    a = np.frombuffer(blk.buf, dtype=np.uint8, count=n).view(dt).reshape(shape) if n else np.zeros(shape, dt)
+    a[...] = 0
+    _PINNED_OWNERS[id(blk)] = blk  # numpy keeps blk.buf alive; the registry keeps blk (and its free) tied to the array
+    import weakref
+    weakref.finalize(a, _PINNED_OWNERS.pop, id(blk), None)
+    return a
+
+
+_PINNED_OWNERS = {}
 
 
 def ring_points(xc, yc):

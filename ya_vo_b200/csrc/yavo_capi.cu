@@ -1392,4 +1392,19 @@ int yavo_epipolar_inliers(yavo_ctx *ctx, const double *F, int m, const int32_t *
     return 0;
 }
 
+// ---- pinned host memory for callers without a CUDA runtime binding of their own -------------------------------
+
+void *yavo_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+
+void yavo_pinned_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 }  // extern "C"

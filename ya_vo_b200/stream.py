@@ -31,9 +31,8 @@ class PinnedBatches:
     """`depth` pinned (page-locked) uint8 buffers of shape [batch, H, W] handed round-robin to the decoder."""
 
     def __init__(self, depth, batch, H, W):
-        import torch
-        self._keep = [torch.empty((batch, H, W), dtype=torch.uint8).pin_memory() for _ in range(depth)]
-        self.buffers = [t.numpy() for t in self._keep]
+        from . import capi
+        self.buffers = [capi.pinned_zeros((batch, H, W), np.uint8) for _ in range(depth)]
 
 
 class FrameStream:
@@ -132,8 +131,9 @@ def run_sequence(ctx, stream, do_match=True, on_frame=None, on_tracks=None, trac
                 on_tracks(f, trk["xy"][i - 1], trk["status"][i - 1], trk["err"][i - 1])
             delivered += 1
 
-    outs = [ctx.alloc_batch_outputs(stream.batch), ctx.alloc_batch_outputs(stream.batch)]
-    trks = [ctx.alloc_track_outputs(stream.batch), ctx.alloc_track_outputs(stream.batch)] if tracking else [None, None]
+    # page-locked result arrays: the device-to-host copies of a submit run behind the call, not inside it
+    outs = [ctx.alloc_batch_outputs(stream.batch, pinned=True) for _ in range(2)]
+    trks = [ctx.alloc_track_outputs(stream.batch, pinned=True) for _ in range(2)] if tracking else [None, None]
     turn = 0
     try:
         for a, b, frames, bi in stream:
