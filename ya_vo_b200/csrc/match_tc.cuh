@@ -1,0 +1,328 @@
+// match_tc.cuh — K5t: brute-force Hamming match on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Reference semantics: Brief::matchFeatures / hammingDistance (reference src/BriefDescriptor.cc:139-183):
+// for every query descriptor the train descriptor with the smallest 256-bit Hamming distance, the LOWEST
+// train index among equal minima.
+//
+// Formulation.  A descriptor bit b is written as the FP8 (e4m3) number +1.0 (b = 0, byte 0x38) or -1.0
+// (b = 1, byte 0xB8).  Then for two descriptors  dot = sum_k a_k * b_k = 256 - 2 * hamming,  every partial sum is
+// an integer of magnitude <= 256 and therefore exact in the FP32 accumulator: the result is bit-exact integer
+// arithmetic, only carried out by tcgen05.mma (kind::f8f6f4, M = 128 queries x N = 256 train x K = 32 per
+// instruction, 8 instructions per 128 x 256 tile) instead of 4.2 M XOR/POPC chains per frame pair.
+//
+// One persistent CTA per SM, three warp roles connected by mbarriers:
+//   * expander warps: read the packed descriptors (32 bytes each) from global memory and write the +-1.0
+//     bytes into shared memory directly in the canonical K-major, non-swizzled UMMA operand layout
+//     (8 x 16-byte core matrices: chunk c of row r at  c * rows * 16 + r * 16);  one SHF + one LOP3 per four
+//     operand bytes.  The order of the 256 bit positions along K is permuted (bit 8b+s of word i sits at
+//     k = 32 i + 4 s + b), identically for both operands, which a dot product does not see.
+//   * one MMA thread: 8 tcgen05.mma per train tile into one of two 128 x 256 FP32 accumulators in TMEM,
+//     tcgen05.commit onto the mbarriers that free the operand stage and publish the accumulator.
+//   * four epilogue warps (one per TMEM lane quarter, thread = query row): tcgen05.ld 32 columns at a time,
+//     key = 256 * distance + column as ONE FFMA (32768 + j - 128 * dot), running minimum of the keys = the
+//     reference's first-minimum rule inside a tile; tiles are visited in ascending order and only a strictly
+//     smaller distance replaces the best one, which extends the rule across tiles.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace yavo {
+namespace tcm {
+
+constexpr int TQ = 128;                 // queries per work item  (UMMA M)
+constexpr int TT = 256;                 // train descriptors per tile (UMMA N)
+constexpr int KBYTES = 256;             // operand bytes per descriptor (one FP8 per bit)
+constexpr int A_BYTES = TQ * KBYTES;    // 32 KB
+constexpr int B_BYTES = TT * KBYTES;    // 64 KB
+constexpr int NSTAGE = 2;               // operand stages (A: per work item, B: per train tile) and accumulators
+constexpr int EPI_WARPS = 4;            // warps 0..3: TMEM lane quarter == warp index
+constexpr int MMA_WARP = EPI_WARPS;     // warp 4
+constexpr int EXP_WARPS = 8;            // warps 5..12
+constexpr int THREADS = 32 * (EPI_WARPS + 1 + EXP_WARPS);
+constexpr int SMEM_BYTES = NSTAGE * (A_BYTES + B_BYTES);
+constexpr uint32_t TMEM_COLS = 512;     // two 128 x 256 FP32 accumulators
+
+__device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(saddr(bar)),
+        "r"(parity)
+        : "memory");
+}
+// tcgen05.commit: the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread is done
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(saddr(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy that tcgen05.mma reads operands through
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major, no swizzle, descriptor version 1 (sm_100):
+// bits [0,14) start address >> 4, [16,30) leading-dimension byte offset >> 4 (distance between the two 16-byte
+// K chunks of one instruction), [32,46) stride byte offset >> 4 (distance between 8-row groups), [46,48) = 1.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr & 0x3ffffu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+// Instruction descriptor of kind::f8f6f4: D = F32 (bits [4,6) = 1), A = B = E4M3 (0), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TT >> 3) << 17) | ((uint32_t)(TQ >> 4) << 24);
+
+__device__ __forceinline__ void mma_f8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate)
+        : "memory");
+}
+
+#define YAVO_TM32(v) \
+    "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), \
+    "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), \
+    "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), \
+    "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+#define YAVO_TM32_RW(v) \
+    "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), \
+    "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), \
+    "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), \
+    "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+
+// 32 consecutive accumulator columns of this thread's TMEM lane (asynchronous: see tmem_wait)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, "
+        "%24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : YAVO_TM32(v)
+        : "r"(taddr)
+        : "memory");
+}
+// tcgen05.wait::ld; the registers are listed as read-write operands so that no use of them is scheduled above it
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : YAVO_TM32_RW(v)::"memory");
+}
+
+// Words 4h..4h+3 of one descriptor -> operand chunks 8h..8h+7 of row r of a tile with R rows.
+__device__ __forceinline__ void expand_half(uint8_t *tile, int R, int r, int h, const uint4 &w) {
+    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        uint32_t o[8];
+#pragma unroll
+        for (int s = 0; s < 8; s++) o[s] = ((ws[i] << (7 - s)) & 0x80808080u) | 0x38383838u;
+        uint8_t *p = tile + (size_t)(8 * h + 2 * i) * R * 16 + r * 16;
+        *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<uint4 *>(p + R * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// running minimum over 32 accumulator columns; JB = first column of the chunk inside the tile
+template <int JB>
+__device__ __forceinline__ float min_keys(const uint32_t (&v)[32], float m, int lim) {
+    if (lim >= 32) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            const float k0 = __fmaf_rn(__uint_as_float(v[i]), -128.0f, 32768.0f + (float)(JB + i));
+            const float k1 = __fmaf_rn(__uint_as_float(v[i + 1]), -128.0f, 32768.0f + (float)(JB + i + 1));
+            m = fminf(m, fminf(k0, k1));
+        }
+    } else {  // last tile of a train set: columns beyond the set do not take part
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const float k = __fmaf_rn(__uint_as_float(v[i]), -128.0f, 32768.0f + (float)(JB + i));
+            if (i < lim) m = fminf(m, k);
+        }
+    }
+    return m;
+}
+
+// Work item = (pair, tile of TQ queries).  Set addressing as in match_partial_kernel: pair p takes its queries
+// from set p + q_set_offset and its train descriptors from set p + t_set_offset of arrays with set_stride_words
+// words per set; n*_all == nullptr means every set holds n*_fixed descriptors.  out_* rows have out_stride entries.
+// dbg_dots (test tool only): the 128 x 256 dot products of the first tile of work item 0.
+__global__ void __launch_bounds__(THREADS, 1)
+match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
+                const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
+                size_t set_stride_words, int q_set_offset, int t_set_offset, int pairs, int q_tiles, int out_stride,
+                int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_dots,
+                int desc_variant) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bars[6 * NSTAGE];
+    __shared__ uint32_t tmem_base_s;
+    uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *b_full = bars + 2 * NSTAGE, *b_empty = bars + 3 * NSTAGE;
+    uint64_t *acc_full = bars + 4 * NSTAGE, *acc_empty = bars + 5 * NSTAGE;
+    uint8_t *sA = smem_raw, *sB = smem_raw + NSTAGE * A_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            bar_init(&a_full[s], EXP_WARPS);
+            bar_init(&a_empty[s], 1);
+            bar_init(&b_full[s], EXP_WARPS);
+            bar_init(&b_empty[s], 1);
+            bar_init(&acc_full[s], 1);
+            bar_init(&acc_empty[s], EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const int items = pairs * q_tiles;
+    uint32_t a_cnt = 0, t_cnt = 0;  // A stages used so far (work items with train tiles); train tiles so far
+
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int pair = item / q_tiles, q0 = (item - pair * q_tiles) * TQ;
+        const int nq = nq_all ? nq_all[pair + q_set_offset] : nq_fixed;
+        const int nt = nt_all ? nt_all[pair + t_set_offset] : nt_fixed;
+        if (q0 >= nq) continue;
+        const int n_tiles = (nt + TT - 1) / TT;
+        const uint32_t *dq = dq_all + (size_t)(pair + q_set_offset) * set_stride_words;
+        const uint32_t *dt = dt_all + (size_t)(pair + t_set_offset) * set_stride_words;
+
+        if (warp < EPI_WARPS) {
+            // ------------------------------------------------ epilogue: thread = query row
+            int best_d = 0x7fffffff, best_j = -1;
+            for (int t = 0; t < n_tiles; t++, t_cnt++) {
+                const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                bar_wait(&acc_full[s], ph);
+                fence_after_sync();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * TT;
+                const int nvalid = min(TT, nt - t * TT);
+                float m = 3.0e38f;
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+#define YAVO_EPI_STEP(C)                                                                   \
+    {                                                                                      \
+        tmem_wait(v0);                                                                     \
+        if ((C + 1) * 32 < nvalid) tmem_ld32(taddr + (C + 1) * 32, v1);                    \
+        if (dbg_dots && item == 0 && t == 0)                                               \
+            for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + C * 32 + i] = __uint_as_float(v0[i]); \
+        m = min_keys<C * 32>(v0, m, nvalid - C * 32);                                      \
+        if ((C + 1) * 32 < nvalid) {                                                       \
+            tmem_wait(v1);                                                                 \
+            if ((C + 2) * 32 < nvalid) tmem_ld32(taddr + (C + 2) * 32, v0);                \
+            if (dbg_dots && item == 0 && t == 0)                                           \
+                for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + (C + 1) * 32 + i] = __uint_as_float(v1[i]); \
+            m = min_keys<(C + 1) * 32>(v1, m, nvalid - (C + 1) * 32);                      \
+        }                                                                                  \
+    }
+                YAVO_EPI_STEP(0)
+                if (64 < nvalid) YAVO_EPI_STEP(2)
+                if (128 < nvalid) YAVO_EPI_STEP(4)
+                if (192 < nvalid) YAVO_EPI_STEP(6)
+#undef YAVO_EPI_STEP
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) bar_arrive(&acc_empty[s]);
+                const int ki = (int)m;  // 256 * distance + column, exact
+                if ((ki >> 8) < best_d) {
+                    best_d = ki >> 8;
+                    best_j = t * TT + (ki & 255);
+                }
+            }
+            const int q = q0 + warp * 32 + lane;
+            if (q < nq) {
+                out_idx[(size_t)pair * out_stride + q] = best_j;  // empty train set: -1 / INT_MAX as the reference leaves it
+                out_dist[(size_t)pair * out_stride + q] = best_d;
+            }
+        } else if (warp == MMA_WARP) {
+            // ------------------------------------------------ MMA issue: one thread
+            if (n_tiles > 0) {
+                if (lane == 0) {
+                    const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
+                    const uint32_t a_lbo = desc_variant ? 128u : TQ * 16u, a_sbo = desc_variant ? TQ * 16u : 128u;
+                    const uint32_t b_lbo = desc_variant ? 128u : TT * 16u, b_sbo = desc_variant ? TT * 16u : 128u;
+                    const uint64_t adesc0 = smem_desc(saddr(sA + as * A_BYTES), a_lbo, a_sbo);
+                    bar_wait(&a_full[as], aph);
+                    for (int t = 0; t < n_tiles; t++, t_cnt++) {
+                        const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                        bar_wait(&b_full[s], ph);
+                        bar_wait(&acc_empty[s], ph ^ 1);
+                        fence_after_sync();
+                        const uint64_t bdesc0 = smem_desc(saddr(sB + s * B_BYTES), b_lbo, b_sbo);
+                        const uint32_t tacc = tmem_base + s * TT;
+#pragma unroll
+                        for (int k = 0; k < KBYTES / 32; k++)  // K = 32 operand bytes (two 16-byte chunks) per instruction
+                            mma_f8(tacc, adesc0 + (uint64_t)((k * 2 * TQ * 16) >> 4), bdesc0 + (uint64_t)((k * 2 * TT * 16) >> 4), k > 0);
+                        mma_commit(&b_empty[s]);
+                        mma_commit(&acc_full[s]);
+                    }
+                    mma_commit(&a_empty[as]);
+                } else {
+                    t_cnt += n_tiles;
+                }
+                a_cnt++;
+                __syncwarp();
+            }
+        } else {
+            // ------------------------------------------------ expanders: packed bits -> +-1.0 operand bytes
+            if (n_tiles > 0) {
+                const int ew = warp - (EPI_WARPS + 1);  // 0..7
+                const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
+                const uint4 zero = make_uint4(0, 0, 0, 0);
+                {   // A: 4 row groups of 32 x 2 halves = 8 tasks, one per warp
+                    const int r = (ew >> 1) * 32 + lane, h = ew & 1;
+                    const uint4 w = (q0 + r < nq) ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8) + h) : zero;
+                    bar_wait(&a_empty[as], aph ^ 1);
+                    expand_half(sA + as * A_BYTES, TQ, r, h, w);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(&a_full[as]);
+                }
+                // B: 8 row groups x 2 halves = 16 tasks, two per warp (both halves of row group ew)
+                const int r = ew * 32 + lane;
+                uint4 c0 = (r < nt) ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)r * 8)) : zero;
+                uint4 c1 = (r < nt) ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)r * 8) + 1) : zero;
+                for (int t = 0; t < n_tiles; t++, t_cnt++) {
+                    const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                    const int rn = (t + 1) * TT + r;  // prefetch the next tile's words before this one is expanded
+                    const bool more = (t + 1 < n_tiles) && rn < nt;
+                    const uint4 n0 = more ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)rn * 8)) : zero;
+                    const uint4 n1 = more ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)rn * 8) + 1) : zero;
+                    bar_wait(&b_empty[s], ph ^ 1);
+                    expand_half(sB + s * B_BYTES, TT, r, 0, c0);
+                    expand_half(sB + s * B_BYTES, TT, r, 1, c1);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(&b_full[s]);
+                    c0 = n0;
+                    c1 = n1;
+                }
+                a_cnt++;
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        fence_after_sync();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tcm
+}  // namespace yavo
