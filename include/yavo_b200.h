@@ -64,7 +64,7 @@ void *yavo_get_stream(yavo_ctx *ctx);
 /* measurement: when on, every kernel launch is bracketed by a CUDA event pair on the context's stream.
  * yavo_profile_collect synchronises and returns, per kernel class
  * {0 repitch, 1 detect_blur, 2 compact_score, 3 select_topk, 4 brief, 5 match_partial, 6 match_reduce,
- *  7 filter_pairs},
+ *  7 filter_pairs, 8 pyr_down, 9 klt_track, 10 epipolar_inliers, 11 match_tc},
  * the summed device time in ms and the number of launches since the last collect / set_profiling. */
 int yavo_set_profiling(yavo_ctx *ctx, int on);
 int yavo_profile_collect(yavo_ctx *ctx, double *ms_per_class, int *launches_per_class, int n_classes);
@@ -131,6 +131,11 @@ int yavo_brief_describe(yavo_ctx *ctx, int slot, const int32_t *rows, const int3
  * per query (ratio test), out_rev_idx[j] = best query for train j (cross-check). */
 int yavo_match(yavo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
                int32_t *out_idx, int32_t *out_dist, int32_t *out_second, int32_t *out_rev_idx);
+
+/* Which kernel computes the matches: 0 (default) = K5t, tcgen05 tensor cores on +-1.0 FP8 expansions of the
+ * descriptor bits (exact: every partial sum is an integer <= 256); 1 = K5, XOR / carry-save / POPC on the integer
+ * pipes.  Both give identical results; out_second of yavo_match always comes from K5. */
+int yavo_set_matcher(yavo_ctx *ctx, int kind);
 
 /* Brief::removeOutliers (src/BriefDescriptor.cc:213-231): keep[i] = dist[i] < max(2*min(dist), threshold).
  * O(n) host arithmetic on the distances yavo_match returned; returns the kept count (>= 0). */

@@ -134,6 +134,42 @@ def test_match_bit_exact(ctx, oracle, n1, n2):
     assert np.array_equal(rev, erev)
 
 
+@pytest.mark.parametrize("matcher", ["tc", "popc"])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (7, 3), (127, 255), (128, 256), (129, 257), (2000, 2000), (1950, 1949),
+                                   (333, 4097), (4096, 129), (300, 0), (0, 40), (9000, 7000)])
+def test_match_tensor_core_and_integer_kernels(ctx, oracle, matcher, n1, n2):
+    """Brief::matchFeatures (src/BriefDescriptor.cc:163-183) through both device matchers: the tcgen05 kernel works on
+    +-1.0 FP8 expansions of the bits (every partial sum is an integer <= 256, exact in FP32), the other one on
+    XOR / POPC; distances, indices and the first-minimum rule must agree with the oracle bit for bit, including
+    all-equal descriptors (every distance 0 -> index 0), exact duplicates and tile-boundary sizes."""
+    d1 = synth.synth_descriptors(n1, n1 * 131 + n2)
+    d2 = synth.planted_descriptors(d1, n2, 7) if (n1 and n2) else synth.synth_descriptors(n2, 1)
+    if n2 > 300:
+        d2[290] = d2[10]   # duplicated train descriptors in different tiles: the lowest index wins
+        d2[40] = d2[10]
+    if n1 > 5 and n2 > 5:
+        d1[3] = d2[5]      # distance 0
+        d1[4] = ~d2[5]     # distance 256 to one train descriptor
+    ctx.set_matcher(matcher)
+    try:
+        idx, dist = ctx.match(d1, d2)
+    finally:
+        ctx.set_matcher("tc")
+    eidx, edist = oracle.match(d1, d2)
+    assert np.array_equal(dist, edist)
+    assert np.array_equal(idx, eidx)
+
+
+def test_match_tensor_core_extreme_distances(ctx, oracle):
+    """all-zero vs all-one descriptors (distance 256 everywhere) and identical sets (distance 0, ties on every row)"""
+    z = np.zeros((300, 32), np.uint8)
+    o = np.full((520, 32), 255, np.uint8)
+    for a, b in ((z, o), (o, z), (z, z[:257]), (o, o)):
+        idx, dist = ctx.match(a, b)
+        eidx, edist = oracle.match(a, b)
+        assert np.array_equal(idx, eidx) and np.array_equal(dist, edist)
+
+
 def test_frontend_batch_matches_oracle_pipeline(cuda_lib, oracle, offsets, kitti):
     """configs 2/3 in miniature: consecutive frames, FAST+BRIEF on each, match f-1 -> f."""
     a = synth.synth_frame("G30", 1000)

@@ -26,7 +26,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
-    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free", "yavo_set_matcher",
 ]
 
 
@@ -132,7 +132,7 @@ class Context:
         return int(self._L.yavo_get_stream(self._h) or 0)
 
     KERNEL_CLASSES = ("repitch", "detect_blur", "compact_score", "select_topk", "brief", "match_partial", "match_reduce",
-                      "filter_pairs", "pyr_down", "klt_track", "epipolar_inliers")
+                      "filter_pairs", "pyr_down", "klt_track", "epipolar_inliers", "match_tc")
 
     def set_profiling(self, on):
         self._ck(self._L.yavo_set_profiling(self._h, int(bool(on))))
@@ -258,6 +258,10 @@ class Context:
         self._ck(self._L.yavo_filter_pairs(self._h, int(slot0), int(n), int(threshold), _p(n_pairs), _p(min_dist),
                                            _p(pairs)))
         return n_pairs, min_dist, pairs
+
+    def set_matcher(self, kind):
+        """0 = tensor-core matcher (default), 1 = POPC matcher; identical results."""
+        self._ck(self._L.yavo_set_matcher(self._h, {"tc": 0, "popc": 1}.get(kind, kind)))
 
     def set_sub_batch(self, frames):
         self._ck(self._L.yavo_set_sub_batch(self._h, int(frames)))

@@ -160,8 +160,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
                 const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
                 size_t set_stride_words, int q_set_offset, int t_set_offset, int pairs, int q_tiles, int out_stride,
-                int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_dots,
-                int desc_variant) {
+                int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_dots = nullptr) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bars[6 * NSTAGE];
     __shared__ uint32_t tmem_base_s;
@@ -253,16 +252,14 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
             if (n_tiles > 0) {
                 if (lane == 0) {
                     const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
-                    const uint32_t a_lbo = desc_variant ? 128u : TQ * 16u, a_sbo = desc_variant ? TQ * 16u : 128u;
-                    const uint32_t b_lbo = desc_variant ? 128u : TT * 16u, b_sbo = desc_variant ? TT * 16u : 128u;
-                    const uint64_t adesc0 = smem_desc(saddr(sA + as * A_BYTES), a_lbo, a_sbo);
+                    const uint64_t adesc0 = smem_desc(saddr(sA + as * A_BYTES), TQ * 16u, 128u);
                     bar_wait(&a_full[as], aph);
                     for (int t = 0; t < n_tiles; t++, t_cnt++) {
                         const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
                         bar_wait(&b_full[s], ph);
                         bar_wait(&acc_empty[s], ph ^ 1);
                         fence_after_sync();
-                        const uint64_t bdesc0 = smem_desc(saddr(sB + s * B_BYTES), b_lbo, b_sbo);
+                        const uint64_t bdesc0 = smem_desc(saddr(sB + s * B_BYTES), TT * 16u, 128u);
                         const uint32_t tacc = tmem_base + s * TT;
 #pragma unroll
                         for (int k = 0; k < KBYTES / 32; k++)  // K = 32 operand bytes (two 16-byte chunks) per instruction
