@@ -99,8 +99,8 @@ int main(int argc, char **argv) {
                 for (int j = 0; j < std::min(256, n[1]); j++) {
                     int d = 0;
                     for (int w = 0; w < 8; w++) d += __builtin_popcount(Q[i * 8 + w] ^ T[j * 8 + w]);
-                    if (dots[i * 256 + j] != (float)(256 - 2 * d)) {
-                        if (dot_bad < 8) printf("dot[%d][%d] = %g, expected %d\n", i, j, dots[i * 256 + j], 256 - 2 * d);
+                    if (dots[i * 256 + j] != (float)(256 * d + j - 32768)) {
+                        if (dot_bad < 8) printf("acc[%d][%d] = %g, expected %d\n", i, j, dots[i * 256 + j], 256 * d + j - 32768);
                         dot_bad++;
                     }
                 }

@@ -4,11 +4,15 @@
 // for every query descriptor the train descriptor with the smallest 256-bit Hamming distance, the LOWEST
 // train index among equal minima.
 //
-// Formulation.  A descriptor bit b is written as the FP8 (e4m3) number +1.0 (b = 0, byte 0x38) or -1.0
-// (b = 1, byte 0xB8).  Then for two descriptors  dot = sum_k a_k * b_k = 256 - 2 * hamming,  every partial sum is
-// an integer of magnitude <= 256 and therefore exact in the FP32 accumulator: the result is bit-exact integer
-// arithmetic, only carried out by tcgen05.mma (kind::f8f6f4, M = 128 queries x N = 256 train x K = 32 per
-// instruction, 8 instructions per 128 x 256 tile) instead of 4.2 M XOR/POPC chains per frame pair.
+// Formulation.  A query bit b is written as the FP8 (e4m3) number +1.0 (b = 0, byte 0x38) or -1.0 (b = 1, byte
+// 0xB8), a train bit as -128.0 (b = 0, byte 0xF0) or +128.0 (b = 1, byte 0x70).  Over the 256 bit positions
+//   sum_k a_k * b_k = -128 * (256 - 2 * hamming) = 256 * hamming - 32768,
+// and a ninth K slice adds the train column: query bytes {1, 16, 0, ...} times train bytes {j & 15, j >> 4, 0, ...}
+// = j, so the accumulator itself holds  key - 32768  with  key = 256 * hamming + j  — the (distance, index) pair
+// whose minimum is the reference's "first minimum wins".  Every product and every partial sum is an integer of
+// magnitude < 2^16, exact in the FP32 accumulator: this is bit-exact integer arithmetic carried out by
+// tcgen05.mma (kind::f8f6f4, M = 128 queries x N = 256 train x K = 32 per instruction, 9 instructions per
+// 128 x 256 tile) instead of 4.2 M XOR/POPC chains per frame pair, and the epilogue is a bare minimum.
 //
 // One persistent CTA per SM, three warp roles connected by mbarriers:
 //   * expander warps: read the packed descriptors (32 bytes each) from global memory and write the +-1.0
@@ -19,9 +23,8 @@
 //   * one MMA thread: 8 tcgen05.mma per train tile into one of two 128 x 256 FP32 accumulators in TMEM,
 //     tcgen05.commit onto the mbarriers that free the operand stage and publish the accumulator.
 //   * four epilogue warps (one per TMEM lane quarter, thread = query row): tcgen05.ld 32 columns at a time,
-//     key = 256 * distance + column as ONE FFMA (32768 + j - 128 * dot), running minimum of the keys = the
-//     reference's first-minimum rule inside a tile; tiles are visited in ascending order and only a strictly
-//     smaller distance replaces the best one, which extends the rule across tiles.
+//     one 3-input minimum per two keys on four independent chains; tiles are visited in ascending order and
+//     only a strictly smaller distance replaces the best one, which extends the first-minimum rule across tiles.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -39,7 +42,9 @@ constexpr int EPI_WARPS = 4;            // warps 0..3: TMEM lane quarter == warp
 constexpr int MMA_WARP = EPI_WARPS;     // warp 4
 constexpr int EXP_WARPS = 8;            // warps 5..12
 constexpr int THREADS = 32 * (EPI_WARPS + 1 + EXP_WARPS);
-constexpr int SMEM_BYTES = NSTAGE * (A_BYTES + B_BYTES);
+constexpr int AX_BYTES = TQ * 32;        // constant ninth K slice of the queries  {1, 16, 0, ...}
+constexpr int BX_BYTES = TT * 32;        // constant ninth K slice of a train tile {j & 15, j >> 4, 0, ...}
+constexpr int SMEM_BYTES = NSTAGE * (A_BYTES + B_BYTES) + AX_BYTES + BX_BYTES;
 constexpr uint32_t TMEM_COLS = 512;     // two 128 x 256 FP32 accumulators
 
 __device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -118,44 +123,61 @@ __device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" : YAVO_TM32_RW(v)::"memory");
 }
 
+// (a & b) | c  and  (a & b) ^ c  as ONE LOP3 each (two different immediates would cost the compiler two)
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0x6A;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // Words 4h..4h+3 of one descriptor -> operand chunks 8h..8h+7 of row r of a tile with R rows.
-__device__ __forceinline__ void expand_half(uint8_t *tile, int R, int r, int h, const uint4 &w) {
+// TRAIN = false: bytes +-1.0 (0x38 | sign);  TRAIN = true: bytes -+128.0 (0xF0 ^ sign).
+template <bool TRAIN>
+__device__ __forceinline__ void expand_half(uint8_t *tile, int R, int r, int h, const uint4 &w, uint32_t msk, uint32_t cst) {
     const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         uint32_t o[8];
 #pragma unroll
-        for (int s = 0; s < 8; s++) o[s] = ((ws[i] << (7 - s)) & 0x80808080u) | 0x38383838u;
+        for (int s = 0; s < 8; s++) o[s] = TRAIN ? and_xor(ws[i] << (7 - s), msk, cst) : and_or(ws[i] << (7 - s), msk, cst);
         uint8_t *p = tile + (size_t)(8 * h + 2 * i) * R * 16 + r * 16;
         *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
         *reinterpret_cast<uint4 *>(p + R * 16) = make_uint4(o[4], o[5], o[6], o[7]);
     }
 }
 
-// running minimum over 32 accumulator columns; JB = first column of the chunk inside the tile
-template <int JB>
-__device__ __forceinline__ float min_keys(const uint32_t (&v)[32], float m, int lim) {
-    if (lim >= 32) {
+// e4m3 byte of an integer 0..16 (exact: at most four significant bits)
+__device__ __forceinline__ uint32_t e4m3_small_int(uint32_t n) {
+    if (n == 0) return 0;
+    const uint32_t e = 31 - __clz(n);
+    return ((e + 7) << 3) | (((n << 3) >> e) & 7);
+}
+
+// running minima (four independent chains) over 32 accumulator columns that already hold key - 32768;
+// col0 = first column of the chunk inside the tile, nvalid = train descriptors in this tile
+__device__ __forceinline__ void min_keys(const uint32_t (&v)[32], float (&m)[4], int col0, int nvalid) {
+    if (col0 + 32 <= nvalid) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-            const float k0 = __fmaf_rn(__uint_as_float(v[i]), -128.0f, 32768.0f + (float)(JB + i));
-            const float k1 = __fmaf_rn(__uint_as_float(v[i + 1]), -128.0f, 32768.0f + (float)(JB + i + 1));
-            m = fminf(m, fminf(k0, k1));
+        for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) m[c] = fminf(m[c], fminf(__uint_as_float(v[i + 2 * c]), __uint_as_float(v[i + 2 * c + 1])));
         }
     } else {  // last tile of a train set: columns beyond the set do not take part
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            const float k = __fmaf_rn(__uint_as_float(v[i]), -128.0f, 32768.0f + (float)(JB + i));
-            if (i < lim) m = fminf(m, k);
-        }
+        for (int i = 0; i < 32; i++)
+            if (col0 + i < nvalid) m[i & 3] = fminf(m[i & 3], __uint_as_float(v[i]));
     }
-    return m;
 }
 
 // Work item = (pair, tile of TQ queries).  Set addressing as in match_partial_kernel: pair p takes its queries
 // from set p + q_set_offset and its train descriptors from set p + t_set_offset of arrays with set_stride_words
 // words per set; n*_all == nullptr means every set holds n*_fixed descriptors.  out_* rows have out_stride entries.
-// dbg_dots (test tool only): the 128 x 256 dot products of the first tile of work item 0.
+// dbg_dots (test tool only): the 128 x 256 accumulator values (key - 32768) of the first tile of work item 0.
 __global__ void __launch_bounds__(THREADS, 1)
 match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
                 const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
@@ -167,6 +189,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
     uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *b_full = bars + 2 * NSTAGE, *b_empty = bars + 3 * NSTAGE;
     uint64_t *acc_full = bars + 4 * NSTAGE, *acc_empty = bars + 5 * NSTAGE;
     uint8_t *sA = smem_raw, *sB = smem_raw + NSTAGE * A_BYTES;
+    uint8_t *sAX = sB + NSTAGE * B_BYTES, *sBX = sAX + AX_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
@@ -180,6 +203,16 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // constant ninth K slice (two 16-byte chunks per row, the second one zero)
+    for (int i = threadIdx.x; i < TQ + TT; i += THREADS) {
+        const bool q = i < TQ;
+        const int r = q ? i : i - TQ;
+        uint8_t *p = q ? sAX + r * 16 : sBX + r * 16;
+        const uint32_t w0 = q ? (0x38u | (0x58u << 8)) : (e4m3_small_int(r & 15) | (e4m3_small_int(r >> 4) << 8));
+        *reinterpret_cast<uint4 *>(p) = make_uint4(w0, 0, 0, 0);
+        *reinterpret_cast<uint4 *>(p + (q ? TQ : TT) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -210,33 +243,27 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * TT;
                 const int nvalid = min(TT, nt - t * TT);
-                float m = 3.0e38f;
+                float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr, v0);
-#define YAVO_EPI_STEP(C)                                                                   \
-    {                                                                                      \
-        tmem_wait(v0);                                                                     \
-        if ((C + 1) * 32 < nvalid) tmem_ld32(taddr + (C + 1) * 32, v1);                    \
-        if (dbg_dots && item == 0 && t == 0)                                               \
-            for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + C * 32 + i] = __uint_as_float(v0[i]); \
-        m = min_keys<C * 32>(v0, m, nvalid - C * 32);                                      \
-        if ((C + 1) * 32 < nvalid) {                                                       \
-            tmem_wait(v1);                                                                 \
-            if ((C + 2) * 32 < nvalid) tmem_ld32(taddr + (C + 2) * 32, v0);                \
-            if (dbg_dots && item == 0 && t == 0)                                           \
-                for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + (C + 1) * 32 + i] = __uint_as_float(v1[i]); \
-            m = min_keys<(C + 1) * 32>(v1, m, nvalid - (C + 1) * 32);                      \
-        }                                                                                  \
-    }
-                YAVO_EPI_STEP(0)
-                if (64 < nvalid) YAVO_EPI_STEP(2)
-                if (128 < nvalid) YAVO_EPI_STEP(4)
-                if (192 < nvalid) YAVO_EPI_STEP(6)
-#undef YAVO_EPI_STEP
+#pragma unroll 1
+                for (int c = 0; c < TT / 64; c++) {
+                    tmem_wait(v0);
+                    tmem_ld32(taddr + c * 64 + 32, v1);
+                    if (dbg_dots && item == 0 && t == 0)
+                        for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + c * 64 + i] = __uint_as_float(v0[i]);
+                    min_keys(v0, m4, c * 64, nvalid);
+                    tmem_wait(v1);
+                    if (c + 1 < TT / 64) tmem_ld32(taddr + c * 64 + 64, v0);
+                    if (dbg_dots && item == 0 && t == 0)
+                        for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + c * 64 + 32 + i] = __uint_as_float(v1[i]);
+                    min_keys(v1, m4, c * 64 + 32, nvalid);
+                }
+                const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) bar_arrive(&acc_empty[s]);
-                const int ki = (int)m;  // 256 * distance + column, exact
+                const int ki = (int)m + 32768;  // 256 * distance + column, exact
                 if ((ki >> 8) < best_d) {
                     best_d = ki >> 8;
                     best_j = t * TT + (ki & 255);
@@ -253,6 +280,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                 if (lane == 0) {
                     const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
                     const uint64_t adesc0 = smem_desc(saddr(sA + as * A_BYTES), TQ * 16u, 128u);
+                    const uint64_t adescx = smem_desc(saddr(sAX), TQ * 16u, 128u), bdescx = smem_desc(saddr(sBX), TT * 16u, 128u);
                     bar_wait(&a_full[as], aph);
                     for (int t = 0; t < n_tiles; t++, t_cnt++) {
                         const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
@@ -264,6 +292,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
 #pragma unroll
                         for (int k = 0; k < KBYTES / 32; k++)  // K = 32 operand bytes (two 16-byte chunks) per instruction
                             mma_f8(tacc, adesc0 + (uint64_t)((k * 2 * TQ * 16) >> 4), bdesc0 + (uint64_t)((k * 2 * TT * 16) >> 4), k > 0);
+                        mma_f8(tacc, adescx, bdescx, 1);  // + column index
                         mma_commit(&b_empty[s]);
                         mma_commit(&acc_full[s]);
                     }
@@ -284,7 +313,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                     const int r = (ew >> 1) * 32 + lane, h = ew & 1;
                     const uint4 w = (q0 + r < nq) ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8) + h) : zero;
                     bar_wait(&a_empty[as], aph ^ 1);
-                    expand_half(sA + as * A_BYTES, TQ, r, h, w);
+                    expand_half<false>(sA + as * A_BYTES, TQ, r, h, w, 0x80808080u, 0x38383838u);
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) bar_arrive(&a_full[as]);
@@ -300,8 +329,8 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                     const uint4 n0 = more ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)rn * 8)) : zero;
                     const uint4 n1 = more ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)rn * 8) + 1) : zero;
                     bar_wait(&b_empty[s], ph ^ 1);
-                    expand_half(sB + s * B_BYTES, TT, r, 0, c0);
-                    expand_half(sB + s * B_BYTES, TT, r, 1, c1);
+                    expand_half<true>(sB + s * B_BYTES, TT, r, 0, c0, 0x80808080u, 0xF0F0F0F0u);
+                    expand_half<true>(sB + s * B_BYTES, TT, r, 1, c1, 0x80808080u, 0xF0F0F0F0u);
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) bar_arrive(&b_full[s]);
