@@ -63,7 +63,7 @@ int main(int argc, char **argv) {
     CK(cudaMemset(d_idx, 0xee, (size_t)pairs * stride * 4));
     CK(cudaMemset(d_dist, 0xee, (size_t)pairs * stride * 4));
     CK(cudaMemset(d_dots, 0, 128 * 256 * 4));
-    CK(cudaFuncSetAttribute(yavo::tcm::match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, yavo::tcm::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(yavo::tcm::match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, yavo::tcm::SMEM_BYTES));
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -74,7 +74,7 @@ int main(int argc, char **argv) {
     float best_ms = 1e30f;
     for (int rep = 0; rep < reps; rep++) {
         CK(cudaEventRecord(e0));
-        yavo::tcm::match_tc_kernel<<<grid, yavo::tcm::THREADS, yavo::tcm::SMEM_BYTES>>>(
+        yavo::tcm::match_tc_kernel<true><<<grid, yavo::tcm::THREADS, yavo::tcm::SMEM_BYTES>>>(
             d_desc, d_n, 0, d_desc, d_n, 0, (size_t)stride * 8, 0, 1, pairs, q_tiles, stride, d_idx, d_dist,
             rep == 0 ? d_dots : nullptr);
         CK(cudaEventRecord(e1));

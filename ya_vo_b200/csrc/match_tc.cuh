@@ -15,8 +15,9 @@
 // 128 x 256 tile) instead of 4.2 M XOR/POPC chains per frame pair, and the epilogue is a bare minimum.
 //
 // One persistent CTA per SM, three warp roles connected by mbarriers:
-//   * expander warps: read the packed descriptors (32 bytes each) from global memory and write the +-1.0
-//     bytes into shared memory directly in the canonical K-major, non-swizzled UMMA operand layout
+//   * one loader thread: cp.async.bulk (TMA engine) of the packed descriptors (32 bytes each) of the next operand
+//     tiles into a small shared-memory ring, completion on an mbarrier;
+//   * expander warps: read the packed bits from the ring and write the FP8 bytes into shared memory directly in the canonical K-major, non-swizzled UMMA operand layout
 //     (8 x 16-byte core matrices: chunk c of row r at  c * rows * 16 + r * 16);  one SHF + one LOP3 per four
 //     operand bytes.  The order of the 256 bit positions along K is permuted (bit 8b+s of word i sits at
 //     k = 32 i + 4 s + b), identically for both operands, which a dot product does not see.
@@ -38,13 +39,16 @@ constexpr int KBYTES = 256;             // operand bytes per descriptor (one FP8
 constexpr int A_BYTES = TQ * KBYTES;    // 32 KB
 constexpr int B_BYTES = TT * KBYTES;    // 64 KB
 constexpr int NSTAGE = 2;               // operand stages (A: per work item, B: per train tile) and accumulators
-constexpr int EPI_WARPS = 4;            // warps 0..3: TMEM lane quarter == warp index
-constexpr int MMA_WARP = EPI_WARPS;     // warp 4
-constexpr int EXP_WARPS = 8;            // warps 5..12
-constexpr int THREADS = 32 * (EPI_WARPS + 1 + EXP_WARPS);
+constexpr int EPI_WARPS = 8;            // warps 0..7: TMEM lane quarter == warp & 3, accumulator == warp >> 2
+constexpr int MMA_WARP = EPI_WARPS;     // warp 8
+constexpr int EXP_WARPS = 8;            // warps 9..16
+constexpr int LOAD_WARP = EPI_WARPS + 1 + EXP_WARPS;  // warp 17: one thread issues the bulk copies of the packed bits
+constexpr int THREADS = 32 * (EPI_WARPS + 2 + EXP_WARPS);
+constexpr int NRING = 2;                // packed-descriptor ring: one entry = the bits of one operand tile
+constexpr int RING_BYTES = TT * 32;     // 8 KB
 constexpr int AX_BYTES = TQ * 32;        // constant ninth K slice of the queries  {1, 16, 0, ...}
 constexpr int BX_BYTES = TT * 32;        // constant ninth K slice of a train tile {j & 15, j >> 4, 0, ...}
-constexpr int SMEM_BYTES = NSTAGE * (A_BYTES + B_BYTES) + AX_BYTES + BX_BYTES;
+constexpr int SMEM_BYTES = NSTAGE * (A_BYTES + B_BYTES) + AX_BYTES + BX_BYTES + NRING * RING_BYTES;
 constexpr uint32_t TMEM_COLS = 512;     // two 128 x 256 FP32 accumulators
 
 __device__ __forceinline__ uint32_t saddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -66,6 +70,15 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
         "}\n" ::"r"(saddr(bar)),
         "r"(parity)
         : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+}
+// bulk asynchronous copy global -> shared (TMA engine), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(dst)),
+                 "l"(src), "r"(bytes), "r"(saddr(bar))
+                 : "memory");
 }
 // tcgen05.commit: the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread is done
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
@@ -138,16 +151,23 @@ __device__ __forceinline__ uint32_t and_xor(uint32_t a, uint32_t b, uint32_t c) 
 // Words 4h..4h+3 of one descriptor -> operand chunks 8h..8h+7 of row r of a tile with R rows.
 // TRAIN = false: bytes +-1.0 (0x38 | sign);  TRAIN = true: bytes -+128.0 (0xF0 ^ sign).
 template <bool TRAIN>
-__device__ __forceinline__ void expand_half(uint8_t *tile, int R, int r, int h, const uint4 &w, uint32_t msk, uint32_t cst) {
-    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
+__device__ __forceinline__ void expand_half(uint32_t tile /* shared-window address */, int R, int r, int h, const uint4 &w, uint32_t msk, uint32_t cst) {
+    uint32_t w0 = w.x, w1 = w.y, w2 = w.z, w3 = w.w;
+    uint32_t p = tile + (uint32_t)(8 * h * R * 16 + r * 16);
+    // a real loop over the four words: the stores of one word go out before the ALU work of the next one (fully
+    // unrolled, ptxas gathers all 16 stores of a row at the end and every expander warp stalls on the store
+    // queue at the same time)
+#pragma unroll 1
     for (int i = 0; i < 4; i++) {
         uint32_t o[8];
 #pragma unroll
-        for (int s = 0; s < 8; s++) o[s] = TRAIN ? and_xor(ws[i] << (7 - s), msk, cst) : and_or(ws[i] << (7 - s), msk, cst);
-        uint8_t *p = tile + (size_t)(8 * h + 2 * i) * R * 16 + r * 16;
-        *reinterpret_cast<uint4 *>(p) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4 *>(p + R * 16) = make_uint4(o[4], o[5], o[6], o[7]);
+        for (int s = 0; s < 8; s++) o[s] = TRAIN ? and_xor(w0 << (7 - s), msk, cst) : and_or(w0 << (7 - s), msk, cst);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p + R * 16), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+        p += 2 * R * 16;
+        w0 = w1;
+        w1 = w2;
+        w2 = w3;
     }
 }
 
@@ -159,15 +179,16 @@ __device__ __forceinline__ uint32_t e4m3_small_int(uint32_t n) {
 }
 
 // running minima (four independent chains) over 32 accumulator columns that already hold key - 32768;
-// col0 = first column of the chunk inside the tile, nvalid = train descriptors in this tile
+// FULL = false: col0 = first column of the chunk inside the tile, nvalid = train descriptors in this tile
+template <bool FULL>
 __device__ __forceinline__ void min_keys(const uint32_t (&v)[32], float (&m)[4], int col0, int nvalid) {
-    if (col0 + 32 <= nvalid) {
+    if (FULL) {
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
 #pragma unroll
             for (int c = 0; c < 4; c++) m[c] = fminf(m[c], fminf(__uint_as_float(v[i + 2 * c]), __uint_as_float(v[i + 2 * c + 1])));
         }
-    } else {  // last tile of a train set: columns beyond the set do not take part
+    } else {  // columns beyond the set do not take part
 #pragma unroll
         for (int i = 0; i < 32; i++)
             if (col0 + i < nvalid) m[i & 3] = fminf(m[i & 3], __uint_as_float(v[i]));
@@ -178,28 +199,35 @@ __device__ __forceinline__ void min_keys(const uint32_t (&v)[32], float (&m)[4],
 // from set p + q_set_offset and its train descriptors from set p + t_set_offset of arrays with set_stride_words
 // words per set; n*_all == nullptr means every set holds n*_fixed descriptors.  out_* rows have out_stride entries.
 // dbg_dots (test tool only): the 128 x 256 accumulator values (key - 32768) of the first tile of work item 0.
+template <bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
 match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
                 const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
                 size_t set_stride_words, int q_set_offset, int t_set_offset, int pairs, int q_tiles, int out_stride,
-                int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_dots = nullptr) {
+                int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_dots) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bars[6 * NSTAGE];
+    __shared__ uint64_t bars[6 * NSTAGE + 2 * NRING];
     __shared__ uint32_t tmem_base_s;
+    __shared__ int2 comb[2][TQ];  // (distance, index) of accumulator group 1, double-buffered over work items
     uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *b_full = bars + 2 * NSTAGE, *b_empty = bars + 3 * NSTAGE;
     uint64_t *acc_full = bars + 4 * NSTAGE, *acc_empty = bars + 5 * NSTAGE;
+    uint64_t *r_full = bars + 6 * NSTAGE, *r_empty = r_full + NRING;
     uint8_t *sA = smem_raw, *sB = smem_raw + NSTAGE * A_BYTES;
-    uint8_t *sAX = sB + NSTAGE * B_BYTES, *sBX = sAX + AX_BYTES;
+    uint8_t *sAX = sB + NSTAGE * B_BYTES, *sBX = sAX + AX_BYTES, *sRing = sBX + BX_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) {
-            bar_init(&a_full[s], EXP_WARPS);
+            bar_init(&a_full[s], EXP_WARPS / 2);
             bar_init(&a_empty[s], 1);
-            bar_init(&b_full[s], EXP_WARPS);
+            bar_init(&b_full[s], EXP_WARPS / 2);
             bar_init(&b_empty[s], 1);
             bar_init(&acc_full[s], 1);
-            bar_init(&acc_empty[s], EPI_WARPS);
+            bar_init(&acc_empty[s], EPI_WARPS / 2);
+        }
+        for (int s = 0; s < NRING; s++) {
+            bar_init(&r_full[s], 1);
+            bar_init(&r_empty[s], EXP_WARPS / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -223,6 +251,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
     const uint32_t tmem_base = tmem_base_s;
 
     const int items = pairs * q_tiles;
+    uint32_t e_cnt = 0;             // work items seen by the epilogue warps
     uint32_t a_cnt = 0, t_cnt = 0;  // A stages used so far (work items with train tiles); train tiles so far
 
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -235,44 +264,74 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
         const uint32_t *dt = dt_all + (size_t)(pair + t_set_offset) * set_stride_words;
 
         if (warp < EPI_WARPS) {
-            // ------------------------------------------------ epilogue: thread = query row
+            // ------------------------------------------------ epilogue: thread = query row; warps 0-3 drain
+            // accumulator 0 (every other tile), warps 4-7 accumulator 1, lane quarter = warp & 3
+            const int g = warp >> 2, row = (warp & 3) * 32 + lane;
             int best_d = 0x7fffffff, best_j = -1;
-            for (int t = 0; t < n_tiles; t++, t_cnt++) {
-                const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
-                bar_wait(&acc_full[s], ph);
+            for (int t = ((t_cnt & 1) == (uint32_t)g) ? 0 : 1; t < n_tiles; t += 2) {
+                const uint32_t ph = ((t_cnt + t) >> 1) & 1;
+                bar_wait(&acc_full[g], ph);
                 fence_after_sync();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + s * TT;
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * TT;
                 const int nvalid = min(TT, nt - t * TT);
                 float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
                 uint32_t v0[32], v1[32];
                 tmem_ld32(taddr, v0);
+                if (nvalid == TT) {
 #pragma unroll 1
-                for (int c = 0; c < TT / 64; c++) {
-                    tmem_wait(v0);
-                    tmem_ld32(taddr + c * 64 + 32, v1);
-                    if (dbg_dots && item == 0 && t == 0)
-                        for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + c * 64 + i] = __uint_as_float(v0[i]);
-                    min_keys(v0, m4, c * 64, nvalid);
-                    tmem_wait(v1);
-                    if (c + 1 < TT / 64) tmem_ld32(taddr + c * 64 + 64, v0);
-                    if (dbg_dots && item == 0 && t == 0)
-                        for (int i = 0; i < 32; i++) dbg_dots[(warp * 32 + lane) * TT + c * 64 + 32 + i] = __uint_as_float(v1[i]);
-                    min_keys(v1, m4, c * 64 + 32, nvalid);
+#if defined(YAVO_TC_EXP_EPI_HALF)
+                    for (int c = 0; c < TT / 128; c++) {
+#elif defined(YAVO_TC_EXP_NO_EPI)
+                    for (int c = 0; c < 0; c++) {
+#else
+                    for (int c = 0; c < TT / 64; c++) {
+#endif
+                        tmem_wait(v0);
+                        tmem_ld32(taddr + c * 64 + 32, v1);
+                        if (DBG && dbg_dots && item == 0 && t == 0)
+                            for (int i = 0; i < 32; i++) dbg_dots[row * TT + c * 64 + i] = __uint_as_float(v0[i]);
+                        min_keys<true>(v0, m4, 0, 0);
+                        tmem_wait(v1);
+                        if (c + 1 < TT / 64) tmem_ld32(taddr + c * 64 + 64, v0);
+                        if (DBG && dbg_dots && item == 0 && t == 0)
+                            for (int i = 0; i < 32; i++) dbg_dots[row * TT + c * 64 + 32 + i] = __uint_as_float(v1[i]);
+                        min_keys<true>(v1, m4, 0, 0);
+                    }
+                } else {  // last tile of a train set
+#pragma unroll 1
+                    for (int c = 0; c < TT / 32; c++) {
+                        tmem_wait(v0);
+                        min_keys<false>(v0, m4, c * 32, nvalid);
+                        if (c + 1 < TT / 32) tmem_ld32(taddr + c * 32 + 32, v0);
+                    }
                 }
                 const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) bar_arrive(&acc_empty[s]);
+                if (lane == 0) bar_arrive(&acc_empty[g]);
                 const int ki = (int)m + 32768;  // 256 * distance + column, exact
                 if ((ki >> 8) < best_d) {
                     best_d = ki >> 8;
                     best_j = t * TT + (ki & 255);
                 }
             }
-            const int q = q0 + warp * 32 + lane;
-            if (q < nq) {
-                out_idx[(size_t)pair * out_stride + q] = best_j;  // empty train set: -1 / INT_MAX as the reference leaves it
-                out_dist[(size_t)pair * out_stride + q] = best_d;
+            t_cnt += n_tiles;
+            // combine the two accumulator groups: smallest distance, then smallest index
+            int2 *cb = comb[e_cnt & 1];
+            e_cnt++;
+            if (g == 1) cb[row] = make_int2(best_d, best_j);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            if (g == 0) {
+                const int2 o = cb[row];
+                if (o.x < best_d || (o.x == best_d && o.y < best_j)) {
+                    best_d = o.x;
+                    best_j = o.y;
+                }
+                const int q = q0 + row;
+                if (q < nq) {
+                    out_idx[(size_t)pair * out_stride + q] = best_j;  // empty train set: -1 / INT_MAX as the reference leaves it
+                    out_dist[(size_t)pair * out_stride + q] = best_d;
+                }
             }
         } else if (warp == MMA_WARP) {
             // ------------------------------------------------ MMA issue: one thread
@@ -290,9 +349,17 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                         const uint64_t bdesc0 = smem_desc(saddr(sB + s * B_BYTES), TT * 16u, 128u);
                         const uint32_t tacc = tmem_base + s * TT;
 #pragma unroll
+#if defined(YAVO_TC_EXP_MMA_HALF)
+                        for (int k = 0; k < KBYTES / 64; k++)
+#elif defined(YAVO_TC_EXP_NO_MMA)
+                        for (int k = 0; k < 0; k++)
+#else
                         for (int k = 0; k < KBYTES / 32; k++)  // K = 32 operand bytes (two 16-byte chunks) per instruction
+#endif
                             mma_f8(tacc, adesc0 + (uint64_t)((k * 2 * TQ * 16) >> 4), bdesc0 + (uint64_t)((k * 2 * TT * 16) >> 4), k > 0);
+#ifndef YAVO_TC_EXP_NO_MMA
                         mma_f8(tacc, adescx, bdescx, 1);  // + column index
+#endif
                         mma_commit(&b_empty[s]);
                         mma_commit(&acc_full[s]);
                     }
@@ -303,39 +370,63 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                 a_cnt++;
                 __syncwarp();
             }
+        } else if (warp == LOAD_WARP) {
+            // ------------------------------------------------ loader: packed bits of the operand tiles -> ring
+            // (the expanders must not have global loads in flight: their proxy fence waits for them)
+            if (n_tiles > 0 && lane == 0) {
+                for (int t = 0; t < n_tiles; t++, t_cnt++) {  // ring stage = operand stage = expander group
+                    const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                    const uint32_t bytes = 32u * (uint32_t)min(TT, nt - t * TT);
+                    bar_wait(&r_empty[s], ph ^ 1);
+                    bar_expect_tx(&r_full[s], bytes);
+                    bulk_load(sRing + s * RING_BYTES, dt + (size_t)t * TT * 8, bytes, &r_full[s]);
+                }
+            } else {
+                t_cnt += n_tiles;
+            }
         } else {
-            // ------------------------------------------------ expanders: packed bits -> +-1.0 operand bytes
+            // ------------------------------------------------ expanders: packed bits -> FP8 operand bytes
+            // Two groups of four warps take alternate tiles (group = operand stage), so that one group's proxy
+            // fence (hundreds of cycles) runs under the other group's ALU work.
             if (n_tiles > 0) {
-                const int ew = warp - (EPI_WARPS + 1);  // 0..7
+                const int ew = warp - (EPI_WARPS + 1), ge = ew >> 2, k = ew & 3;
                 const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
                 const uint4 zero = make_uint4(0, 0, 0, 0);
-                {   // A: 4 row groups of 32 x 2 halves = 8 tasks, one per warp
-                    const int r = (ew >> 1) * 32 + lane, h = ew & 1;
-                    const uint4 w = (q0 + r < nq) ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8) + h) : zero;
+                if (ge == (int)as) {  // query tile: rows k*32 .. +31, both halves (once per work item: plain loads)
+                    const int r = k * 32 + lane;
+                    const bool in = q0 + r < nq;
+                    const uint4 w0 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8)) : zero;
+                    const uint4 w1 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8) + 1) : zero;
                     bar_wait(&a_empty[as], aph ^ 1);
-                    expand_half<false>(sA + as * A_BYTES, TQ, r, h, w, 0x80808080u, 0x38383838u);
+                    expand_half<false>(saddr(sA + as * A_BYTES), TQ, r, 0, w0, 0x80808080u, 0x38383838u);
+                    expand_half<false>(saddr(sA + as * A_BYTES), TQ, r, 1, w1, 0x80808080u, 0x38383838u);
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) bar_arrive(&a_full[as]);
                 }
-                // B: 8 row groups x 2 halves = 16 tasks, two per warp (both halves of row group ew)
-                const int r = ew * 32 + lane;
-                uint4 c0 = (r < nt) ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)r * 8)) : zero;
-                uint4 c1 = (r < nt) ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)r * 8) + 1) : zero;
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
                     const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
-                    const int rn = (t + 1) * TT + r;  // prefetch the next tile's words before this one is expanded
-                    const bool more = (t + 1 < n_tiles) && rn < nt;
-                    const uint4 n0 = more ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)rn * 8)) : zero;
-                    const uint4 n1 = more ? __ldg(reinterpret_cast<const uint4 *>(dt + (size_t)rn * 8) + 1) : zero;
+                    if (ge != (int)s) continue;
+                    const uint32_t rs = s, rph = ph;
+                    const int r = k * 64 + lane;  // train tile: rows k*64 .. +63
+                    bar_wait(&r_full[rs], rph);
+                    const bool in0 = t * TT + r < nt, in1 = t * TT + r + 32 < nt;
+                    const uint8_t *src = sRing + rs * RING_BYTES + r * 32;
+                    const uint4 c0 = in0 ? *reinterpret_cast<const uint4 *>(src) : zero;
+                    const uint4 c1 = in0 ? *reinterpret_cast<const uint4 *>(src + 16) : zero;
+                    const uint4 c2 = in1 ? *reinterpret_cast<const uint4 *>(src + 1024) : zero;
+                    const uint4 c3 = in1 ? *reinterpret_cast<const uint4 *>(src + 1040) : zero;
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(&r_empty[rs]);
                     bar_wait(&b_empty[s], ph ^ 1);
-                    expand_half<true>(sB + s * B_BYTES, TT, r, 0, c0, 0x80808080u, 0xF0F0F0F0u);
-                    expand_half<true>(sB + s * B_BYTES, TT, r, 1, c1, 0x80808080u, 0xF0F0F0F0u);
+                    const uint32_t tile = saddr(sB + s * B_BYTES);
+                    expand_half<true>(tile, TT, r, 0, c0, 0x80808080u, 0xF0F0F0F0u);
+                    expand_half<true>(tile, TT, r, 1, c1, 0x80808080u, 0xF0F0F0F0u);
+                    expand_half<true>(tile, TT, r + 32, 0, c2, 0x80808080u, 0xF0F0F0F0u);
+                    expand_half<true>(tile, TT, r + 32, 1, c3, 0x80808080u, 0xF0F0F0F0u);
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) bar_arrive(&b_full[s]);
-                    c0 = n0;
-                    c1 = n1;
                 }
                 a_cnt++;
             }

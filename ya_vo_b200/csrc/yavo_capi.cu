@@ -571,7 +571,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), 64 * sizeof(int)));
     CKC(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)select_smem_bytes()));
-    CKC(cudaFuncSetAttribute(tcm::match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm::SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(tcm::match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm::SMEM_BYTES));
     CKC(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device));
 #undef CKC
     *out = c;
@@ -848,9 +848,9 @@ static int launch_match_tc(yavo_ctx *ctx, const uint32_t *dq_all, const int *nq_
     const long long items = (long long)pairs * q_tiles;
     if (items <= 0) return 0;
     const int grid = (int)std::min<long long>(items, ctx->n_sms);
-    PROF(KC_MATCH_TC, tcm::match_tc_kernel<<<grid, tcm::THREADS, tcm::SMEM_BYTES, ctx->stream>>>(
+    PROF(KC_MATCH_TC, tcm::match_tc_kernel<false><<<grid, tcm::THREADS, tcm::SMEM_BYTES, ctx->stream>>>(
                           dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
-                          out_stride, o_idx, o_dist));
+                          out_stride, o_idx, o_dist, nullptr));
     CK_LAUNCH();
     return 0;
 }
