@@ -132,9 +132,10 @@ int yavo_brief_describe(yavo_ctx *ctx, int slot, const int32_t *rows, const int3
 int yavo_match(yavo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int n2,
                int32_t *out_idx, int32_t *out_dist, int32_t *out_second, int32_t *out_rev_idx);
 
-/* Which kernel computes the matches: 0 (default) = K5t, tcgen05 tensor cores on +-1.0 FP8 expansions of the
- * descriptor bits (exact: every partial sum is an integer <= 256); 1 = K5, XOR / carry-save / POPC on the integer
- * pipes.  Both give identical results; out_second of yavo_match always comes from K5. */
+/* Which kernel computes the matches: 0 (default) = K5t4, tcgen05 tensor cores (kind::mxf4) on +-1 e2m1 expansions of
+ * the descriptor bits; 2 = K5t, the same on FP8 expansions (kind::f8f6f4); 1 = K5, XOR / carry-save / POPC on the integer
+ * pipes.  All three give identical results (every partial sum of the tensor-core forms is an integer < 2^16, exact in the
+ * FP32 accumulator); out_second of yavo_match always comes from K5. */
 int yavo_set_matcher(yavo_ctx *ctx, int kind);
 
 /* Brief::removeOutliers (src/BriefDescriptor.cc:213-231): keep[i] = dist[i] < max(2*min(dist), threshold).

@@ -134,8 +134,8 @@ def test_match_bit_exact(ctx, oracle, n1, n2):
     assert np.array_equal(rev, erev)
 
 
-@pytest.mark.parametrize("matcher", ["tc", "popc"])
-@pytest.mark.parametrize("n1,n2", [(1, 1), (7, 3), (127, 255), (128, 256), (129, 257), (2000, 2000), (1950, 1949),
+@pytest.mark.parametrize("matcher", ["tc", "tc8", "popc"])
+@pytest.mark.parametrize("n1,n2", [(1, 1), (7, 3), (127, 255), (128, 224), (128, 256), (129, 225), (129, 257), (500, 449), (2000, 2000), (1950, 1949),
                                    (333, 4097), (4096, 129), (300, 0), (0, 40), (9000, 7000)])
 def test_match_tensor_core_and_integer_kernels(ctx, oracle, matcher, n1, n2):
     """Brief::matchFeatures (src/BriefDescriptor.cc:163-183) through both device matchers: the tcgen05 kernel works on

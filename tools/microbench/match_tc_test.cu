@@ -9,7 +9,15 @@
 #include <random>
 #include <vector>
 
-#include "../../ya_vo_b200/csrc/match_tc.cuh"
+#include "../../ya_vo_b200/csrc/match_tc4.cuh"
+
+#ifdef TC4   // packed 4-bit operands (kind::mxf4), 128 x 224 tiles
+#define KERNEL yavo::tcm4::match_tc4_kernel<true>
+constexpr int TILE_N = yavo::tcm4::T4, SMEM = yavo::tcm4::SMEM4_BYTES;
+#else        // FP8 operands (kind::f8f6f4), 128 x 256 tiles
+#define KERNEL yavo::tcm::match_tc_kernel<true>
+constexpr int TILE_N = yavo::tcm::TT, SMEM = yavo::tcm::SMEM_BYTES;
+#endif
 
 #define CK(x)                                                                              \
     do {                                                                                   \
@@ -63,7 +71,7 @@ int main(int argc, char **argv) {
     CK(cudaMemset(d_idx, 0xee, (size_t)pairs * stride * 4));
     CK(cudaMemset(d_dist, 0xee, (size_t)pairs * stride * 4));
     CK(cudaMemset(d_dots, 0, 128 * 256 * 4));
-    CK(cudaFuncSetAttribute(yavo::tcm::match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, yavo::tcm::SMEM_BYTES));
+    CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     int dev = 0, sms = 0;
     CK(cudaGetDevice(&dev));
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -74,7 +82,7 @@ int main(int argc, char **argv) {
     float best_ms = 1e30f;
     for (int rep = 0; rep < reps; rep++) {
         CK(cudaEventRecord(e0));
-        yavo::tcm::match_tc_kernel<true><<<grid, yavo::tcm::THREADS, yavo::tcm::SMEM_BYTES>>>(
+        KERNEL<<<grid, yavo::tcm::THREADS, SMEM>>>(
             d_desc, d_n, 0, d_desc, d_n, 0, (size_t)stride * 8, 0, 1, pairs, q_tiles, stride, d_idx, d_dist,
             rep == 0 ? d_dots : nullptr);
         CK(cudaEventRecord(e1));
@@ -96,11 +104,11 @@ int main(int argc, char **argv) {
         const uint32_t *Q = &desc[(size_t)p * stride * 8], *T = &desc[(size_t)(p + 1) * stride * 8];
         if (p == 0)
             for (int i = 0; i < std::min(128, n[0]); i++)
-                for (int j = 0; j < std::min(256, n[1]); j++) {
+                for (int j = 0; j < std::min(TILE_N, n[1]); j++) {
                     int d = 0;
                     for (int w = 0; w < 8; w++) d += __builtin_popcount(Q[i * 8 + w] ^ T[j * 8 + w]);
-                    if (dots[i * 256 + j] != (float)(256 * d + j - 32768)) {
-                        if (dot_bad < 8) printf("acc[%d][%d] = %g, expected %d\n", i, j, dots[i * 256 + j], 256 * d + j - 32768);
+                    if (dots[i * TILE_N + j] != (float)(256 * d + j - 32768)) {
+                        if (dot_bad < 8) printf("acc[%d][%d] = %g, expected %d\n", i, j, dots[i * TILE_N + j], 256 * d + j - 32768);
                         dot_bad++;
                     }
                 }

@@ -260,8 +260,9 @@ class Context:
         return n_pairs, min_dist, pairs
 
     def set_matcher(self, kind):
-        """0 = tensor-core matcher (default), 1 = POPC matcher; identical results."""
-        self._ck(self._L.yavo_set_matcher(self._h, {"tc": 0, "popc": 1}.get(kind, kind)))
+        """'tc' / 0 = tensor-core matcher on packed 4-bit operands (default), 'tc8' / 2 = on FP8 operands,
+        'popc' / 1 = integer-pipe matcher; identical results."""
+        self._ck(self._L.yavo_set_matcher(self._h, {"tc": 0, "popc": 1, "tc8": 2}.get(kind, kind)))
 
     def set_sub_batch(self, frames):
         self._ck(self._L.yavo_set_sub_batch(self._h, int(frames)))

@@ -416,8 +416,6 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                     const uint4 c1 = in0 ? *reinterpret_cast<const uint4 *>(src + 16) : zero;
                     const uint4 c2 = in1 ? *reinterpret_cast<const uint4 *>(src + 1024) : zero;
                     const uint4 c3 = in1 ? *reinterpret_cast<const uint4 *>(src + 1040) : zero;
-                    __syncwarp();
-                    if (lane == 0) bar_arrive(&r_empty[rs]);
                     bar_wait(&b_empty[s], ph ^ 1);
                     const uint32_t tile = saddr(sB + s * B_BYTES);
                     expand_half<true>(tile, TT, r, 0, c0, 0x80808080u, 0xF0F0F0F0u);
@@ -426,7 +424,10 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                     expand_half<true>(tile, TT, r + 32, 1, c3, 0x80808080u, 0xF0F0F0F0u);
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) bar_arrive(&b_full[s]);
+                    if (lane == 0) {
+                        bar_arrive(&r_empty[rs]);  // only now: the ring reads above have certainly completed (their values were used)
+                        bar_arrive(&b_full[s]);
+                    }
                 }
                 a_cnt++;
             }

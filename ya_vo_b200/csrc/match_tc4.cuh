@@ -1,0 +1,346 @@
+// match_tc4.cuh — K5t4: the tensor-core Hamming matcher of match_tc.cuh on PACKED 4-bit operands
+// (tcgen05.mma kind::mxf4, block-scaled, K = 64 per instruction).  Same reference semantics
+// (Brief::matchFeatures, reference src/BriefDescriptor.cc:139-183) and the same bit-exact argument; what changes:
+//
+//   * a descriptor bit becomes one e2m1 nibble: query bit 0 -> +1.0 (0x2), 1 -> -1.0 (0xA); train bit 0 -> -1.0,
+//     1 -> +1.0, and the train operand's block scale factors (UE8M0, kept in TMEM) are all 2^7, the query operand's
+//     all 1: sum_k a_k * b_k * 128 = 256 * hamming - 32768, every partial sum an integer < 2^16, exact in FP32.
+//     Eight nibbles come out of ONE LOP3 ((w << k) & 0x88888888, | or ^ a constant) instead of four bytes, so the
+//     expansion — which the integer ALU pipe (64 lanes / clk / SM) bounds in the FP8 version — costs half, the
+//     operand tiles are half as large in shared memory, and one instruction covers 64 bit positions:
+//     4 + 1 instructions of 112 clk per 128 x 224 tile instead of 8 + 1 of 128 clk per 128 x 256 tile.
+//   * all scale factors of an operand are EQUAL, so the TMEM layout of the scale-factor matrices does not matter:
+//     two 32-column regions are filled with the bytes 0x7F (1.0) and 0x86 (128.0) once per CTA.
+//   * the fifth instruction adds the train column j (scale factors 1 on both sides): query nibbles
+//     {1, 4, 4 x4, 4 x16} times train nibbles {j & 3, (j >> 2) & 3, (j >> 4) & 3 x4, (j >> 6) & 3 x16}.
+//   * N = 224 so that two accumulators (448 columns) and the scale factors (64 columns) fit the 512 TMEM columns;
+//     2000 keypoints = 9 tiles of 224 with 0.8 % padding.
+//
+// Warp roles, barriers and the first-minimum rule are those of match_tc.cuh.
+#pragma once
+#include "match_tc.cuh"
+
+namespace yavo {
+namespace tcm4 {
+
+using namespace tcm;  // barrier / fence / descriptor / tcgen05.ld helpers
+
+constexpr int Q4 = 128;                  // queries per work item (UMMA M)
+constexpr int T4 = 224;                  // train descriptors per tile (UMMA N)
+constexpr int ROWB = 128;                // operand bytes per descriptor (two e2m1 per byte)
+constexpr int A4_BYTES = Q4 * ROWB;      // 16 KB
+constexpr int B4_BYTES = T4 * ROWB;      // 28 KB
+constexpr int AX4_BYTES = Q4 * 32;       // constant index slice, queries
+constexpr int BX4_BYTES = T4 * 32;       // constant index slice, train columns
+constexpr int RING4_BYTES = T4 * 32;     // packed bits of one train tile
+constexpr int SMEM4_BYTES = NSTAGE * (A4_BYTES + B4_BYTES) + AX4_BYTES + BX4_BYTES + NSTAGE * RING4_BYTES;
+constexpr uint32_t SF_ONE_COL = 448, SF_128_COL = 480;  // TMEM columns of the two scale-factor regions
+
+// Block-scaled instruction descriptor (kind::mxf4): A = B = E2M1 (1) at bits 7 / 10, both K-major, N >> 3 at bit 17,
+// scale format UE8M0 (1) at bit 23, M >> 4 at bit 24, K = 64 (bit 31 = 0), scale-factor ids 0.
+constexpr uint32_t IDESC4 = (1u << 7) | (1u << 10) | ((uint32_t)(T4 >> 3) << 17) | (1u << 23) | ((uint32_t)(Q4 >> 4) << 24);
+
+__device__ __forceinline__ void mma_f4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t sfa, uint32_t sfb,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.scale_vec::2X [%0], %1, %2, %3, [%5], [%6], p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(IDESC4), "r"(accumulate), "r"(sfa), "r"(sfb)
+        : "memory");
+}
+
+// 32 TMEM columns of this warp's lane quarter <- one 32-bit value
+__device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t v) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1};" ::"r"(taddr),
+        "r"(v)
+        : "memory");
+}
+
+// One descriptor (8 words = 256 bits) -> 128 operand bytes = chunks 0..7 of row r of a tile with R rows;
+// word i becomes chunk i: nibble q of output word s holds bit 4q + s of the word.
+template <bool TRAIN>
+__device__ __forceinline__ void expand_row4(uint32_t tile, int R, int r, const uint4 &lo, const uint4 &hi) {
+    const uint32_t msk = 0x88888888u, cst = TRAIN ? 0xAAAAAAAAu : 0x22222222u;
+    uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t p = tile + (uint32_t)(r * 16);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t o[4];
+#pragma unroll
+        for (int s = 0; s < 4; s++) o[s] = TRAIN ? and_xor(w[i] << (3 - s), msk, cst) : and_or(w[i] << (3 - s), msk, cst);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        p += R * 16;
+    }
+}
+
+// e2m1 nibble of an integer 0..4
+__device__ __forceinline__ uint32_t e2m1_small_int(uint32_t n) { return n == 0 ? 0u : n == 1 ? 2u : n == 2 ? 4u : n == 3 ? 5u : 6u; }
+
+// the 22 nibbles of the index slice: weights (queries) or digits of j (train column)
+__device__ __forceinline__ uint4 index_slice(bool query, uint32_t j) {
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int e = 0; e < 22; e++) {
+        const uint32_t digit = e == 0 ? (j & 3) : e == 1 ? ((j >> 2) & 3) : e < 6 ? ((j >> 4) & 3) : ((j >> 6) & 3);
+        const uint32_t v = query ? (e == 0 ? 1u : 4u) : digit;
+        w[e >> 3] |= e2m1_small_int(v) << (4 * (e & 7));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool FULL>
+__device__ __forceinline__ void min_keys4(const uint32_t (&v)[32], float (&m)[4], int col0, int nvalid) {
+    if (FULL) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) m[c] = fminf(m[c], fminf(__uint_as_float(v[i + 2 * c]), __uint_as_float(v[i + 2 * c + 1])));
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+            if (col0 + i < nvalid) m[i & 3] = fminf(m[i & 3], __uint_as_float(v[i]));
+    }
+}
+
+// Arguments as match_tc_kernel.  dbg_acc (test tool only): the 128 x 224 accumulator values (key - 32768) of the
+// first tile of work item 0.
+template <bool DBG>
+__global__ void __launch_bounds__(THREADS, 1)
+match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
+                 const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
+                 size_t set_stride_words, int q_set_offset, int t_set_offset, int pairs, int q_tiles, int out_stride,
+                 int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_acc) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bars[8 * NSTAGE];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int2 comb[2][Q4];
+    uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *b_full = bars + 2 * NSTAGE, *b_empty = bars + 3 * NSTAGE;
+    uint64_t *acc_full = bars + 4 * NSTAGE, *acc_empty = bars + 5 * NSTAGE;
+    uint64_t *r_full = bars + 6 * NSTAGE, *r_empty = bars + 7 * NSTAGE;
+    uint8_t *sA = smem_raw, *sB = sA + NSTAGE * A4_BYTES, *sAX = sB + NSTAGE * B4_BYTES, *sBX = sAX + AX4_BYTES;
+    uint8_t *sRing = sBX + BX4_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTAGE; s++) {
+            bar_init(&a_full[s], EXP_WARPS / 2);
+            bar_init(&a_empty[s], 1);
+            bar_init(&b_full[s], EXP_WARPS / 2);
+            bar_init(&b_empty[s], 1);
+            bar_init(&acc_full[s], 1);
+            bar_init(&acc_empty[s], EPI_WARPS / 2);
+            bar_init(&r_full[s], 1);
+            bar_init(&r_empty[s], EXP_WARPS / 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // constant index slice: chunk 0 = 22 nibbles, chunk 1 = 0
+    for (int i = threadIdx.x; i < Q4 + T4; i += THREADS) {
+        const bool q = i < Q4;
+        const int r = q ? i : i - Q4;
+        uint8_t *p = q ? sAX + r * 16 : sBX + r * 16;
+        *reinterpret_cast<uint4 *>(p) = index_slice(q, (uint32_t)r);
+        *reinterpret_cast<uint4 *>(p + (q ? Q4 : T4) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_async_smem();
+    if (warp == MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    if (warp < 4) {  // scale factors: every byte of a region is the same UE8M0 value
+        const uint32_t lanes = (uint32_t)(warp * 32) << 16;
+        tmem_fill32(tmem_base + lanes + SF_ONE_COL, 0x7f7f7f7fu);  // 2^0
+        tmem_fill32(tmem_base + lanes + SF_128_COL, 0x86868686u);  // 2^7
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+
+    const int items = pairs * q_tiles;
+    uint32_t e_cnt = 0, a_cnt = 0, t_cnt = 0;
+
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int pair = item / q_tiles, q0 = (item - pair * q_tiles) * Q4;
+        const int nq = nq_all ? nq_all[pair + q_set_offset] : nq_fixed;
+        const int nt = nt_all ? nt_all[pair + t_set_offset] : nt_fixed;
+        if (q0 >= nq) continue;
+        const int n_tiles = (nt + T4 - 1) / T4;
+        const uint32_t *dq = dq_all + (size_t)(pair + q_set_offset) * set_stride_words;
+        const uint32_t *dt = dt_all + (size_t)(pair + t_set_offset) * set_stride_words;
+
+        if (warp < EPI_WARPS) {
+            // ------------------------------------------------ epilogue (two groups on alternate accumulators)
+            const int g = warp >> 2, row = (warp & 3) * 32 + lane;
+            int best_d = 0x7fffffff, best_j = -1;
+            for (int t = ((t_cnt & 1) == (uint32_t)g) ? 0 : 1; t < n_tiles; t += 2) {
+                const uint32_t ph = ((t_cnt + t) >> 1) & 1;
+                bar_wait(&acc_full[g], ph);
+                fence_after_sync();
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * T4;
+                const int nvalid = min(T4, nt - t * T4);
+                float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+                uint32_t v0[32], v1[32];
+                tmem_ld32(taddr, v0);
+                if (nvalid == T4) {
+#pragma unroll 1
+                    for (int c = 0; c < T4 / 64; c++) {  // 3 x 64 columns ...
+                        tmem_wait(v0);
+                        tmem_ld32(taddr + c * 64 + 32, v1);
+                        if (DBG && dbg_acc && item == 0 && t == 0)
+                            for (int i = 0; i < 32; i++) dbg_acc[row * T4 + c * 64 + i] = __uint_as_float(v0[i]);
+                        min_keys4<true>(v0, m4, 0, 0);
+                        tmem_wait(v1);
+                        tmem_ld32(taddr + c * 64 + 64, v0);
+                        if (DBG && dbg_acc && item == 0 && t == 0)
+                            for (int i = 0; i < 32; i++) dbg_acc[row * T4 + c * 64 + 32 + i] = __uint_as_float(v1[i]);
+                        min_keys4<true>(v1, m4, 0, 0);
+                    }
+                    tmem_wait(v0);  // ... + the last 32
+                    if (DBG && dbg_acc && item == 0 && t == 0)
+                        for (int i = 0; i < 32; i++) dbg_acc[row * T4 + 192 + i] = __uint_as_float(v0[i]);
+                    min_keys4<true>(v0, m4, 0, 0);
+                } else {  // last tile of a train set
+#pragma unroll 1
+                    for (int c = 0; c < T4 / 32; c++) {
+                        tmem_wait(v0);
+                        min_keys4<false>(v0, m4, c * 32, nvalid);
+                        if (c + 1 < T4 / 32) tmem_ld32(taddr + c * 32 + 32, v0);
+                    }
+                }
+                const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+                fence_before_sync();
+                __syncwarp();
+                if (lane == 0) bar_arrive(&acc_empty[g]);
+                const int ki = (int)m + 32768;  // 256 * distance + column, exact
+                if ((ki >> 8) < best_d) {
+                    best_d = ki >> 8;
+                    best_j = t * T4 + (ki & 255);
+                }
+            }
+            t_cnt += n_tiles;
+            int2 *cb = comb[e_cnt & 1];
+            e_cnt++;
+            if (g == 1) cb[row] = make_int2(best_d, best_j);
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            if (g == 0) {
+                const int2 o = cb[row];
+                if (o.x < best_d || (o.x == best_d && o.y < best_j)) {
+                    best_d = o.x;
+                    best_j = o.y;
+                }
+                const int q = q0 + row;
+                if (q < nq) {
+                    out_idx[(size_t)pair * out_stride + q] = best_j;  // empty train set: -1 / INT_MAX
+                    out_dist[(size_t)pair * out_stride + q] = best_d;
+                }
+            }
+        } else if (warp == MMA_WARP) {
+            // ------------------------------------------------ MMA issue: one thread
+            if (n_tiles > 0) {
+                if (lane == 0) {
+                    const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
+                    const uint64_t adesc0 = smem_desc(saddr(sA + as * A4_BYTES), Q4 * 16u, 128u);
+                    const uint64_t adescx = smem_desc(saddr(sAX), Q4 * 16u, 128u), bdescx = smem_desc(saddr(sBX), T4 * 16u, 128u);
+                    const uint32_t sf1 = tmem_base + SF_ONE_COL, sf128 = tmem_base + SF_128_COL;
+                    bar_wait(&a_full[as], aph);
+                    for (int t = 0; t < n_tiles; t++, t_cnt++) {
+                        const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                        bar_wait(&b_full[s], ph);
+                        bar_wait(&acc_empty[s], ph ^ 1);
+                        fence_after_sync();
+                        const uint64_t bdesc0 = smem_desc(saddr(sB + s * B4_BYTES), T4 * 16u, 128u);
+                        const uint32_t tacc = tmem_base + s * T4;
+#pragma unroll
+                        for (int k = 0; k < ROWB / 32; k++)  // K = 64 nibbles = 32 operand bytes (two chunks) per instruction
+                            mma_f4(tacc, adesc0 + (uint64_t)((k * 2 * Q4 * 16) >> 4), bdesc0 + (uint64_t)((k * 2 * T4 * 16) >> 4), sf1,
+                                   sf128, k > 0);
+                        mma_f4(tacc, adescx, bdescx, sf1, sf1, 1);  // + column index
+                        mma_commit(&b_empty[s]);
+                        mma_commit(&acc_full[s]);
+                    }
+                    mma_commit(&a_empty[as]);
+                } else {
+                    t_cnt += n_tiles;
+                }
+                a_cnt++;
+                __syncwarp();
+            }
+        } else if (warp == LOAD_WARP) {
+            // ------------------------------------------------ loader: packed bits of the train tiles -> ring
+            if (n_tiles > 0 && lane == 0) {
+                for (int t = 0; t < n_tiles; t++, t_cnt++) {
+                    const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                    const uint32_t bytes = 32u * (uint32_t)min(T4, nt - t * T4);
+                    bar_wait(&r_empty[s], ph ^ 1);
+                    bar_expect_tx(&r_full[s], bytes);
+                    bulk_load(sRing + s * RING4_BYTES, dt + (size_t)t * T4 * 8, bytes, &r_full[s]);
+                }
+            } else {
+                t_cnt += n_tiles;
+            }
+        } else {
+            // ------------------------------------------------ expanders (two groups on alternate operand stages)
+            if (n_tiles > 0) {
+                const int ew = warp - (EPI_WARPS + 1), ge = ew >> 2, k = ew & 3;
+                const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
+                const uint4 zero = make_uint4(0, 0, 0, 0);
+                if (ge == (int)as) {  // query tile: rows k*32 .. +31
+                    const int r = k * 32 + lane;
+                    const bool in = q0 + r < nq;
+                    const uint4 w0 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8)) : zero;
+                    const uint4 w1 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8) + 1) : zero;
+                    bar_wait(&a_empty[as], aph ^ 1);
+                    expand_row4<false>(saddr(sA + as * A4_BYTES), Q4, r, w0, w1);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) bar_arrive(&a_full[as]);
+                }
+                for (int t = 0; t < n_tiles; t++, t_cnt++) {
+                    const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                    if (ge != (int)s) continue;
+                    const int r = k * 64 + lane;  // train tile: rows k*64 .. +63 (k = 3: 192 .. 223 only)
+                    bar_wait(&r_full[s], ph);
+                    const bool in0 = t * T4 + r < nt, in1 = r + 32 < T4 && t * T4 + r + 32 < nt;
+                    const uint8_t *src = sRing + s * RING4_BYTES + r * 32;
+                    const uint4 c0 = in0 ? *reinterpret_cast<const uint4 *>(src) : zero;
+                    const uint4 c1 = in0 ? *reinterpret_cast<const uint4 *>(src + 16) : zero;
+                    const uint4 c2 = in1 ? *reinterpret_cast<const uint4 *>(src + 1024) : zero;
+                    const uint4 c3 = in1 ? *reinterpret_cast<const uint4 *>(src + 1040) : zero;
+                    bar_wait(&b_empty[s], ph ^ 1);
+                    const uint32_t tile = saddr(sB + s * B4_BYTES);
+                    expand_row4<true>(tile, T4, r, c0, c1);
+                    if (r + 32 < T4) expand_row4<true>(tile, T4, r + 32, c2, c3);
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        bar_arrive(&r_empty[s]);  // only now: the ring reads above have certainly completed (their values were used)
+                        bar_arrive(&b_full[s]);
+                    }
+                }
+                a_cnt++;
+            }
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) {
+        fence_after_sync();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace tcm4
+}  // namespace yavo

@@ -14,7 +14,7 @@
 #include "../../include/yavo_b200.h"
 #include "yavo_kernels.cuh"
 #include "klt_kernels.cuh"
-#include "match_tc.cuh"
+#include "match_tc4.cuh"
 
 using namespace yavo;
 
@@ -81,7 +81,7 @@ struct yavo_ctx {
     unsigned long long n_tickets = 0;
     char raw_used[2] = {0, 0};
     int pipeline_chunk = 0;  // frames per copy/compute stage of the host-batch path (0 = automatic)
-    int matcher = 0;    // 0 = tensor-core matcher (K5t), 1 = POPC matcher (K5)
+    int matcher = 0;    // 0 = tensor-core matcher on packed 4-bit operands (K5t4), 1 = POPC matcher (K5), 2 = tensor-core matcher on FP8 operands (K5t)
     int n_sms = 148;
     int sub_batch = 0;  // frames per kernel sub-batch of yavo_frontend_batch (0 = the whole batch in one set of launches)
     // tracking step (klt_kernels.cuh): pyramid levels 1..KLT_MAX_LEVELS per slot, allocated on first use
@@ -572,6 +572,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)select_smem_bytes()));
     CKC(cudaFuncSetAttribute(tcm::match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm::SMEM_BYTES));
+    CKC(cudaFuncSetAttribute(tcm4::match_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm4::SMEM4_BYTES));
     CKC(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device));
 #undef CKC
     *out = c;
@@ -848,9 +849,14 @@ static int launch_match_tc(yavo_ctx *ctx, const uint32_t *dq_all, const int *nq_
     const long long items = (long long)pairs * q_tiles;
     if (items <= 0) return 0;
     const int grid = (int)std::min<long long>(items, ctx->n_sms);
-    PROF(KC_MATCH_TC, tcm::match_tc_kernel<false><<<grid, tcm::THREADS, tcm::SMEM_BYTES, ctx->stream>>>(
-                          dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
-                          out_stride, o_idx, o_dist, nullptr));
+    if (ctx->matcher == 2)
+        PROF(KC_MATCH_TC, tcm::match_tc_kernel<false><<<grid, tcm::THREADS, tcm::SMEM_BYTES, ctx->stream>>>(
+                              dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
+                              out_stride, o_idx, o_dist, nullptr));
+    else
+        PROF(KC_MATCH_TC, tcm4::match_tc4_kernel<false><<<grid, tcm::THREADS, tcm4::SMEM4_BYTES, ctx->stream>>>(
+                              dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
+                              out_stride, o_idx, o_dist, nullptr));
     CK_LAUNCH();
     return 0;
 }
@@ -859,7 +865,7 @@ static int match_device(yavo_ctx *ctx, const uint32_t *dq, int n1, const uint32_
                         int32_t *o_dist, int32_t *o_sec) {
     // tensor-core matcher unless the caller wants the second-best distance (ratio-test extension), which only
     // the POPC kernel tracks
-    if (!o_sec && ctx->matcher == 0) return launch_match_tc(ctx, dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, 1, n1, n1, o_idx, o_dist);
+    if (!o_sec && ctx->matcher != 1) return launch_match_tc(ctx, dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, 1, n1, n1, o_idx, o_dist);
     const int chunks = choose_chunks(n1, n2, 1);
     const int chunk = std::max(1, (std::max(n2, 1) + chunks - 1) / chunks);
     if (int r = ensure_partials(ctx, (size_t)n1 * chunks)) return r;
@@ -963,7 +969,7 @@ static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool l
     }
     const int m0 = (link_prev && slot0 > 0) ? slot0 - 1 : slot0;  // first query slot
     const int pairs = slot0 + n - 1 - m0;
-    if (do_match && pairs > 0 && ctx->matcher == 0) {
+    if (do_match && pairs > 0 && ctx->matcher != 1) {
         // pair p: queries = slot m0+p, train = slot m0+p+1; results stored at the train slot
         const size_t mo = (size_t)m0 * ctx->max_kp;
         if (int r = launch_match_tc(ctx, ctx->d_desc + mo * 8, ctx->d_nbk + m0, 0, ctx->d_desc + mo * 8, ctx->d_nbk + m0, 0,
@@ -1214,7 +1220,7 @@ extern "C" int yavo_debug_select_timing(yavo_ctx *ctx, long long *out /* 64 x 8 
 #endif
 
 int yavo_set_matcher(yavo_ctx *ctx, int kind) {
-    if (!ctx || kind < 0 || kind > 1) return YAVO_ERR_INVALID;
+    if (!ctx || kind < 0 || kind > 2) return YAVO_ERR_INVALID;
     ctx->matcher = kind;
     return 0;
 }
