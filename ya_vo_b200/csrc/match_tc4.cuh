@@ -8,13 +8,14 @@
 //     Eight nibbles come out of ONE LOP3 ((w << k) & 0x88888888, | or ^ a constant) instead of four bytes, so the
 //     expansion — which the integer ALU pipe (64 lanes / clk / SM) bounds in the FP8 version — costs half, the
 //     operand tiles are half as large in shared memory, and one instruction covers 64 bit positions:
-//     4 + 1 instructions of 112 clk per 128 x 224 tile instead of 8 + 1 of 128 clk per 128 x 256 tile.
+//     4 + 1 instructions of 56 clk per 128 x 112 tile instead of 8 + 1 of 128 clk per 128 x 256 tile.
 //   * all scale factors of an operand are EQUAL, so the TMEM layout of the scale-factor matrices does not matter:
 //     two 32-column regions are filled with the bytes 0x7F (1.0) and 0x86 (128.0) once per CTA.
 //   * the fifth instruction adds the train column j (scale factors 1 on both sides): query nibbles
 //     {1, 4, 4 x4, 4 x16} times train nibbles {j & 3, (j >> 2) & 3, (j >> 4) & 3 x4, (j >> 6) & 3 x16}.
-//   * N = 224 so that two accumulators (448 columns) and the scale factors (64 columns) fit the 512 TMEM columns;
-//     2000 keypoints = 9 tiles of 224 with 0.8 % padding.
+//   * N = 112: four accumulators (448 columns) and the scale factors (64 columns) fit the 512 TMEM columns, and four
+//     tiles in flight hide the ~400-clk mbarrier hand-offs between the MMA thread and the epilogue warps;
+//     2000 keypoints = 18 tiles of 112 with 0.8 % padding.
 //
 // Warp roles, barriers and the first-minimum rule are those of match_tc.cuh.
 #pragma once
@@ -26,19 +27,41 @@ namespace tcm4 {
 using namespace tcm;  // barrier / fence / descriptor / tcgen05.ld helpers
 
 constexpr int Q4 = 128;                  // queries per work item (UMMA M)
-constexpr int T4 = 224;                  // train descriptors per tile (UMMA N)
+#ifndef YAVO_TC4_N
+#define YAVO_TC4_N 224
+#endif
+constexpr int T4 = YAVO_TC4_N;           // train descriptors per tile (UMMA N): 224 (two accumulators) or 112 (four)
+constexpr int NACC = 448 / T4;           // accumulators in TMEM (448 columns; the scale factors take the other 64)
+constexpr int RPW = T4 > 128 ? 64 : 32;  // train rows per expander warp
 constexpr int ROWB = 128;                // operand bytes per descriptor (two e2m1 per byte)
 constexpr int A4_BYTES = Q4 * ROWB;      // 16 KB
-constexpr int B4_BYTES = T4 * ROWB;      // 28 KB
+constexpr int B4_BYTES = T4 * ROWB;      // 28 KB / 14 KB
 constexpr int AX4_BYTES = Q4 * 32;       // constant index slice, queries
 constexpr int BX4_BYTES = T4 * 32;       // constant index slice, train columns
 constexpr int RING4_BYTES = T4 * 32;     // packed bits of one train tile
-constexpr int SMEM4_BYTES = NSTAGE * (A4_BYTES + B4_BYTES) + AX4_BYTES + BX4_BYTES + NSTAGE * RING4_BYTES;
+constexpr int NB4 = 4;                   // train-tile operand stages and packed-bit ring entries (even: stage parity = expander group)
+#ifndef YAVO_TC4_NR
+#define YAVO_TC4_NR 4
+#endif
+constexpr int NR4 = YAVO_TC4_NR;         // packed-bit ring entries (even): a bulk copy takes ~1600 clk to complete, several must be in flight
+constexpr int SMEM4_BYTES = NSTAGE * A4_BYTES + NB4 * B4_BYTES + AX4_BYTES + BX4_BYTES + NR4 * RING4_BYTES;
 constexpr uint32_t SF_ONE_COL = 448, SF_128_COL = 480;  // TMEM columns of the two scale-factor regions
 
 // Block-scaled instruction descriptor (kind::mxf4): A = B = E2M1 (1) at bits 7 / 10, both K-major, N >> 3 at bit 17,
 // scale format UE8M0 (1) at bit 23, M >> 4 at bit 24, K = 64 (bit 31 = 0), scale-factor ids 0.
 constexpr uint32_t IDESC4 = (1u << 7) | (1u << 10) | ((uint32_t)(T4 >> 3) << 17) | (1u << 23) | ((uint32_t)(Q4 >> 4) << 24);
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(p));
+    return p != 0;
+}
 
 __device__ __forceinline__ void mma_f4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t sfa, uint32_t sfb,
                                        uint32_t accumulate) {
@@ -60,6 +83,26 @@ __device__ __forceinline__ void tmem_fill32(uint32_t taddr, uint32_t v) {
         "%1, %1, %1};" ::"r"(taddr),
         "r"(v)
         : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// one tcgen05.wait::ld for two loads in flight; every destination register is tied to it
+__device__ __forceinline__ void tmem_wait2(uint32_t (&a)[32], uint32_t (&b)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : YAVO_TM32_RW(a)::"memory");
+    asm volatile("" : YAVO_TM32_RW(b)::"memory");
+}
+__device__ __forceinline__ void tmem_wait2b(uint32_t (&a)[32], uint32_t (&d)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" : YAVO_TM32_RW(a)::"memory");
+    asm volatile(""
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]), "+r"(d[8]), "+r"(d[9]),
+                   "+r"(d[10]), "+r"(d[11]), "+r"(d[12]), "+r"(d[13]), "+r"(d[14]), "+r"(d[15])::"memory");
 }
 
 // One descriptor (8 words = 256 bits) -> 128 operand bytes = chunks 0..7 of row r of a tile with R rows;
@@ -118,24 +161,31 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                  size_t set_stride_words, int q_set_offset, int t_set_offset, int pairs, int q_tiles, int out_stride,
                  int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_acc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ uint64_t bars[8 * NSTAGE];
+    __shared__ uint64_t bars[2 * NSTAGE + 2 * NACC + 2 * NB4 + 2 * NR4];
     __shared__ uint32_t tmem_base_s;
     __shared__ int2 comb[2][Q4];
-    uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *b_full = bars + 2 * NSTAGE, *b_empty = bars + 3 * NSTAGE;
-    uint64_t *acc_full = bars + 4 * NSTAGE, *acc_empty = bars + 5 * NSTAGE;
-    uint64_t *r_full = bars + 6 * NSTAGE, *r_empty = bars + 7 * NSTAGE;
-    uint8_t *sA = smem_raw, *sB = sA + NSTAGE * A4_BYTES, *sAX = sB + NSTAGE * B4_BYTES, *sBX = sAX + AX4_BYTES;
+    uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *acc_full = bars + 2 * NSTAGE, *acc_empty = acc_full + NACC;
+    uint64_t *b_full = acc_empty + NACC, *b_empty = b_full + NB4, *r_full = b_empty + NB4, *r_empty = r_full + NR4;
+    uint8_t *sA = smem_raw, *sB = sA + NSTAGE * A4_BYTES, *sAX = sB + NB4 * B4_BYTES, *sBX = sAX + AX4_BYTES;
     uint8_t *sRing = sBX + BX4_BYTES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: provably warp-uniform, so the role branches and everything the MMA warp computes
+    // stay in uniform registers (with a lane-0 branch around them every tcgen05.mma costs an ELECT / R2UR.BROADCAST loop)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) {
             bar_init(&a_full[s], EXP_WARPS / 2);
             bar_init(&a_empty[s], 1);
-            bar_init(&b_full[s], EXP_WARPS / 2);
-            bar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < NACC; s++) {
             bar_init(&acc_full[s], 1);
             bar_init(&acc_empty[s], EPI_WARPS / 2);
+        }
+        for (int s = 0; s < NB4; s++) {
+            bar_init(&b_full[s], EXP_WARPS / 2);
+            bar_init(&b_empty[s], 1);
+        }
+        for (int s = 0; s < NR4; s++) {
             bar_init(&r_full[s], 1);
             bar_init(&r_empty[s], EXP_WARPS / 2);
         }
@@ -157,7 +207,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
-    const uint32_t tmem_base = tmem_base_s;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_s, 0);
     if (warp < 4) {  // scale factors: every byte of a region is the same UE8M0 value
         const uint32_t lanes = (uint32_t)(warp * 32) << 16;
         tmem_fill32(tmem_base + lanes + SF_ONE_COL, 0x7f7f7f7fu);  // 2^0
@@ -185,44 +235,53 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
             const int g = warp >> 2, row = (warp & 3) * 32 + lane;
             int best_d = 0x7fffffff, best_j = -1;
             for (int t = ((t_cnt & 1) == (uint32_t)g) ? 0 : 1; t < n_tiles; t += 2) {
-                const uint32_t ph = ((t_cnt + t) >> 1) & 1;
-                bar_wait(&acc_full[g], ph);
+                const uint32_t acc = (t_cnt + t) % NACC, ph = ((t_cnt + t) / NACC) & 1;
+                bar_wait(&acc_full[acc], ph);
                 fence_after_sync();
-                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * T4;
+                const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * T4;
                 const int nvalid = min(T4, nt - t * T4);
                 float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
-                uint32_t v0[32], v1[32];
-                tmem_ld32(taddr, v0);
-                if (nvalid == T4) {
+                uint32_t v0[32], v1[32], v2[32], v3[16];
+                const bool full = nvalid == T4;
+                // 112 columns at a time = 32 + 32 | 32 + 16: the second pair is loaded while the first is reduced
 #pragma unroll 1
-                    for (int c = 0; c < T4 / 64; c++) {  // 3 x 64 columns ...
-                        tmem_wait(v0);
-                        tmem_ld32(taddr + c * 64 + 32, v1);
-                        if (DBG && dbg_acc && item == 0 && t == 0)
-                            for (int i = 0; i < 32; i++) dbg_acc[row * T4 + c * 64 + i] = __uint_as_float(v0[i]);
-                        min_keys4<true>(v0, m4, 0, 0);
-                        tmem_wait(v1);
-                        tmem_ld32(taddr + c * 64 + 64, v0);
-                        if (DBG && dbg_acc && item == 0 && t == 0)
-                            for (int i = 0; i < 32; i++) dbg_acc[row * T4 + c * 64 + 32 + i] = __uint_as_float(v1[i]);
-                        min_keys4<true>(v1, m4, 0, 0);
+                for (int h = 0; h < T4 / 112; h++) {
+                    const uint32_t ta = taddr + h * 112;
+                    const int c0 = h * 112;
+                    tmem_ld32(ta, v0);
+                    tmem_ld32(ta + 32, v1);
+                    tmem_wait2(v0, v1);
+#ifndef YAVO_TC_EXP_NO_EPI
+                    if (full) min_keys4<true>(v0, m4, 0, 0); else min_keys4<false>(v0, m4, c0, nvalid);
+                    tmem_ld32(ta + 64, v2);
+                    if (full) min_keys4<true>(v1, m4, 0, 0); else min_keys4<false>(v1, m4, c0 + 32, nvalid);
+                    tmem_ld16(ta + 96, v3);
+                    tmem_wait2b(v2, v3);
+                    if (full) {
+                        min_keys4<true>(v2, m4, 0, 0);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) m4[(i >> 1) & 3] = fminf(m4[(i >> 1) & 3], fminf(__uint_as_float(v3[i]), __uint_as_float(v3[i + 1])));
+                    } else {  // last tile of a train set
+                        min_keys4<false>(v2, m4, c0 + 64, nvalid);
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if (c0 + 96 + i < nvalid) m4[i & 3] = fminf(m4[i & 3], __uint_as_float(v3[i]));
                     }
-                    tmem_wait(v0);  // ... + the last 32
-                    if (DBG && dbg_acc && item == 0 && t == 0)
-                        for (int i = 0; i < 32; i++) dbg_acc[row * T4 + 192 + i] = __uint_as_float(v0[i]);
-                    min_keys4<true>(v0, m4, 0, 0);
-                } else {  // last tile of a train set
-#pragma unroll 1
-                    for (int c = 0; c < T4 / 32; c++) {
-                        tmem_wait(v0);
-                        min_keys4<false>(v0, m4, c * 32, nvalid);
-                        if (c + 1 < T4 / 32) tmem_ld32(taddr + c * 32 + 32, v0);
+#endif
+                }
+#ifndef YAVO_TC_EXP_NO_EPI
+                if (DBG && dbg_acc && item == 0 && t == 0) {  // (test tool) re-read the tile
+                    for (int c = 0; c < T4 / 16; c++) {
+                        tmem_ld16(taddr + 16 * c, v3);
+                        tmem_wait2b(v2, v3);
+                        for (int i = 0; i < 16; i++) dbg_acc[row * T4 + 16 * c + i] = __uint_as_float(v3[i]);
                     }
                 }
+#endif
                 const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) bar_arrive(&acc_empty[g]);
+                if (lane == 0) bar_arrive(&acc_empty[acc]);
                 const int ki = (int)m + 32768;  // 256 * distance + column, exact
                 if ((ki >> 8) < best_d) {
                     best_d = ki >> 8;
@@ -247,41 +306,43 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 }
             }
         } else if (warp == MMA_WARP) {
-            // ------------------------------------------------ MMA issue: one thread
+            // ------------------------------------------------ MMA issue: the whole warp runs the loop (uniform
+            // control flow and operands), one elected lane issues tcgen05.mma / tcgen05.commit
             if (n_tiles > 0) {
-                if (lane == 0) {
-                    const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
-                    const uint64_t adesc0 = smem_desc(saddr(sA + as * A4_BYTES), Q4 * 16u, 128u);
-                    const uint64_t adescx = smem_desc(saddr(sAX), Q4 * 16u, 128u), bdescx = smem_desc(saddr(sBX), T4 * 16u, 128u);
-                    const uint32_t sf1 = tmem_base + SF_ONE_COL, sf128 = tmem_base + SF_128_COL;
-                    bar_wait(&a_full[as], aph);
-                    for (int t = 0; t < n_tiles; t++, t_cnt++) {
-                        const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
-                        bar_wait(&b_full[s], ph);
-                        bar_wait(&acc_empty[s], ph ^ 1);
-                        fence_after_sync();
-                        const uint64_t bdesc0 = smem_desc(saddr(sB + s * B4_BYTES), T4 * 16u, 128u);
-                        const uint32_t tacc = tmem_base + s * T4;
+                const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
+                const uint64_t adesc0 = smem_desc(saddr(sA + as * A4_BYTES), Q4 * 16u, 128u);
+                const uint64_t adescx = smem_desc(saddr(sAX), Q4 * 16u, 128u), bdescx = smem_desc(saddr(sBX), T4 * 16u, 128u);
+                const uint32_t sf1 = tmem_base + SF_ONE_COL, sf128 = tmem_base + SF_128_COL;
+                bar_wait(&a_full[as], aph);
+                for (int t = 0; t < n_tiles; t++, t_cnt++) {
+                    const uint32_t s = t_cnt % NACC, ph = (t_cnt / NACC) & 1;    // accumulator
+                    const uint32_t bs = t_cnt % NB4, bph = (t_cnt / NB4) & 1;    // operand stage
+                    bar_wait(&b_full[bs], bph);
+                    bar_wait(&acc_empty[s], ph ^ 1);
+                    fence_after_sync();
+                    const uint64_t bdesc0 = smem_desc(saddr(sB + bs * B4_BYTES), T4 * 16u, 128u);
+                    const uint32_t tacc = tmem_base + s * T4;
+                    if (elect_one()) {
+#ifndef YAVO_TC_EXP_NO_MMA
 #pragma unroll
                         for (int k = 0; k < ROWB / 32; k++)  // K = 64 nibbles = 32 operand bytes (two chunks) per instruction
                             mma_f4(tacc, adesc0 + (uint64_t)((k * 2 * Q4 * 16) >> 4), bdesc0 + (uint64_t)((k * 2 * T4 * 16) >> 4), sf1,
                                    sf128, k > 0);
                         mma_f4(tacc, adescx, bdescx, sf1, sf1, 1);  // + column index
-                        mma_commit(&b_empty[s]);
+#endif
+                        mma_commit(&b_empty[bs]);
                         mma_commit(&acc_full[s]);
+                        if (t == n_tiles - 1) mma_commit(&a_empty[as]);
                     }
-                    mma_commit(&a_empty[as]);
-                } else {
-                    t_cnt += n_tiles;
+                    __syncwarp();
                 }
                 a_cnt++;
-                __syncwarp();
             }
         } else if (warp == LOAD_WARP) {
             // ------------------------------------------------ loader: packed bits of the train tiles -> ring
             if (n_tiles > 0 && lane == 0) {
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
-                    const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
+                    const uint32_t s = t_cnt % NR4, ph = (t_cnt / NR4) & 1;
                     const uint32_t bytes = 32u * (uint32_t)min(T4, nt - t * T4);
                     bar_wait(&r_empty[s], ph ^ 1);
                     bar_expect_tx(&r_full[s], bytes);
@@ -308,24 +369,26 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     if (lane == 0) bar_arrive(&a_full[as]);
                 }
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
-                    const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
-                    if (ge != (int)s) continue;
-                    const int r = k * 64 + lane;  // train tile: rows k*64 .. +63 (k = 3: 192 .. 223 only)
-                    bar_wait(&r_full[s], ph);
-                    const bool in0 = t * T4 + r < nt, in1 = r + 32 < T4 && t * T4 + r + 32 < nt;
-                    const uint8_t *src = sRing + s * RING4_BYTES + r * 32;
+                    if (ge != (int)(t_cnt & 1)) continue;
+                    const uint32_t s = t_cnt % NB4, ph = (t_cnt / NB4) & 1;    // operand stage
+                    const uint32_t rs = t_cnt % NR4, rph = (t_cnt / NR4) & 1;  // ring entry
+                    const int r = k * RPW + lane;  // train tile: rows k*RPW .. +RPW-1, as far as the tile goes
+                    bar_wait(&r_full[rs], rph);
+                    const bool in0 = r < T4 && t * T4 + r < nt, in1 = RPW > 32 && r + 32 < T4 && t * T4 + r + 32 < nt;
+                    const uint8_t *src = sRing + rs * RING4_BYTES + r * 32;
                     const uint4 c0 = in0 ? *reinterpret_cast<const uint4 *>(src) : zero;
                     const uint4 c1 = in0 ? *reinterpret_cast<const uint4 *>(src + 16) : zero;
                     const uint4 c2 = in1 ? *reinterpret_cast<const uint4 *>(src + 1024) : zero;
                     const uint4 c3 = in1 ? *reinterpret_cast<const uint4 *>(src + 1040) : zero;
                     bar_wait(&b_empty[s], ph ^ 1);
-                    const uint32_t tile = saddr(sB + s * B4_BYTES);
-                    expand_row4<true>(tile, T4, r, c0, c1);
-                    if (r + 32 < T4) expand_row4<true>(tile, T4, r + 32, c2, c3);
+#ifndef YAVO_TC_EXP_NO_EXP
+                    if (r < T4) expand_row4<true>(saddr(sB + s * B4_BYTES), T4, r, c0, c1);
+                    if (RPW > 32 && r + 32 < T4) expand_row4<true>(saddr(sB + s * B4_BYTES), T4, r + 32, c2, c3);
                     fence_async_smem();
+#endif
                     __syncwarp();
                     if (lane == 0) {
-                        bar_arrive(&r_empty[s]);  // only now: the ring reads above have certainly completed (their values were used)
+                        bar_arrive(&r_empty[rs]);  // only now: the ring reads above have certainly completed (their values were used)
                         bar_arrive(&b_full[s]);
                     }
                 }
