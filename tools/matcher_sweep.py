@@ -11,8 +11,10 @@ from ya_vo_b200 import capi, synth  # noqa: E402
 
 def main():
     sizes = [1024, 2048, 4096, 8192, 16384, 32768, 65536]
-    out = {"unit": "Gpairs/s", "note": "match_partial + match_reduce device time, descriptors already on the device side of "
-           "yavo_match's H2D; second-best tracking on (SECOND variant) when ext=1", "rows": []}
+    out = {"unit": "Gpairs/s", "note": "device time of the match kernels (match_tc, or match_partial + match_reduce), descriptors "
+           "already on the device side of yavo_match's H2D; matcher = tc (tcgen05 kind::mxf4, default), tc8 (kind::f8f6f4) or "
+           "popc (integer pipes); ext=1: second-best distance (always the popc kernel) + cross-check (the selected matcher)",
+           "rows": []}
     with capi.Context(device=0, n_slots=1, max_rows=64, max_cols=128, max_kp=16) as ctx:
         for n1 in sizes:
             for n2 in sizes:
@@ -20,7 +22,8 @@ def main():
                     continue
                 d1 = synth.synth_descriptors(n1, n1 * 131 + n2)
                 d2 = synth.synth_descriptors(n2, n1 * 131 + n2 + 1)
-                for ext in (0, 1):
+                for matcher, ext in (("tc", 0), ("tc8", 0), ("popc", 0), ("tc", 1)):
+                    ctx.set_matcher(matcher)
                     ctx.match(d1, d2, extensions=False)  # warm
                     ctx.set_profiling(True)
                     reps = 3 if n1 * n2 < (1 << 30) else 1
@@ -31,9 +34,9 @@ def main():
                             idx, dist = ctx.match(d1, d2)
                     prof = ctx.profile_collect()
                     ctx.set_profiling(False)
-                    ms = (prof["match_partial"][0] + prof["match_reduce"][0]) / reps
+                    ms = (prof["match_tc"][0] + prof["match_partial"][0] + prof["match_reduce"][0]) / reps
                     pairs = n1 * n2 * (2 if ext else 1)  # the cross-check runs the kernel a second time, roles swapped
-                    out["rows"].append({"n1": n1, "n2": n2, "ext": ext, "ms": ms, "gpairs": pairs / ms / 1e6})
+                    out["rows"].append({"n1": n1, "n2": n2, "matcher": matcher, "ext": ext, "ms": ms, "gpairs": pairs / ms / 1e6})
     print(json.dumps(out))
 
 
