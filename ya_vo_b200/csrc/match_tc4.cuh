@@ -33,6 +33,12 @@ constexpr int Q4 = 128;                  // queries per work item (UMMA M)
 constexpr int T4 = YAVO_TC4_N;           // train descriptors per tile (UMMA N): 224 (two accumulators) or 112 (four)
 constexpr int NACC = 448 / T4;           // accumulators in TMEM (448 columns; the scale factors take the other 64)
 constexpr int RPW = T4 > 128 ? 64 : 32;  // train rows per expander warp
+#ifndef YAVO_TC4_EPI_SPLIT
+#define YAVO_TC4_EPI_SPLIT 1
+#endif
+// epilogue split: true = both warps of a TMEM lane quarter drain EVERY tile, 112 columns each (two tcgen05.ld round trips per
+// tile and warp); false = warps 0-3 / 4-7 take alternate tiles whole (four round trips)
+constexpr bool EPI_SPLIT = YAVO_TC4_EPI_SPLIT && T4 == 224;
 constexpr int ROWB = 128;                // operand bytes per descriptor (two e2m1 per byte)
 constexpr int A4_BYTES = Q4 * ROWB;      // 16 KB
 constexpr int B4_BYTES = T4 * ROWB;      // 28 KB / 14 KB
@@ -179,7 +185,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
         }
         for (int s = 0; s < NACC; s++) {
             bar_init(&acc_full[s], 1);
-            bar_init(&acc_empty[s], EPI_WARPS / 2);
+            bar_init(&acc_empty[s], EPI_SPLIT ? EPI_WARPS : EPI_WARPS / 2);
         }
         for (int s = 0; s < NB4; s++) {
             bar_init(&b_full[s], EXP_WARPS / 2);
@@ -234,7 +240,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
             // ------------------------------------------------ epilogue (two groups on alternate accumulators)
             const int g = warp >> 2, row = (warp & 3) * 32 + lane;
             int best_d = 0x7fffffff, best_j = -1;
-            for (int t = ((t_cnt & 1) == (uint32_t)g) ? 0 : 1; t < n_tiles; t += 2) {
+            for (int t = EPI_SPLIT ? 0 : (((t_cnt & 1) == (uint32_t)g) ? 0 : 1); t < n_tiles; t += EPI_SPLIT ? 1 : 2) {
                 const uint32_t acc = (t_cnt + t) % NACC, ph = ((t_cnt + t) / NACC) & 1;
                 bar_wait(&acc_full[acc], ph);
                 fence_after_sync();
@@ -245,7 +251,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 const bool full = nvalid == T4;
                 // 112 columns at a time = 32 + 32 | 32 + 16: the second pair is loaded while the first is reduced
 #pragma unroll 1
-                for (int h = 0; h < T4 / 112; h++) {
+                for (int h = EPI_SPLIT ? g : 0; h < (EPI_SPLIT ? g + 1 : T4 / 112); h++) {
                     const uint32_t ta = taddr + h * 112;
                     const int c0 = h * 112;
                     tmem_ld32(ta, v0);
@@ -283,7 +289,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 __syncwarp();
                 if (lane == 0) bar_arrive(&acc_empty[acc]);
                 const int ki = (int)m + 32768;  // 256 * distance + column, exact
-                if ((ki >> 8) < best_d) {
+                if (m < 1.0e30f /* this warp's columns may all lie beyond the train set */ && (ki >> 8) < best_d) {
                     best_d = ki >> 8;
                     best_j = t * T4 + (ki & 255);
                 }
