@@ -58,7 +58,25 @@ __device__ __forceinline__ void bar_init(uint64_t *bar, int count) {
 __device__ __forceinline__ void bar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(saddr(bar)) : "memory");
 }
+#ifndef YAVO_TC_WAIT_HINT_NS
+#define YAVO_TC_WAIT_HINT_NS 0
+#endif
+// mbarrier wait: try_wait suspends the thread in hardware until the phase completes or a time limit passes (with
+// YAVO_TC_WAIT_HINT_NS > 0 that limit is given explicitly, so that waiting warps poll less often)
 __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
+#if YAVO_TC_WAIT_HINT_NS > 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(saddr(bar)),
+        "r"(parity), "r"((uint32_t)YAVO_TC_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -70,6 +88,7 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, uint32_t parity) {
         "}\n" ::"r"(saddr(bar)),
         "r"(parity)
         : "memory");
+#endif
 }
 __device__ __forceinline__ void bar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");

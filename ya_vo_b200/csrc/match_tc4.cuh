@@ -254,9 +254,11 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 for (int h = EPI_SPLIT ? g : 0; h < (EPI_SPLIT ? g + 1 : T4 / 112); h++) {
                     const uint32_t ta = taddr + h * 112;
                     const int c0 = h * 112;
+#ifndef YAVO_TC_EXP_NO_LD
                     tmem_ld32(ta, v0);
                     tmem_ld32(ta + 32, v1);
                     tmem_wait2(v0, v1);
+#endif
 #ifndef YAVO_TC_EXP_NO_EPI
                     if (full) min_keys4<true>(v0, m4, 0, 0); else min_keys4<false>(v0, m4, c0, nvalid);
                     tmem_ld32(ta + 64, v2);
@@ -350,9 +352,11 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
                     const uint32_t s = t_cnt % NR4, ph = (t_cnt / NR4) & 1;
                     const uint32_t bytes = 32u * (uint32_t)min(T4, nt - t * T4);
+#ifndef YAVO_TC_EXP_NO_TMA
                     bar_wait(&r_empty[s], ph ^ 1);
                     bar_expect_tx(&r_full[s], bytes);
                     bulk_load(sRing + s * RING4_BYTES, dt + (size_t)t * T4 * 8, bytes, &r_full[s]);
+#endif
                 }
             } else {
                 t_cnt += n_tiles;
@@ -379,7 +383,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     const uint32_t s = t_cnt % NB4, ph = (t_cnt / NB4) & 1;    // operand stage
                     const uint32_t rs = t_cnt % NR4, rph = (t_cnt / NR4) & 1;  // ring entry
                     const int r = k * RPW + lane;  // train tile: rows k*RPW .. +RPW-1, as far as the tile goes
+#ifndef YAVO_TC_EXP_NO_TMA
                     bar_wait(&r_full[rs], rph);
+#endif
                     const bool in0 = r < T4 && t * T4 + r < nt, in1 = RPW > 32 && r + 32 < T4 && t * T4 + r + 32 < nt;
                     const uint8_t *src = sRing + rs * RING4_BYTES + r * 32;
                     const uint4 c0 = in0 ? *reinterpret_cast<const uint4 *>(src) : zero;
@@ -394,7 +400,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
 #endif
                     __syncwarp();
                     if (lane == 0) {
+#ifndef YAVO_TC_EXP_NO_TMA
                         bar_arrive(&r_empty[rs]);  // only now: the ring reads above have certainly completed (their values were used)
+#endif
                         bar_arrive(&b_full[s]);
                     }
                 }
