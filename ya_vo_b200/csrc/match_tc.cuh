@@ -108,6 +108,37 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the async proxy that tcgen05.mma reads operands through
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// The same on shared-window addresses computed once per kernel: taking the address of a __shared__ object inside the
+// loops costs an S2R (SR_CgaCtaId) + LEA per barrier operation.
+__device__ __forceinline__ void bar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, no swizzle, descriptor version 1 (sm_100):
 // bits [0,14) start address >> 4, [16,30) leading-dimension byte offset >> 4 (distance between the two 16-byte
 // K chunks of one instruction), [32,46) stride byte offset >> 4 (distance between 8-row groups), [46,48) = 1.
@@ -228,25 +259,27 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
     __shared__ uint64_t bars[6 * NSTAGE + 2 * NRING];
     __shared__ uint32_t tmem_base_s;
     __shared__ int2 comb[2][TQ];  // (distance, index) of accumulator group 1, double-buffered over work items
-    uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *b_full = bars + 2 * NSTAGE, *b_empty = bars + 3 * NSTAGE;
-    uint64_t *acc_full = bars + 4 * NSTAGE, *acc_empty = bars + 5 * NSTAGE;
-    uint64_t *r_full = bars + 6 * NSTAGE, *r_empty = r_full + NRING;
-    uint8_t *sA = smem_raw, *sB = smem_raw + NSTAGE * A_BYTES;
-    uint8_t *sAX = sB + NSTAGE * B_BYTES, *sBX = sAX + AX_BYTES, *sRing = sBX + BX_BYTES;
+    uint32_t bars_s, smem_s;  // shared-window addresses, computed once (through an opaque move: no rematerialisation)
+    asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(bars_s), "=r"(smem_s) : "r"(saddr(bars)), "r"(saddr(smem_raw)));
+    const uint32_t a_full = bars_s, a_empty = a_full + 8 * NSTAGE, b_full = a_empty + 8 * NSTAGE, b_empty = b_full + 8 * NSTAGE;
+    const uint32_t acc_full = b_empty + 8 * NSTAGE, acc_empty = acc_full + 8 * NSTAGE, r_full = acc_empty + 8 * NSTAGE, r_empty = r_full + 8 * NRING;
+    const uint32_t sA = smem_s, sB = sA + NSTAGE * A_BYTES, sAX = sB + NSTAGE * B_BYTES, sBX = sAX + AX_BYTES, sRing = sBX + BX_BYTES;
+    uint8_t *const gAX = smem_raw + NSTAGE * (A_BYTES + B_BYTES), *const gBX = gAX + AX_BYTES;  // generic pointers (set-up only)
+    const uint8_t *const gRing = gBX + BX_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) {
-            bar_init(&a_full[s], EXP_WARPS / 2);
-            bar_init(&a_empty[s], 1);
-            bar_init(&b_full[s], EXP_WARPS / 2);
-            bar_init(&b_empty[s], 1);
-            bar_init(&acc_full[s], 1);
-            bar_init(&acc_empty[s], EPI_WARPS / 2);
+            bar_init(a_full + 8 * (s), EXP_WARPS / 2);
+            bar_init(a_empty + 8 * (s), 1);
+            bar_init(b_full + 8 * (s), EXP_WARPS / 2);
+            bar_init(b_empty + 8 * (s), 1);
+            bar_init(acc_full + 8 * (s), 1);
+            bar_init(acc_empty + 8 * (s), EPI_WARPS / 2);
         }
         for (int s = 0; s < NRING; s++) {
-            bar_init(&r_full[s], 1);
-            bar_init(&r_empty[s], EXP_WARPS / 2);
+            bar_init(r_full + 8 * (s), 1);
+            bar_init(r_empty + 8 * (s), EXP_WARPS / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -254,7 +287,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
     for (int i = threadIdx.x; i < TQ + TT; i += THREADS) {
         const bool q = i < TQ;
         const int r = q ? i : i - TQ;
-        uint8_t *p = q ? sAX + r * 16 : sBX + r * 16;
+        uint8_t *p = q ? gAX + r * 16 : gBX + r * 16;
         const uint32_t w0 = q ? (0x38u | (0x58u << 8)) : (e4m3_small_int(r & 15) | (e4m3_small_int(r >> 4) << 8));
         *reinterpret_cast<uint4 *>(p) = make_uint4(w0, 0, 0, 0);
         *reinterpret_cast<uint4 *>(p + (q ? TQ : TT) * 16) = make_uint4(0, 0, 0, 0);
@@ -289,7 +322,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
             int best_d = 0x7fffffff, best_j = -1;
             for (int t = ((t_cnt & 1) == (uint32_t)g) ? 0 : 1; t < n_tiles; t += 2) {
                 const uint32_t ph = ((t_cnt + t) >> 1) & 1;
-                bar_wait(&acc_full[g], ph);
+                bar_wait(acc_full + 8 * (g), ph);
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * TT;
                 const int nvalid = min(TT, nt - t * TT);
@@ -327,7 +360,7 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                 const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) bar_arrive(&acc_empty[g]);
+                if (lane == 0) bar_arrive(acc_empty + 8 * (g));
                 const int ki = (int)m + 32768;  // 256 * distance + column, exact
                 if ((ki >> 8) < best_d) {
                     best_d = ki >> 8;
@@ -357,15 +390,15 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
             if (n_tiles > 0) {
                 if (lane == 0) {
                     const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
-                    const uint64_t adesc0 = smem_desc(saddr(sA + as * A_BYTES), TQ * 16u, 128u);
-                    const uint64_t adescx = smem_desc(saddr(sAX), TQ * 16u, 128u), bdescx = smem_desc(saddr(sBX), TT * 16u, 128u);
-                    bar_wait(&a_full[as], aph);
+                    const uint64_t adesc0 = smem_desc(sA + as * A_BYTES, TQ * 16u, 128u);
+                    const uint64_t adescx = smem_desc(sAX, TQ * 16u, 128u), bdescx = smem_desc(sBX, TT * 16u, 128u);
+                    bar_wait(a_full + 8 * (as), aph);
                     for (int t = 0; t < n_tiles; t++, t_cnt++) {
                         const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
-                        bar_wait(&b_full[s], ph);
-                        bar_wait(&acc_empty[s], ph ^ 1);
+                        bar_wait(b_full + 8 * (s), ph);
+                        bar_wait(acc_empty + 8 * (s), ph ^ 1);
                         fence_after_sync();
-                        const uint64_t bdesc0 = smem_desc(saddr(sB + s * B_BYTES), TT * 16u, 128u);
+                        const uint64_t bdesc0 = smem_desc(sB + s * B_BYTES, TT * 16u, 128u);
                         const uint32_t tacc = tmem_base + s * TT;
 #pragma unroll
 #if defined(YAVO_TC_EXP_MMA_HALF)
@@ -379,10 +412,10 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
 #ifndef YAVO_TC_EXP_NO_MMA
                         mma_f8(tacc, adescx, bdescx, 1);  // + column index
 #endif
-                        mma_commit(&b_empty[s]);
-                        mma_commit(&acc_full[s]);
+                        mma_commit(b_empty + 8 * (s));
+                        mma_commit(acc_full + 8 * (s));
                     }
-                    mma_commit(&a_empty[as]);
+                    mma_commit(a_empty + 8 * (as));
                 } else {
                     t_cnt += n_tiles;
                 }
@@ -396,9 +429,9 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {  // ring stage = operand stage = expander group
                     const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
                     const uint32_t bytes = 32u * (uint32_t)min(TT, nt - t * TT);
-                    bar_wait(&r_empty[s], ph ^ 1);
-                    bar_expect_tx(&r_full[s], bytes);
-                    bulk_load(sRing + s * RING_BYTES, dt + (size_t)t * TT * 8, bytes, &r_full[s]);
+                    bar_wait(r_empty + 8 * (s), ph ^ 1);
+                    bar_expect_tx(r_full + 8 * (s), bytes);
+                    bulk_load(sRing + s * RING_BYTES, dt + (size_t)t * TT * 8, bytes, r_full + 8 * (s));
                 }
             } else {
                 t_cnt += n_tiles;
@@ -416,27 +449,27 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                     const bool in = q0 + r < nq;
                     const uint4 w0 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8)) : zero;
                     const uint4 w1 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8) + 1) : zero;
-                    bar_wait(&a_empty[as], aph ^ 1);
-                    expand_half<false>(saddr(sA + as * A_BYTES), TQ, r, 0, w0, 0x80808080u, 0x38383838u);
-                    expand_half<false>(saddr(sA + as * A_BYTES), TQ, r, 1, w1, 0x80808080u, 0x38383838u);
+                    bar_wait(a_empty + 8 * (as), aph ^ 1);
+                    expand_half<false>(sA + as * A_BYTES, TQ, r, 0, w0, 0x80808080u, 0x38383838u);
+                    expand_half<false>(sA + as * A_BYTES, TQ, r, 1, w1, 0x80808080u, 0x38383838u);
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) bar_arrive(&a_full[as]);
+                    if (lane == 0) bar_arrive(a_full + 8 * (as));
                 }
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
                     const uint32_t s = t_cnt & 1, ph = (t_cnt >> 1) & 1;
                     if (ge != (int)s) continue;
                     const uint32_t rs = s, rph = ph;
                     const int r = k * 64 + lane;  // train tile: rows k*64 .. +63
-                    bar_wait(&r_full[rs], rph);
+                    bar_wait(r_full + 8 * (rs), rph);
                     const bool in0 = t * TT + r < nt, in1 = t * TT + r + 32 < nt;
-                    const uint8_t *src = sRing + rs * RING_BYTES + r * 32;
+                    const uint8_t *src = gRing + rs * RING_BYTES + r * 32;
                     const uint4 c0 = in0 ? *reinterpret_cast<const uint4 *>(src) : zero;
                     const uint4 c1 = in0 ? *reinterpret_cast<const uint4 *>(src + 16) : zero;
                     const uint4 c2 = in1 ? *reinterpret_cast<const uint4 *>(src + 1024) : zero;
                     const uint4 c3 = in1 ? *reinterpret_cast<const uint4 *>(src + 1040) : zero;
-                    bar_wait(&b_empty[s], ph ^ 1);
-                    const uint32_t tile = saddr(sB + s * B_BYTES);
+                    bar_wait(b_empty + 8 * (s), ph ^ 1);
+                    const uint32_t tile = sB + s * B_BYTES;
                     expand_half<true>(tile, TT, r, 0, c0, 0x80808080u, 0xF0F0F0F0u);
                     expand_half<true>(tile, TT, r, 1, c1, 0x80808080u, 0xF0F0F0F0u);
                     expand_half<true>(tile, TT, r + 32, 0, c2, 0x80808080u, 0xF0F0F0F0u);
@@ -444,8 +477,8 @@ match_tc_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        bar_arrive(&r_empty[rs]);  // only now: the ring reads above have certainly completed (their values were used)
-                        bar_arrive(&b_full[s]);
+                        bar_arrive(r_empty + 8 * (rs));  // only now: the ring reads above have certainly completed (their values were used)
+                        bar_arrive(b_full + 8 * (s));
                     }
                 }
                 a_cnt++;

@@ -170,30 +170,34 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
     __shared__ uint64_t bars[2 * NSTAGE + 2 * NACC + 2 * NB4 + 2 * NR4];
     __shared__ uint32_t tmem_base_s;
     __shared__ int2 comb[2][Q4];
-    uint64_t *a_full = bars, *a_empty = bars + NSTAGE, *acc_full = bars + 2 * NSTAGE, *acc_empty = acc_full + NACC;
-    uint64_t *b_full = acc_empty + NACC, *b_empty = b_full + NB4, *r_full = b_empty + NB4, *r_empty = r_full + NR4;
-    uint8_t *sA = smem_raw, *sB = sA + NSTAGE * A4_BYTES, *sAX = sB + NB4 * B4_BYTES, *sBX = sAX + AX4_BYTES;
-    uint8_t *sRing = sBX + BX4_BYTES;
+    // shared-window addresses, computed once (barriers are 8 bytes apart)
+    uint32_t bars_s, smem_s;  // through an opaque move: the compiler otherwise rematerialises the conversion (S2R + LEA) at every use
+    asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(bars_s), "=r"(smem_s) : "r"(saddr(bars)), "r"(saddr(smem_raw)));
+    const uint32_t a_full = bars_s, a_empty = a_full + 8 * NSTAGE, acc_full = a_empty + 8 * NSTAGE, acc_empty = acc_full + 8 * NACC;
+    const uint32_t b_full = acc_empty + 8 * NACC, b_empty = b_full + 8 * NB4, r_full = b_empty + 8 * NB4, r_empty = r_full + 8 * NR4;
+    const uint32_t sA = smem_s, sB = sA + NSTAGE * A4_BYTES, sAX = sB + NB4 * B4_BYTES, sBX = sAX + AX4_BYTES, sRing = sBX + BX4_BYTES;
+    uint8_t *const gAX = smem_raw + NSTAGE * A4_BYTES + NB4 * B4_BYTES, *const gBX = gAX + AX4_BYTES;  // generic pointers (set-up only)
+    const uint8_t *const gRing = gBX + BX4_BYTES;
     // warp index through a shuffle: provably warp-uniform, so the role branches and everything the MMA warp computes
     // stay in uniform registers (with a lane-0 branch around them every tcgen05.mma costs an ELECT / R2UR.BROADCAST loop)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; s++) {
-            bar_init(&a_full[s], EXP_WARPS / 2);
-            bar_init(&a_empty[s], 1);
+            bar_init(a_full + 8 * (s), EXP_WARPS / 2);
+            bar_init(a_empty + 8 * (s), 1);
         }
         for (int s = 0; s < NACC; s++) {
-            bar_init(&acc_full[s], 1);
-            bar_init(&acc_empty[s], EPI_SPLIT ? EPI_WARPS : EPI_WARPS / 2);
+            bar_init(acc_full + 8 * (s), 1);
+            bar_init(acc_empty + 8 * (s), EPI_SPLIT ? EPI_WARPS : EPI_WARPS / 2);
         }
         for (int s = 0; s < NB4; s++) {
-            bar_init(&b_full[s], EXP_WARPS / 2);
-            bar_init(&b_empty[s], 1);
+            bar_init(b_full + 8 * (s), EXP_WARPS / 2);
+            bar_init(b_empty + 8 * (s), 1);
         }
         for (int s = 0; s < NR4; s++) {
-            bar_init(&r_full[s], 1);
-            bar_init(&r_empty[s], EXP_WARPS / 2);
+            bar_init(r_full + 8 * (s), 1);
+            bar_init(r_empty + 8 * (s), EXP_WARPS / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -201,7 +205,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
     for (int i = threadIdx.x; i < Q4 + T4; i += THREADS) {
         const bool q = i < Q4;
         const int r = q ? i : i - Q4;
-        uint8_t *p = q ? sAX + r * 16 : sBX + r * 16;
+        uint8_t *p = q ? gAX + r * 16 : gBX + r * 16;
         *reinterpret_cast<uint4 *>(p) = index_slice(q, (uint32_t)r);
         *reinterpret_cast<uint4 *>(p + (q ? Q4 : T4) * 16) = make_uint4(0, 0, 0, 0);
     }
@@ -242,7 +246,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
             int best_d = 0x7fffffff, best_j = -1;
             for (int t = EPI_SPLIT ? 0 : (((t_cnt & 1) == (uint32_t)g) ? 0 : 1); t < n_tiles; t += EPI_SPLIT ? 1 : 2) {
                 const uint32_t acc = (t_cnt + t) % NACC, ph = ((t_cnt + t) / NACC) & 1;
-                bar_wait(&acc_full[acc], ph);
+                bar_wait(acc_full + 8 * (acc), ph);
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * T4;
                 const int nvalid = min(T4, nt - t * T4);
@@ -289,7 +293,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
                 fence_before_sync();
                 __syncwarp();
-                if (lane == 0) bar_arrive(&acc_empty[acc]);
+                if (lane == 0) bar_arrive(acc_empty + 8 * (acc));
                 const int ki = (int)m + 32768;  // 256 * distance + column, exact
                 if (m < 1.0e30f /* this warp's columns may all lie beyond the train set */ && (ki >> 8) < best_d) {
                     best_d = ki >> 8;
@@ -318,17 +322,17 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
             // control flow and operands), one elected lane issues tcgen05.mma / tcgen05.commit
             if (n_tiles > 0) {
                 const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
-                const uint64_t adesc0 = smem_desc(saddr(sA + as * A4_BYTES), Q4 * 16u, 128u);
-                const uint64_t adescx = smem_desc(saddr(sAX), Q4 * 16u, 128u), bdescx = smem_desc(saddr(sBX), T4 * 16u, 128u);
+                const uint64_t adesc0 = smem_desc(sA + as * A4_BYTES, Q4 * 16u, 128u);
+                const uint64_t adescx = smem_desc(sAX, Q4 * 16u, 128u), bdescx = smem_desc(sBX, T4 * 16u, 128u);
                 const uint32_t sf1 = tmem_base + SF_ONE_COL, sf128 = tmem_base + SF_128_COL;
-                bar_wait(&a_full[as], aph);
+                bar_wait(a_full + 8 * (as), aph);
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
                     const uint32_t s = t_cnt % NACC, ph = (t_cnt / NACC) & 1;    // accumulator
                     const uint32_t bs = t_cnt % NB4, bph = (t_cnt / NB4) & 1;    // operand stage
-                    bar_wait(&b_full[bs], bph);
-                    bar_wait(&acc_empty[s], ph ^ 1);
+                    bar_wait(b_full + 8 * (bs), bph);
+                    bar_wait(acc_empty + 8 * (s), ph ^ 1);
                     fence_after_sync();
-                    const uint64_t bdesc0 = smem_desc(saddr(sB + bs * B4_BYTES), T4 * 16u, 128u);
+                    const uint64_t bdesc0 = smem_desc(sB + bs * B4_BYTES, T4 * 16u, 128u);
                     const uint32_t tacc = tmem_base + s * T4;
                     if (elect_one()) {
 #ifndef YAVO_TC_EXP_NO_MMA
@@ -338,9 +342,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                                    sf128, k > 0);
                         mma_f4(tacc, adescx, bdescx, sf1, sf1, 1);  // + column index
 #endif
-                        mma_commit(&b_empty[bs]);
-                        mma_commit(&acc_full[s]);
-                        if (t == n_tiles - 1) mma_commit(&a_empty[as]);
+                        mma_commit(b_empty + 8 * (bs));
+                        mma_commit(acc_full + 8 * (s));
+                        if (t == n_tiles - 1) mma_commit(a_empty + 8 * (as));
                     }
                     __syncwarp();
                 }
@@ -353,9 +357,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     const uint32_t s = t_cnt % NR4, ph = (t_cnt / NR4) & 1;
                     const uint32_t bytes = 32u * (uint32_t)min(T4, nt - t * T4);
 #ifndef YAVO_TC_EXP_NO_TMA
-                    bar_wait(&r_empty[s], ph ^ 1);
-                    bar_expect_tx(&r_full[s], bytes);
-                    bulk_load(sRing + s * RING4_BYTES, dt + (size_t)t * T4 * 8, bytes, &r_full[s]);
+                    bar_wait(r_empty + 8 * (s), ph ^ 1);
+                    bar_expect_tx(r_full + 8 * (s), bytes);
+                    bulk_load(sRing + s * RING4_BYTES, dt + (size_t)t * T4 * 8, bytes, r_full + 8 * (s));
 #endif
                 }
             } else {
@@ -372,11 +376,11 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     const bool in = q0 + r < nq;
                     const uint4 w0 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8)) : zero;
                     const uint4 w1 = in ? __ldg(reinterpret_cast<const uint4 *>(dq + (size_t)(q0 + r) * 8) + 1) : zero;
-                    bar_wait(&a_empty[as], aph ^ 1);
-                    expand_row4<false>(saddr(sA + as * A4_BYTES), Q4, r, w0, w1);
+                    bar_wait(a_empty + 8 * (as), aph ^ 1);
+                    expand_row4<false>(sA + as * A4_BYTES, Q4, r, w0, w1);
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) bar_arrive(&a_full[as]);
+                    if (lane == 0) bar_arrive(a_full + 8 * (as));
                 }
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
                     if (ge != (int)(t_cnt & 1)) continue;
@@ -384,26 +388,26 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     const uint32_t rs = t_cnt % NR4, rph = (t_cnt / NR4) & 1;  // ring entry
                     const int r = k * RPW + lane;  // train tile: rows k*RPW .. +RPW-1, as far as the tile goes
 #ifndef YAVO_TC_EXP_NO_TMA
-                    bar_wait(&r_full[rs], rph);
+                    bar_wait(r_full + 8 * (rs), rph);
 #endif
                     const bool in0 = r < T4 && t * T4 + r < nt, in1 = RPW > 32 && r + 32 < T4 && t * T4 + r + 32 < nt;
-                    const uint8_t *src = sRing + rs * RING4_BYTES + r * 32;
+                    const uint8_t *src = gRing + rs * RING4_BYTES + r * 32;
                     const uint4 c0 = in0 ? *reinterpret_cast<const uint4 *>(src) : zero;
                     const uint4 c1 = in0 ? *reinterpret_cast<const uint4 *>(src + 16) : zero;
                     const uint4 c2 = in1 ? *reinterpret_cast<const uint4 *>(src + 1024) : zero;
                     const uint4 c3 = in1 ? *reinterpret_cast<const uint4 *>(src + 1040) : zero;
-                    bar_wait(&b_empty[s], ph ^ 1);
+                    bar_wait(b_empty + 8 * (s), ph ^ 1);
 #ifndef YAVO_TC_EXP_NO_EXP
-                    if (r < T4) expand_row4<true>(saddr(sB + s * B4_BYTES), T4, r, c0, c1);
-                    if (RPW > 32 && r + 32 < T4) expand_row4<true>(saddr(sB + s * B4_BYTES), T4, r + 32, c2, c3);
+                    if (r < T4) expand_row4<true>(sB + s * B4_BYTES, T4, r, c0, c1);
+                    if (RPW > 32 && r + 32 < T4) expand_row4<true>(sB + s * B4_BYTES, T4, r + 32, c2, c3);
                     fence_async_smem();
 #endif
                     __syncwarp();
                     if (lane == 0) {
 #ifndef YAVO_TC_EXP_NO_TMA
-                        bar_arrive(&r_empty[rs]);  // only now: the ring reads above have certainly completed (their values were used)
+                        bar_arrive(r_empty + 8 * (rs));  // only now: the ring reads above have certainly completed (their values were used)
 #endif
-                        bar_arrive(&b_full[s]);
+                        bar_arrive(b_full + 8 * (s));
                     }
                 }
                 a_cnt++;
