@@ -197,3 +197,31 @@ def test_seq00_length_batch(cuda_lib, oracle, offsets):
         idx, dist = out["match_idx"][f, :kq], out["match_dist"][f, :kq]
         assert idx.min() >= 0 and idx.max() < k
         assert np.array_equal(dist, hamming_rows(out["desc"][f - 1, :kq], out["desc"][f, idx]))
+
+
+def test_pinned_arrays_through_the_c_abi(cuda_lib, offsets):
+    """yavo_pinned_alloc / yavo_pinned_free: page-locked frame and result arrays for callers without a CUDA runtime
+    binding; the asynchronous submit / wait pair on them gives the same results as the synchronous call."""
+    frames = np.stack([synth.synth_frame("G30", 1000 + f, 120, 320) for f in range(6)])
+    buf = cuda_lib.pinned_zeros(frames.shape, np.uint8)
+    buf[:] = frames
+    assert buf.flags["C_CONTIGUOUS"] and buf.dtype == np.uint8
+    with cuda_lib.Context(device=0, n_slots=6, max_rows=120, max_cols=320, max_kp=500) as ctx:
+        ctx.set_brief_offsets(offsets)
+        ref = ctx.process_host_batch(frames, True)
+        out = ctx.alloc_batch_outputs(6, pinned=True)
+        _, ticket = ctx.submit_host_batch(buf, True, out)
+        ctx.wait_batch(ticket)
+        ctx.wait()
+    for k in ("n_kp", "rows", "cols", "desc", "match_idx", "match_dist"):
+        assert np.array_equal(out[k], ref[k]), k
+    del buf, out  # the blocks are freed when the last view goes away
+
+
+def test_set_matcher_rejects_unknown_kinds(cuda_lib):
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=64, max_cols=128, max_kp=16) as ctx:
+        for kind in (0, 1, 2, "tc", "tc8", "popc"):
+            ctx.set_matcher(kind)
+        with pytest.raises(cuda_lib.YavoError):
+            ctx.set_matcher(3)
+        ctx.set_matcher("tc")
