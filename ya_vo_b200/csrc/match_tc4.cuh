@@ -30,7 +30,7 @@ constexpr int Q4 = 128;                  // queries per work item (UMMA M)
 #ifndef YAVO_TC4_N
 #define YAVO_TC4_N 224
 #endif
-constexpr int T4 = YAVO_TC4_N;           // train descriptors per tile (UMMA N): 224 (two accumulators) or 112 (four)
+constexpr int T4 = YAVO_TC4_N;           // train descriptors per tile (UMMA N): 224 (two accumulators), 144 (three) or 112 (four)
 constexpr int NACC = 448 / T4;           // accumulators in TMEM (448 columns; the scale factors take the other 64)
 constexpr int RPW = T4 > 128 ? 64 : 32;  // train rows per expander warp
 #ifndef YAVO_TC4_EPI_SPLIT
@@ -38,7 +38,9 @@ constexpr int RPW = T4 > 128 ? 64 : 32;  // train rows per expander warp
 #endif
 // epilogue split: true = both warps of a TMEM lane quarter drain EVERY tile, 112 columns each (two tcgen05.ld round trips per
 // tile and warp); false = warps 0-3 / 4-7 take alternate tiles whole (four round trips)
-constexpr bool EPI_SPLIT = YAVO_TC4_EPI_SPLIT && T4 == 224;
+constexpr bool EPI_SPLIT = YAVO_TC4_EPI_SPLIT && (T4 == 224 || T4 == 144);
+constexpr int CW = T4 == 144 ? 72 : 112;  // accumulator columns per epilogue pass: 32 + 32 + 8 or 32 + 32 + 32 + 16
+static_assert(T4 % CW == 0, "tile width");
 constexpr int ROWB = 128;                // operand bytes per descriptor (two e2m1 per byte)
 constexpr int A4_BYTES = Q4 * ROWB;      // 16 KB
 constexpr int B4_BYTES = T4 * ROWB;      // 28 KB / 14 KB
@@ -98,6 +100,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr)
         : "memory");
+}
+// 8 columns into the first half of a 16-register buffer
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait16(uint32_t (&d)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]), "+r"(d[4]), "+r"(d[5]), "+r"(d[6]), "+r"(d[7]), "+r"(d[8]), "+r"(d[9]),
+                   "+r"(d[10]), "+r"(d[11]), "+r"(d[12]), "+r"(d[13]), "+r"(d[14]), "+r"(d[15])::"memory");
 }
 // one tcgen05.wait::ld for two loads in flight; every destination register is tied to it
 __device__ __forceinline__ void tmem_wait2(uint32_t (&a)[32], uint32_t (&b)[32]) {
@@ -253,11 +267,11 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
                 uint32_t v0[32], v1[32], v2[32], v3[16];
                 const bool full = nvalid == T4;
-                // 112 columns at a time = 32 + 32 | 32 + 16: the second pair is loaded while the first is reduced
+                // CW columns per pass = 32 + 32 | 32 + 16 (or | 8): the second group is loaded while the first is reduced
 #pragma unroll 1
-                for (int h = EPI_SPLIT ? g : 0; h < (EPI_SPLIT ? g + 1 : T4 / 112); h++) {
-                    const uint32_t ta = taddr + h * 112;
-                    const int c0 = h * 112;
+                for (int h = EPI_SPLIT ? g : 0; h < (EPI_SPLIT ? g + 1 : T4 / CW); h++) {
+                    const uint32_t ta = taddr + h * CW;
+                    const int c0 = h * CW;
 #ifndef YAVO_TC_EXP_NO_LD
                     tmem_ld32(ta, v0);
                     tmem_ld32(ta + 32, v1);
@@ -265,19 +279,24 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
 #endif
 #ifndef YAVO_TC_EXP_NO_EPI
                     if (full) min_keys4<true>(v0, m4, 0, 0); else min_keys4<false>(v0, m4, c0, nvalid);
-                    tmem_ld32(ta + 64, v2);
+                    if (CW == 112) tmem_ld32(ta + 64, v2);
                     if (full) min_keys4<true>(v1, m4, 0, 0); else min_keys4<false>(v1, m4, c0 + 32, nvalid);
-                    tmem_ld16(ta + 96, v3);
-                    tmem_wait2b(v2, v3);
+                    constexpr int TAIL = CW == 112 ? 16 : 8, TOFF = CW - TAIL;
+                    if (CW == 112) {
+                        tmem_ld16(ta + TOFF, v3);
+                        tmem_wait2b(v2, v3);
+                        if (full) min_keys4<true>(v2, m4, 0, 0); else min_keys4<false>(v2, m4, c0 + 64, nvalid);
+                    } else {
+                        tmem_ld8(ta + TOFF, v3);
+                        tmem_wait16(v3);
+                    }
                     if (full) {
-                        min_keys4<true>(v2, m4, 0, 0);
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) m4[(i >> 1) & 3] = fminf(m4[(i >> 1) & 3], fminf(__uint_as_float(v3[i]), __uint_as_float(v3[i + 1])));
+                        for (int i = 0; i < TAIL; i += 2) m4[(i >> 1) & 3] = fminf(m4[(i >> 1) & 3], fminf(__uint_as_float(v3[i]), __uint_as_float(v3[i + 1])));
                     } else {  // last tile of a train set
-                        min_keys4<false>(v2, m4, c0 + 64, nvalid);
 #pragma unroll
-                        for (int i = 0; i < 16; i++)
-                            if (c0 + 96 + i < nvalid) m4[i & 3] = fminf(m4[i & 3], __uint_as_float(v3[i]));
+                        for (int i = 0; i < TAIL; i++)
+                            if (c0 + TOFF + i < nvalid) m4[i & 3] = fminf(m4[i & 3], __uint_as_float(v3[i]));
                     }
 #endif
                 }
@@ -285,7 +304,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 if (DBG && dbg_acc && item == 0 && t == 0) {  // (test tool) re-read the tile
                     for (int c = 0; c < T4 / 16; c++) {
                         tmem_ld16(taddr + 16 * c, v3);
-                        tmem_wait2b(v2, v3);
+                        tmem_wait16(v3);
                         for (int i = 0; i < 16; i++) dbg_acc[row * T4 + 16 * c + i] = __uint_as_float(v3[i]);
                     }
                 }
