@@ -1,7 +1,7 @@
 // yavo_kernels.cuh — sm_100a kernels of the YA_VO front end (detect+blur, compact+score, exact
-// top-K select, BRIEF, Hamming match).  No tensor cores: the whole path is byte/integer work
-// (VABSDIFF4 / IDP.4A / IDP.2A / POPC / LOP3) staged through shared memory.  See DESIGN.md for the
-// data layout and the roofline that bounds each kernel.
+// top-K select, BRIEF, integer-pipe Hamming match).  Byte/integer work (VABSDIFF4 / IDP.4A / IDP.2A / POPC / LOP3)
+// staged through shared memory; the tensor-core matchers that replace K5 by default live in match_tc4.cuh /
+// match_tc.cuh.  See DESIGN.md for the data layout and the roofline that bounds each kernel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
