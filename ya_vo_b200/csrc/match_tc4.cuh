@@ -39,6 +39,10 @@ constexpr int RPW = T4 > 128 ? 64 : 32;  // train rows per expander warp
 // epilogue split: true = both warps of a TMEM lane quarter drain EVERY tile, 112 columns each (two tcgen05.ld round trips per
 // tile and warp); false = warps 0-3 / 4-7 take alternate tiles whole (four round trips)
 constexpr bool EPI_SPLIT = YAVO_TC4_EPI_SPLIT && (T4 == 224 || T4 == 144);
+#ifndef YAVO_TC4_NCH
+#define YAVO_TC4_NCH 4
+#endif
+constexpr int NCH = YAVO_TC4_NCH;        // independent minimum chains per epilogue thread (4 or 8)
 constexpr int CW = T4 == 144 ? 72 : 112;  // accumulator columns per epilogue pass: 32 + 32 + 8 or 32 + 32 + 32 + 16
 static_assert(T4 % CW == 0, "tile width");
 constexpr int ROWB = 128;                // operand bytes per descriptor (two e2m1 per byte)
@@ -158,17 +162,17 @@ __device__ __forceinline__ uint4 index_slice(bool query, uint32_t j) {
 }
 
 template <bool FULL>
-__device__ __forceinline__ void min_keys4(const uint32_t (&v)[32], float (&m)[4], int col0, int nvalid) {
+__device__ __forceinline__ void min_keys4(const uint32_t (&v)[32], float (&m)[NCH], int col0, int nvalid) {
     if (FULL) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
+        for (int i = 0; i < 32; i += 2 * NCH) {
 #pragma unroll
-            for (int c = 0; c < 4; c++) m[c] = fminf(m[c], fminf(__uint_as_float(v[i + 2 * c]), __uint_as_float(v[i + 2 * c + 1])));
+            for (int c = 0; c < NCH; c++) m[c] = fminf(m[c], fminf(__uint_as_float(v[i + 2 * c]), __uint_as_float(v[i + 2 * c + 1])));
         }
     } else {
 #pragma unroll
         for (int i = 0; i < 32; i++)
-            if (col0 + i < nvalid) m[i & 3] = fminf(m[i & 3], __uint_as_float(v[i]));
+            if (col0 + i < nvalid) m[i & (NCH - 1)] = fminf(m[i & (NCH - 1)], __uint_as_float(v[i]));
     }
 }
 
@@ -264,7 +268,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * T4;
                 const int nvalid = min(T4, nt - t * T4);
-                float m4[4] = {3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f};
+                float m4[NCH];
+#pragma unroll
+                for (int c = 0; c < NCH; c++) m4[c] = 3.0e38f;
                 uint32_t v0[32], v1[32], v2[32], v3[16];
                 const bool full = nvalid == T4;
                 // CW columns per pass = 32 + 32 | 32 + 16 (or | 8): the second group is loaded while the first is reduced
@@ -292,11 +298,11 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     }
                     if (full) {
 #pragma unroll
-                        for (int i = 0; i < TAIL; i += 2) m4[(i >> 1) & 3] = fminf(m4[(i >> 1) & 3], fminf(__uint_as_float(v3[i]), __uint_as_float(v3[i + 1])));
+                        for (int i = 0; i < TAIL; i += 2) m4[(i >> 1) & (NCH - 1)] = fminf(m4[(i >> 1) & (NCH - 1)], fminf(__uint_as_float(v3[i]), __uint_as_float(v3[i + 1])));
                     } else {  // last tile of a train set
 #pragma unroll
                         for (int i = 0; i < TAIL; i++)
-                            if (c0 + TOFF + i < nvalid) m4[i & 3] = fminf(m4[i & 3], __uint_as_float(v3[i]));
+                            if (c0 + TOFF + i < nvalid) m4[i & (NCH - 1)] = fminf(m4[i & (NCH - 1)], __uint_as_float(v3[i]));
                     }
 #endif
                 }
@@ -309,7 +315,8 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     }
                 }
 #endif
-                const float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+                float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
+                if (NCH == 8) m = fminf(m, fminf(fminf(m4[NCH - 4], m4[NCH - 3]), fminf(m4[NCH - 2], m4[NCH - 1])));
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) bar_arrive(acc_empty + 8 * (acc));
