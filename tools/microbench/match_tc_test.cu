@@ -13,10 +13,10 @@
 
 #ifdef TC4   // packed 4-bit operands (kind::mxf4), 128 x 224 tiles
 #define KERNEL yavo::tcm4::match_tc4_kernel<true>
-constexpr int TILE_N = yavo::tcm4::T4, SMEM = yavo::tcm4::SMEM4_BYTES;
+constexpr int TILE_N = yavo::tcm4::T4, SMEM = yavo::tcm4::SMEM4_BYTES, NTHR = yavo::tcm4::THREADS4;
 #else        // FP8 operands (kind::f8f6f4), 128 x 256 tiles
 #define KERNEL yavo::tcm::match_tc_kernel<true>
-constexpr int TILE_N = yavo::tcm::TT, SMEM = yavo::tcm::SMEM_BYTES;
+constexpr int TILE_N = yavo::tcm::TT, SMEM = yavo::tcm::SMEM_BYTES, NTHR = yavo::tcm::THREADS;
 #endif
 
 #define CK(x)                                                                              \
@@ -82,7 +82,7 @@ int main(int argc, char **argv) {
     float best_ms = 1e30f;
     for (int rep = 0; rep < reps; rep++) {
         CK(cudaEventRecord(e0));
-        KERNEL<<<grid, yavo::tcm::THREADS, SMEM>>>(
+        KERNEL<<<grid, NTHR, SMEM>>>(
             d_desc, d_n, 0, d_desc, d_n, 0, (size_t)stride * 8, 0, 1, pairs, q_tiles, stride, d_idx, d_dist,
             rep == 0 ? d_dots : nullptr);
         CK(cudaEventRecord(e1));

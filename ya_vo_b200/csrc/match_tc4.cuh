@@ -39,6 +39,7 @@ constexpr int RPW = T4 > 128 ? 64 : 32;  // train rows per expander warp
 // epilogue split: true = both warps of a TMEM lane quarter drain EVERY tile, 112 columns each (two tcgen05.ld round trips per
 // tile and warp); false = warps 0-3 / 4-7 take alternate tiles whole (four round trips)
 constexpr bool EPI_SPLIT = YAVO_TC4_EPI_SPLIT && (T4 == 224 || T4 == 144);
+constexpr int THREADS4 = THREADS;
 #ifndef YAVO_TC4_NCH
 #define YAVO_TC4_NCH 4
 #endif
@@ -176,10 +177,23 @@ __device__ __forceinline__ void min_keys4(const uint32_t (&v)[32], float (&m)[NC
     }
 }
 
+// every role walks the same list of work items: role branches outermost, one item loop per role (83 instead of 96
+// registers and 9 % less time than one shared item loop with the role branches inside)
+#define YAVO_TC4_FOR_ITEMS \
+    for (int item = blockIdx.x; item < items; item += gridDim.x) { \
+        const int pair = item / q_tiles, q0 = (item - pair * q_tiles) * Q4; \
+        const int nq = nq_all ? nq_all[pair + q_set_offset] : nq_fixed; \
+        const int nt = nt_all ? nt_all[pair + t_set_offset] : nt_fixed; \
+        if (q0 >= nq) continue; \
+        const int n_tiles = (nt + T4 - 1) / T4; \
+        const uint32_t *dq = dq_all + (size_t)(pair + q_set_offset) * set_stride_words; \
+        const uint32_t *dt = dt_all + (size_t)(pair + t_set_offset) * set_stride_words; \
+        (void)dq; (void)dt; (void)nt; (void)n_tiles;
+
 // Arguments as match_tc_kernel.  dbg_acc (test tool only): the 128 x 224 accumulator values (key - 32768) of the
 // first tile of work item 0.
 template <bool DBG>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(THREADS4, 1)
 match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
                  const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
                  size_t set_stride_words, int q_set_offset, int t_set_offset, int pairs, int q_tiles, int out_stride,
@@ -220,7 +234,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // constant index slice: chunk 0 = 22 nibbles, chunk 1 = 0
-    for (int i = threadIdx.x; i < Q4 + T4; i += THREADS) {
+    for (int i = threadIdx.x; i < Q4 + T4; i += THREADS4) {
         const bool q = i < Q4;
         const int r = q ? i : i - Q4;
         uint8_t *p = q ? gAX + r * 16 : gBX + r * 16;
@@ -249,16 +263,8 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
     const int items = pairs * q_tiles;
     uint32_t e_cnt = 0, a_cnt = 0, t_cnt = 0;
 
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int pair = item / q_tiles, q0 = (item - pair * q_tiles) * Q4;
-        const int nq = nq_all ? nq_all[pair + q_set_offset] : nq_fixed;
-        const int nt = nt_all ? nt_all[pair + t_set_offset] : nt_fixed;
-        if (q0 >= nq) continue;
-        const int n_tiles = (nt + T4 - 1) / T4;
-        const uint32_t *dq = dq_all + (size_t)(pair + q_set_offset) * set_stride_words;
-        const uint32_t *dt = dt_all + (size_t)(pair + t_set_offset) * set_stride_words;
-
-        if (warp < EPI_WARPS) {
+    if (warp < EPI_WARPS) {
+        YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ epilogue (two groups on alternate accumulators)
             const int g = warp >> 2, row = (warp & 3) * 32 + lane;
             int best_d = 0x7fffffff, best_j = -1;
@@ -343,7 +349,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     out_dist[(size_t)pair * out_stride + q] = best_d;
                 }
             }
-        } else if (warp == MMA_WARP) {
+        }
+    } else if (warp == MMA_WARP) {
+        YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ MMA issue: the whole warp runs the loop (uniform
             // control flow and operands), one elected lane issues tcgen05.mma / tcgen05.commit
             if (n_tiles > 0) {
@@ -376,7 +384,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 }
                 a_cnt++;
             }
-        } else if (warp == LOAD_WARP) {
+        }
+    } else if (warp == LOAD_WARP) {
+        YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ loader: packed bits of the train tiles -> ring
             if (n_tiles > 0 && lane == 0) {
                 for (int t = 0; t < n_tiles; t++, t_cnt++) {
@@ -391,7 +401,9 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
             } else {
                 t_cnt += n_tiles;
             }
-        } else {
+        }
+    } else if (warp < LOAD_WARP) {
+        YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ expanders (two groups on alternate operand stages)
             if (n_tiles > 0) {
                 const int ew = warp - (EPI_WARPS + 1), ge = ew >> 2, k = ew & 3;

@@ -854,7 +854,7 @@ static int launch_match_tc(yavo_ctx *ctx, const uint32_t *dq_all, const int *nq_
                               dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
                               out_stride, o_idx, o_dist, nullptr));
     else
-        PROF(KC_MATCH_TC, tcm4::match_tc4_kernel<false><<<grid, tcm::THREADS, tcm4::SMEM4_BYTES, ctx->stream>>>(
+        PROF(KC_MATCH_TC, tcm4::match_tc4_kernel<false><<<grid, tcm4::THREADS4, tcm4::SMEM4_BYTES, ctx->stream>>>(
                               dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
                               out_stride, o_idx, o_dist, nullptr));
     CK_LAUNCH();
