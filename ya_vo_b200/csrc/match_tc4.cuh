@@ -8,14 +8,19 @@
 //     Eight nibbles come out of ONE LOP3 ((w << k) & 0x88888888, | or ^ a constant) instead of four bytes, so the
 //     expansion — which the integer ALU pipe (64 lanes / clk / SM) bounds in the FP8 version — costs half, the
 //     operand tiles are half as large in shared memory, and one instruction covers 64 bit positions:
-//     4 + 1 instructions of 56 clk per 128 x 112 tile instead of 8 + 1 of 128 clk per 128 x 256 tile.
+//     4 + 1 instructions of 112 clk per 128 x 224 tile instead of 8 + 1 of 128 clk per 128 x 256 tile.
 //   * all scale factors of an operand are EQUAL, so the TMEM layout of the scale-factor matrices does not matter:
 //     two 32-column regions are filled with the bytes 0x7F (1.0) and 0x86 (128.0) once per CTA.
 //   * the fifth instruction adds the train column j (scale factors 1 on both sides): query nibbles
 //     {1, 4, 4 x4, 4 x16} times train nibbles {j & 3, (j >> 2) & 3, (j >> 4) & 3 x4, (j >> 6) & 3 x16}.
-//   * N = 112: four accumulators (448 columns) and the scale factors (64 columns) fit the 512 TMEM columns, and four
-//     tiles in flight hide the ~400-clk mbarrier hand-offs between the MMA thread and the epilogue warps;
-//     2000 keypoints = 18 tiles of 112 with 0.8 % padding.
+//   * N = 224: two accumulators (448 columns) and the scale factors (64 columns) fill the 512 TMEM columns;
+//     2000 keypoints = 9 tiles of 224 with 0.8 % padding.  (-DYAVO_TC4_N=144 / 112 give three / four narrower
+//     accumulators; both measured slower on B200: the fixed cost per tile decides, profiles/r1k_match_tc_ncu_summary.md.)
+//   * both epilogue warps of a TMEM lane quarter drain every tile, 112 columns each; the role branches are outermost,
+//     each role with its own loop over the work items (83 registers per thread).
+//
+// The -DYAVO_TC_EXP_* macros switch single pieces of work off for the timing experiments recorded in profiles/
+// (results are wrong with any of them defined; they are never set by the library build).
 //
 // Warp roles, barriers and the first-minimum rule are those of match_tc.cuh.
 #pragma once
@@ -56,7 +61,7 @@ constexpr int NB4 = 4;                   // train-tile operand stages and packed
 #ifndef YAVO_TC4_NR
 #define YAVO_TC4_NR 4
 #endif
-constexpr int NR4 = YAVO_TC4_NR;         // packed-bit ring entries (even): a bulk copy takes ~1600 clk to complete, several must be in flight
+constexpr int NR4 = YAVO_TC4_NR;         // packed-bit ring entries (even); 8 measured no faster than 4
 constexpr int SMEM4_BYTES = NSTAGE * A4_BYTES + NB4 * B4_BYTES + AX4_BYTES + BX4_BYTES + NR4 * RING4_BYTES;
 constexpr uint32_t SF_ONE_COL = 448, SF_128_COL = 480;  // TMEM columns of the two scale-factor regions
 
