@@ -188,10 +188,12 @@ int yavo_set_sub_batch(yavo_ctx *ctx, int frames);
 int yavo_submit_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,
                            int32_t *n_kp, int32_t *out_rows, int32_t *out_cols, float *scores, uint8_t *desc,
                            int32_t *match_idx, int32_t *match_dist);
-/* blocks until the batch with this ticket has its results in its host arrays (later batches keep running) */
+/* blocks until the batch with this ticket has its results in its host arrays (later batches keep running).
+ * Returns YAVO_ERR_CAPACITY / YAVO_ERR_CUDA when THIS batch overflowed the FAST candidate list or tripped the select
+ * kernel's watchdog (every batch carries its own status word; its frames' results are then invalid). */
 int yavo_wait_batch(yavo_ctx *ctx, int ticket);
 /* blocks until every submitted batch has finished and its results are in the host arrays; reports a FAST
- * candidate-list overflow of any of them */
+ * candidate-list overflow of any batch that was not waited for by ticket */
 int yavo_wait(yavo_ctx *ctx);
 
 int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,

@@ -506,10 +506,12 @@ int yavo_oracle_remove_outliers(const int32_t *dist, int n, int threshold, uint8
     if (n == 0) return 0;  // the reference dereferences end() here (UB); defined as "nothing kept"
     int mn = INT_MAX;
     for (int i = 0; i < n; i++) mn = std::min(mn, dist[i]);
-    long long lim = std::max((long long)2 * mn, (long long)threshold);
+    // 2 * distance in the reference's int arithmetic: with an empty train set every distance is INT_MAX and the
+    // product wraps to -2 on the reference's targets (signed overflow, UB by the letter), so nothing is kept
+    const int lim = std::max((int)(2u * (unsigned)mn), threshold);
     int kept = 0;
     for (int i = 0; i < n; i++) {
-        keep[i] = ((long long)dist[i] < lim) ? 1 : 0;
+        keep[i] = (dist[i] < lim) ? 1 : 0;
         kept += keep[i];
     }
     return kept;

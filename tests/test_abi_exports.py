@@ -57,3 +57,38 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cc", ".cpp")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "pyoracle" not in txt and "yavo_oracle" not in txt and "libyavo_oracle" not in txt, f
+
+
+def test_remove_outliers_empty_train_set_keeps_nothing(cuda_lib, oracle):
+    """All distances INT_MAX (empty train set): 2 * INT_MAX wraps to -2 in the reference's int arithmetic
+    (src/BriefDescriptor.cc:224), so max(-2, threshold) = threshold and nothing is kept — host C ABI, device filter
+    and oracle agree."""
+    import numpy as np
+    d = np.full(5, 2**31 - 1, np.int32)
+    assert not cuda_lib.remove_outliers(d, 20).any()
+    assert not oracle.remove_outliers(d, 20).any()
+    d = np.array([2**31 - 1, 7, 2**31 - 1, 13, 14], np.int32)
+    assert np.array_equal(cuda_lib.remove_outliers(d, 20), oracle.remove_outliers(d, 20))
+    assert list(oracle.remove_outliers(d, 20)) == [False, True, False, True, True]
+
+
+def test_pinned_views_keep_their_block_alive(cuda_lib):
+    """Slices handed to callbacks must keep the page-locked block alive after the parent array is dropped."""
+    import ctypes as C
+    import gc
+    import numpy as np
+    libc = C.CDLL(None)
+    libc.malloc.restype = C.c_void_p
+    libc.malloc.argtypes = [C.c_size_t]
+    libc.free.argtypes = [C.c_void_p]
+    freed = []
+    ptr = libc.malloc(4096)
+    a = cuda_lib._owned_view(ptr, 4096, lambda p: (freed.append(p), libc.free(p))).view(np.int32).reshape(32, 32)
+    a[...] = 7
+    row = a[3, :5]
+    del a
+    gc.collect()
+    assert freed == [] and int(row.sum()) == 35
+    del row
+    gc.collect()
+    assert freed == [ptr]

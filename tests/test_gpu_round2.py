@@ -1,0 +1,84 @@
+"""Round-2 regression and feature tests on the GPU (through the C ABI, checked against the oracle)."""
+import numpy as np
+import pytest
+
+from ya_vo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _pin(a):
+    from ya_vo_b200 import capi
+    p = capi.pinned_zeros(a.shape, a.dtype)
+    p[...] = a
+    return p
+
+
+def _same_results(got, exp, n):
+    assert np.array_equal(got["n_kp"][:n], exp["n_kp"][:n])
+    for f in range(n):
+        k = exp["n_kp"][f]
+        for key in ("rows", "cols", "scores", "desc"):
+            assert np.array_equal(got[key][f, :k], exp[key][f, :k]), (key, f)
+        if f > 0:
+            kq = exp["n_kp"][f - 1]
+            assert np.array_equal(got["match_idx"][f, :kq], exp["match_idx"][f, :kq]), f
+            assert np.array_equal(got["match_dist"][f, :kq], exp["match_dist"][f, :kq]), f
+
+
+def test_alternating_batch_sizes_without_waiting(cuda_lib, offsets):
+    """Stage size changes between un-waited submits (64 frames -> 16-frame stages, 512 -> 128): the staging halves move,
+    and a new half may cover both halves of the previous submit (round-1 advisor finding)."""
+    small = _pin(synth.synth_batch(64, "G30", 100, 120, 320))
+    big = _pin(synth.synth_batch(512, "B4", 900, 120, 320))
+    with cuda_lib.Context(device=0, n_slots=512, max_rows=120, max_cols=320, max_kp=300) as ctx:
+        ctx.set_brief_offsets(offsets)
+        es = {k: v.copy() for k, v in ctx.process_host_batch(small, True).items()}
+        eb = {k: v.copy() for k, v in ctx.process_host_batch(big, True).items()}
+        for _ in range(3):
+            o1, t1 = ctx.submit_host_batch(small, True)
+            o2, t2 = ctx.submit_host_batch(big, True)
+            o3, t3 = ctx.submit_host_batch(small, True)
+            ctx.wait_batch(t1)
+            _same_results(o1, es, 64)
+            ctx.wait_batch(t2)
+            _same_results(o2, eb, 512)
+            ctx.wait()
+            _same_results(o3, es, 64)
+
+
+def test_wait_batch_reports_the_overflow_of_its_own_batch(cuda_lib, offsets):
+    """A candidate-list overflow is reported by yavo_wait_batch for the batch that had it, not for its neighbours."""
+    ok = _pin(synth.synth_batch(8, "G30", 5, 120, 320))
+    bad = _pin(synth.synth_batch(8, "U", 6, 120, 320))  # uniform noise: ~4x the candidates
+    with cuda_lib.Context(device=0, n_slots=8, max_rows=120, max_cols=320, max_kp=300, max_cand=900) as ctx:
+        ctx.set_brief_offsets(offsets)
+        exp = {k: v.copy() for k, v in ctx.process_host_batch(ok, True).items()}
+        _, t1 = ctx.submit_host_batch(ok, True)
+        _, t2 = ctx.submit_host_batch(bad, True)
+        o3, t3 = ctx.submit_host_batch(ok, True)
+        ctx.wait_batch(t1)
+        with pytest.raises(cuda_lib.YavoError):
+            ctx.wait_batch(t2)
+        ctx.wait_batch(t3)
+        _same_results(o3, exp, 8)
+        ctx.wait()  # nothing left to report
+        _, t4 = ctx.submit_host_batch(bad, True)
+        with pytest.raises(cuda_lib.YavoError):
+            ctx.wait()  # a batch nobody waited for by ticket is reported here
+
+
+def test_filter_pairs_empty_train_set(cuda_lib, oracle, offsets):
+    """Train frame without keypoints: distances INT_MAX, nothing kept by the device filter or the host one."""
+    a = synth.synth_frame("G30", 1, 120, 320)
+    frames = np.stack([a, np.full_like(a, 128)])
+    with cuda_lib.Context(device=0, n_slots=2, max_rows=120, max_cols=320, max_kp=300) as ctx:
+        ctx.set_brief_offsets(offsets)
+        out = ctx.process_host_batch(frames, True)
+        assert out["n_kp"][1] == 0 and out["n_kp"][0] > 0
+        k = out["n_kp"][0]
+        assert (out["match_dist"][1, :k] == 2**31 - 1).all() and (out["match_idx"][1, :k] == -1).all()
+        n_pairs, min_dist, _ = ctx.filter_pairs(0, 2, 20)
+        assert n_pairs[1] == 0
+        assert not cuda_lib.remove_outliers(out["match_dist"][1, :k], 20).any()
+        assert not oracle.remove_outliers(out["match_dist"][1, :k], 20).any()

@@ -104,3 +104,13 @@ def test_run_sequence_with_tracking_matches_oracle(cuda_lib, oracle, offsets):
         assert np.array_equal(xy[:k].view(np.uint32), o_next.view(np.uint32)), f
         ok = o_st == 1
         assert np.array_equal(er[:k][ok].view(np.uint32), o_err[ok].view(np.uint32)), f
+
+
+def test_batch_of_one_is_rejected():
+    """A 1-frame batch would re-deliver its seam frame forever (round-1 advisor finding)."""
+    from ya_vo_b200 import sharding
+    frames = synth.synth_batch(3, "U", 1, 12, 20)
+    with pytest.raises(ValueError):
+        stream.FrameStream(3, lambda i: frames[i], batch=1, shape=(12, 20))
+    with pytest.raises(ValueError):
+        sharding.process_shard(None, lambda a, b: frames[a:b], 3, 0, 1, batch=1)

@@ -374,22 +374,34 @@ class Context:
         return (counts, best.value, bc.value, res) if residuals else (counts, best.value, bc.value)
 
 
-class _PinnedBlock:
-    """Owner of one yavo_pinned_alloc block; freed when the last numpy view of it is collected."""
+_PINNED_TYPES = {}
 
-    def __init__(self, nbytes):
-        self.ptr = lib().yavo_pinned_alloc(max(int(nbytes), 1))
-        if not self.ptr:
-            raise YavoError("yavo_pinned_alloc(%d) failed" % nbytes)
-        self.buf = (C.c_uint8 * max(int(nbytes), 1)).from_address(self.ptr)
 
-    def __del__(self):
-        try:
-            if self.ptr:
-                lib().yavo_pinned_free(self.ptr)
-                self.ptr = None
-        except Exception:
-            pass
+def _pinned_array_type(nbytes):
+    """ctypes array type whose instances free their page-locked block when collected.  numpy arrays made with
+    np.frombuffer keep the ctypes instance alive as their (transitive) base — including every slice and view derived
+    later — so the block lives exactly as long as anything can still read it."""
+    t = _PINNED_TYPES.get(nbytes)
+    if t is None:
+        class _Pinned(C.c_uint8 * nbytes):
+            _free = None
+
+            def __del__(self):
+                free, self._free = self._free, None
+                if free is not None:
+                    try:
+                        free(C.addressof(self))
+                    except Exception:
+                        pass
+        t = _PINNED_TYPES[nbytes] = _Pinned
+    return t
+
+
+def _owned_view(ptr, nbytes, free):
+    """uint8 numpy array over [ptr, ptr + nbytes) that calls free(ptr) when the last view of it is gone."""
+    blk = _pinned_array_type(nbytes).from_address(ptr)
+    blk._free = free
+    return np.frombuffer(blk, dtype=np.uint8, count=nbytes)
 
 
 def pinned_zeros(shape, dtype=np.uint8):
@@ -397,16 +409,15 @@ def pinned_zeros(shape, dtype=np.uint8):
     shape = (shape,) if np.isscalar(shape) else tuple(shape)
     dt = np.dtype(dtype)
     n = int(np.prod(shape)) * dt.itemsize
-    blk = _PinnedBlock(n)
-    a = np.frombuffer(blk.buf, dtype=np.uint8, count=n).view(dt).reshape(shape) if n else np.zeros(shape, dt)
+    if n == 0:
+        return np.zeros(shape, dt)
+    L = lib()
+    ptr = L.yavo_pinned_alloc(n)
+    if not ptr:
+        raise YavoError("yavo_pinned_alloc(%d) failed" % n)
+    a = _owned_view(ptr, n, L.yavo_pinned_free).view(dt).reshape(shape)
     a[...] = 0
-    _PINNED_OWNERS[id(blk)] = blk  # numpy keeps blk.buf alive; the registry keeps blk (and its free) tied to the array
-    import weakref
-    weakref.finalize(a, _PINNED_OWNERS.pop, id(blk), None)
     return a
-
-
-_PINNED_OWNERS = {}
 
 
 def ring_points(xc, yc):

@@ -49,7 +49,8 @@ struct yavo_ctx {
     int32_t *d_midx = nullptr, *d_mdist = nullptr;
     int32_t *d_pairs = nullptr;  // per slot max_kp x 8 ints: filtered point pairs of (slot-1, slot)
     int *d_npairs = nullptr, *d_minDist = nullptr;
-    int *d_status = nullptr, *d_noob = nullptr;
+    int *d_status = nullptr, *d_noob = nullptr;  // d_status: STATUS_WORDS ints; [STATUS_GENERAL] for the synchronous entry points, [t] for ticket t
+    int *cur_status = nullptr;                   // the word the kernels of the current call report to
     uint32_t *d_offs = nullptr, *d_spos = nullptr;  // BRIEF tests: packed offsets / positions inside a staged patch
     bool offs_set = false;
     // scratch for the explicit-point / explicit-descriptor entry points
@@ -79,7 +80,9 @@ struct yavo_ctx {
     int fetched_C = 0;
     cudaEvent_t ev_ticket[16] = {};
     unsigned long long n_tickets = 0;
+    char ticket_pending[16] = {};  // submitted, status word not yet looked at
     char raw_used[2] = {0, 0};
+    int raw_C = 0;  // frames per staging half of the last submit (the halves sit at buf * raw_C * frame bytes)
     int pipeline_chunk = 0;  // frames per copy/compute stage of the host-batch path (0 = automatic)
     int matcher = 0;    // 0 = tensor-core matcher on packed 4-bit operands (K5t4), 1 = POPC matcher (K5), 2 = tensor-core matcher on FP8 operands (K5t)
     int n_sms = 148;
@@ -113,6 +116,7 @@ struct yavo_ctx {
     std::string err;
 };
 
+enum { STATUS_TICKETS = 16, STATUS_GENERAL = 16, STATUS_WORDS = 17 };
 enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_PYR, KC_KLT, KC_EPI, KC_MATCH_TC, KC_COUNT };
 
 namespace {
@@ -309,25 +313,27 @@ int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
         ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp, score_in_k2(n) ? 0 : 1,
         ctx->d_kp_row + o,
         ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
-        ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->d_status));
+        ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->cur_status));
     CK_LAUNCH();
     return 0;
 }
 
-int check_status(yavo_ctx *ctx) {
-    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (ctx->h_small[0] == 2) {
-        CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
-        return fail(ctx, YAVO_ERR_CUDA, "select kernel watchdog fired (work queue did not drain); results are invalid");
-    }
-    if (ctx->h_small[0] != 0) {
-        CK(cudaMemsetAsync(ctx->d_status, 0, sizeof(int), ctx->stream));
+int status_error(yavo_ctx *ctx, int st) {
+    if (st == 2) return fail(ctx, YAVO_ERR_CUDA, "select kernel watchdog fired (work queue did not drain); results are invalid");
+    if (st != 0)
         return fail(ctx, YAVO_ERR_CAPACITY,
                     "FAST candidate list overflowed max_cand=%d; create the context with a larger max_cand",
                     ctx->max_cand);
-    }
     return 0;
+}
+
+// synchronises ctx->stream; reports (and clears) what the kernels of the synchronous entry points flagged
+int check_status(yavo_ctx *ctx) {
+    CK(cudaMemcpyAsync(ctx->h_small, ctx->d_status + STATUS_GENERAL, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const int st = ctx->h_small[0];
+    if (st != 0) CK(cudaMemsetAsync(ctx->d_status + STATUS_GENERAL, 0, sizeof(int), ctx->stream));
+    return status_error(ctx, st);
 }
 
 int choose_chunks(int nq, int nt, int pairs) {
@@ -560,12 +566,14 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_npairs, S));
     CKC(dalloc(&c->d_minDist, S));
     CKC(cudaMemset(c->d_npairs, 0, S * sizeof(int)));
-    CKC(dalloc(&c->d_status, 1));
+    CKC(cudaMemset(c->d_minDist, 0, S * sizeof(int)));  // row 0 of a yavo_filter_pairs range is never written
+    CKC(dalloc(&c->d_status, STATUS_WORDS));
+    c->cur_status = c->d_status + STATUS_GENERAL;
     CKC(dalloc(&c->d_noob, 1));
     CKC(dalloc(&c->d_offs, 256));
     CKC(dalloc(&c->d_spos, 256));
     CKC(cudaMemset(c->d_frames, 0, S * c->frame_stride));
-    CKC(cudaMemset(c->d_status, 0, sizeof(int)));
+    CKC(cudaMemset(c->d_status, 0, STATUS_WORDS * sizeof(int)));
     CKC(cudaMemset(c->d_nbk, 0, S * sizeof(int)));
     CKC(cudaMemset(c->d_nkp, 0, S * sizeof(int)));
     CKC(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), 64 * sizeof(int)));
@@ -940,7 +948,9 @@ int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *kee
     if (n <= 0 || !dist || !keep) return 0;  // the reference dereferences end() on an empty list (UB)
     int mn = INT_MAX;
     for (int i = 0; i < n; i++) mn = std::min(mn, dist[i]);
-    const long long lim = std::max(2LL * mn, (long long)threshold);
+    // the reference's int arithmetic: 2 * INT_MAX (empty train set) wraps to -2, so nothing is kept — the same
+    // answer filter_pairs_kernel gives
+    const int lim = std::max((int)(2u * (unsigned)mn), threshold);
     int kept = 0;
     for (int i = 0; i < n; i++) {
         keep[i] = dist[i] < lim ? 1 : 0;
@@ -1098,6 +1108,21 @@ int yavo_submit_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows
         if (int r = ensure_pyramid_alloc(ctx)) return r;
         if (int r = ensure_track_buffers(ctx)) return r;
     }
+    if (ctx->raw_C != C || ctx->raw_C * fbytes == 0) {
+        // the staging halves move when the stage size changes: a new half can cover BOTH halves of the previous
+        // submit, so the first copy waits until both have been re-pitched (not only the one with the same index)
+        for (int b = 0; b < 2; b++)
+            if (ctx->raw_used[b]) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_repitched[b], 0));
+    }
+    ctx->raw_C = C;
+    // per-ticket status word: what the kernels of THIS batch flag (candidate overflow, select watchdog)
+    const int ticket = (int)(ctx->n_tickets++ % 16);
+    ctx->cur_status = ctx->d_status + ticket;
+    CK(cudaMemsetAsync(ctx->cur_status, 0, sizeof(int), ctx->stream));
+    struct StatusScope {
+        yavo_ctx *c;
+        ~StatusScope() { c->cur_status = c->d_status + STATUS_GENERAL; }
+    } status_scope{ctx};
     for (int c = 0; c < nchunks; c++) {
         const int buf = c & 1, s0 = c * C, nc = std::min(C, n - s0);
         uint8_t *raw = ctx->d_raw + (size_t)buf * C * fbytes;
@@ -1140,8 +1165,9 @@ int yavo_submit_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows
         CK(cudaEventRecord(ctx->ev_fetched[c], ctx->s_d2h));
         ctx->fetched_valid[c] = 1;
     }
-    // ticket: an event after the last D2H copy of this batch
-    const int ticket = (int)(ctx->n_tickets++ % 16);
+    // ticket: an event after the last D2H copy of this batch; the batch's status word travels with it
+    CK(cudaMemcpyAsync(ctx->h_small + 32 + ticket, ctx->d_status + ticket, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    ctx->ticket_pending[ticket] = 1;
     if (!ctx->ev_ticket[ticket]) CK(cudaEventCreateWithFlags(&ctx->ev_ticket[ticket], cudaEventDisableTiming | cudaEventBlockingSync));
     CK(cudaEventRecord(ctx->ev_ticket[ticket], ctx->s_d2h));
     return ticket;
@@ -1151,7 +1177,9 @@ int yavo_wait_batch(yavo_ctx *ctx, int ticket) {
     if (!ctx || ticket < 0 || ticket >= 16 || !ctx->ev_ticket[ticket]) return YAVO_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->ev_ticket[ticket]));
-    return 0;
+    if (!ctx->ticket_pending[ticket]) return 0;
+    ctx->ticket_pending[ticket] = 0;
+    return status_error(ctx, ctx->h_small[32 + ticket]);  // overflow / watchdog of THIS batch
 }
 
 int yavo_wait(yavo_ctx *ctx) {
@@ -1161,7 +1189,14 @@ int yavo_wait(yavo_ctx *ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->s_d2h) CK(cudaStreamSynchronize(ctx->s_d2h));
     for (size_t c = 0; c < ctx->fetched_valid.size(); c++) ctx->fetched_valid[c] = 0;
-    return check_status(ctx);
+    int st = 0;  // batches nobody called yavo_wait_batch for
+    for (int t = 0; t < 16; t++)
+        if (ctx->ticket_pending[t]) {
+            ctx->ticket_pending[t] = 0;
+            if (ctx->h_small[32 + t] != 0 && st == 0) st = ctx->h_small[32 + t];
+        }
+    if (int r = check_status(ctx)) return r;
+    return status_error(ctx, st);
 }
 
 int yavo_process_host_batch(yavo_ctx *ctx, const uint8_t *pixels, int n, int rows, int cols, int do_match,

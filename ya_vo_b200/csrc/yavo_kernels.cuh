@@ -1207,11 +1207,11 @@ filter_pairs_kernel(const int32_t *__restrict__ midx, const int32_t *__restrict_
         s_min = m;
     }
     __syncthreads();
-    const long long lim = max(2LL * s_min, (long long)threshold);
+    const int lim = max((int)(2u * (unsigned)s_min), threshold);  // int arithmetic of the reference: 2 * INT_MAX wraps to -2
     int run = 0;
     for (int base = 0; base < nq; base += K6_THREADS) {
         const int i = base + tid;
-        const bool keep = i < nq && nt > 0 && (long long)md[i] < lim;
+        const bool keep = i < nq && nt > 0 && md[i] < lim;
         const unsigned b = __ballot_sync(0xffffffffu, keep);
         __syncthreads();
         if (lane == 0) red[warp] = __popc(b);

@@ -33,6 +33,9 @@ def process_shard(ctx, load_frames, n_frames, rank, world, batch, do_match=True)
     load_frames(a, b) -> uint8 array [b-a, H, W] (pinned or pageable host memory).
     Returns a dict of per-frame results for frames [lo, hi): n_kp, rows, cols, scores, desc and, for f > 0,
     match_idx / match_dist of the pair (f-1, f)."""
+    if batch < 2:
+        # each batch re-loads the previous batch's last frame (the seam): a 1-frame batch would never advance
+        raise ValueError("process_shard needs batch >= 2 (got %d)" % batch)
     first, lo, hi = shard_plan(n_frames, world)[rank]
     K = ctx.max_kp
     n_own = hi - lo

@@ -42,6 +42,9 @@ class FrameStream:
     last frame of the previous batch (the seam frame)."""
 
     def __init__(self, n_frames, read, batch, shape, prefetch=2, buffers=None):
+        if batch < 2:
+            # every batch after the first re-uses one frame as its seam: a 1-frame batch would never advance
+            raise ValueError("FrameStream needs batch >= 2 (got %d)" % batch)
         self.n, self.read, self.batch, self.shape = n_frames, read, batch, shape
         self.buffers = buffers or [np.empty((batch,) + tuple(shape), np.uint8) for _ in range(prefetch + 2)]
         self._q = queue.Queue(maxsize=prefetch)
