@@ -12,7 +12,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_CSRC, "libyavo_b200.so")
+# YAVO_LIB_PATH: tuning experiments only (A/B runs of differently built libraries in one GPU session)
+LIB_PATH = os.environ.get("YAVO_LIB_PATH") or os.path.join(_CSRC, "libyavo_b200.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "yavo_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -40,6 +41,8 @@ def _sources():
 
 def build(force=False, verbose=False):
     """Compile the CUDA library for sm_100a (cross-compiles without a GPU)."""
+    if os.environ.get("YAVO_LIB_PATH"):
+        return LIB_PATH  # an explicitly chosen build is used as it is
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in _sources())
     if not (force or stale):
         return LIB_PATH

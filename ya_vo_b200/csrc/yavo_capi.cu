@@ -28,15 +28,17 @@ struct yavo_ctx {
     int n_slots = 0, max_rows = 0, max_cols = 0, max_kp = 0, max_cand = 0;
     int pitch = 0;       // device row pitch in bytes (multiple of 128)
     int rows_alloc = 0;  // rows per slot
-    int mask_words = 0;  // pitch / 32
+    int seg_cols = 0;    // tile columns per row of the segment table (pitch / TW)
     size_t frame_stride = 0;
     std::vector<int> slot_rows, slot_cols;
     std::vector<char> slot_blur_valid;  // blurred plane of the slot is current
     // device buffers (per slot)
     uint8_t *d_frames = nullptr, *d_blur = nullptr;
-    uint32_t *d_mask = nullptr;
-    int *d_rowcnt = nullptr;
-    yavo_ent *d_cand = nullptr;
+    CUtensorMap frames_map;  // d_frames as a 3-D tensor (byte in row, row, slot): K1 stages a tile with one tensor copy
+    CUtensorMap blur_map;    // d_blur likewise, box = the 32 x 17 byte patch the BRIEF kernel stages per keypoint
+    yavo_ent *d_pool = nullptr;  // per slot max_cand scored corners in tile order (written by K1)
+    uint32_t *d_seg = nullptr;   // per slot rows_alloc x seg_cols: pool offset << 8 | count of each (row, tile column)
+    yavo_ent *d_cand = nullptr;  // per slot max_cand: the select kernel's sort buffer when the list exceeds its shared memory
     int *d_ncand = nullptr;
     uint32_t *d_scratch = nullptr;
     int32_t *d_kp_row = nullptr, *d_kp_col = nullptr;
@@ -176,6 +178,27 @@ cudaError_t dalloc(T **p, size_t n) {
     return cudaMalloc(reinterpret_cast<void **>(p), std::max<size_t>(n, 1) * sizeof(T));
 }
 
+// CUtensorMap of the frame slots: u8 [n_slots][rows_alloc][pitch], box = one staged tile (SROW x SH bytes of one slot).
+// cuTensorMapEncodeTiled is fetched from the driver at run time, so the library does not link libcuda.
+int encode_slot_map(yavo_ctx *ctx, CUtensorMap *map, void *base, int box_w, int box_h) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, YAVO_ERR_CUDA, "the driver does not export cuTensorMapEncodeTiled");
+    const cuuint64_t gdim[3] = {(cuuint64_t)ctx->pitch, (cuuint64_t)ctx->rows_alloc, (cuuint64_t)ctx->n_slots};
+    const cuuint64_t gstride[2] = {(cuuint64_t)ctx->pitch, (cuuint64_t)ctx->frame_stride};  // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = reinterpret_cast<encode_fn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, base, gdim, gstride, box,
+                                                       estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, YAVO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    return 0;
+}
+
 size_t select_smem_bytes() { return ((sizeof(SelShared) + 15) & ~size_t(15)) + sizeof(yavo_ent) * SEL_SMEM_ENTS; }
 
 int ensure_stage(yavo_ctx *ctx, size_t bytes) {
@@ -262,55 +285,40 @@ int check_uploaded(yavo_ctx *ctx, int slot0, int n) {
     return 0;
 }
 
-// K1 (+K2) over slots [slot0, slot0+n)
-int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur, bool score = false) {
+// K1 over slots [slot0, slot0+n): corners scored and left in the slots' pools + segment tables, blurred planes
+int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t fs = ctx->frame_stride;
     const uint8_t *frames = ctx->d_frames + fs * slot0;
     uint8_t *blur = ctx->d_blur + fs * slot0;
-    uint32_t *mask = ctx->d_mask + (size_t)slot0 * ctx->rows_alloc * ctx->mask_words;
-    int *rowcnt = ctx->d_rowcnt + (size_t)slot0 * ctx->rows_alloc;
+    yavo_ent *pool = ctx->d_pool + (size_t)slot0 * ctx->max_cand;
+    uint32_t *seg = ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols;
+    int *ncand = ctx->d_ncand + slot0;
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
-    if (do_fast) CK(cudaMemsetAsync(rowcnt, 0, sizeof(int) * (size_t)n * ctx->rows_alloc, ctx->stream));
+    if (do_fast) CK(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)n, ctx->stream));
     if (do_fast && do_blur)
         PROF(KC_DETECT, detect_blur_kernel<true, true><<<grid, K1_THREADS, 0, ctx->stream>>>(
-            frames, fs, ctx->pitch, H, W, blur, mask, ctx->mask_words, rowcnt, ctx->rows_alloc));
+            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
     else if (do_fast)
         PROF(KC_DETECT, detect_blur_kernel<true, false><<<grid, K1_THREADS, 0, ctx->stream>>>(
-            frames, fs, ctx->pitch, H, W, blur, mask, ctx->mask_words, rowcnt, ctx->rows_alloc));
+            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
     else
         PROF(KC_DETECT, detect_blur_kernel<false, true><<<grid, K1_THREADS, 0, ctx->stream>>>(
-            frames, fs, ctx->pitch, H, W, blur, mask, ctx->mask_words, rowcnt, ctx->rows_alloc));
+            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
     CK_LAUNCH();
     if (do_blur)
         for (int s = slot0; s < slot0 + n; s++) ctx->slot_blur_valid[s] = 1;
-    if (do_fast) {
-        dim3 g2((H + K2_ROWS - 1) / K2_ROWS, n);
-        // the candidate list in scan order; scores are filled in by the select kernel unless asked for here
-        if (score)
-            PROF(KC_COMPACT, compact_score_kernel<true><<<g2, K2_THREADS, 0, ctx->stream>>>(
-                frames, fs, ctx->pitch, H, W, mask, ctx->mask_words, rowcnt, ctx->rows_alloc,
-                ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0));
-        else
-            PROF(KC_COMPACT, compact_score_kernel<false><<<g2, K2_THREADS, 0, ctx->stream>>>(
-                frames, fs, ctx->pitch, H, W, mask, ctx->mask_words, rowcnt, ctx->rows_alloc,
-                ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0));
-        CK_LAUNCH();
-    }
     return 0;
 }
 
 // K3 over slots [slot0, slot0+n)
-// K2 scores the candidates itself when only a few frames are in flight (its grid covers every row of every
-// frame); with many frames the select kernel scores while loading, in issue slots it would otherwise idle in
-inline bool score_in_k2(int n) { return n < 16; }
-
 int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t o = (size_t)slot0 * ctx->max_kp;
     PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->stream>>>(
-        ctx->d_frames + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
-        ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp, score_in_k2(n) ? 0 : 1,
+        ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW,
+        ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
+        ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp,
         ctx->d_kp_row + o,
         ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
         ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->cur_status));
@@ -521,11 +529,16 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     c->max_rows = max_rows;
     c->max_cols = max_cols;
     c->max_kp = max_kp;
-    if (max_cand <= 0) max_cand = std::max(1024, (std::max(max_rows - 8, 1) * std::max(max_cols - 8, 1)) / 4);
+    if (max_cand <= 0)
+        max_cand = (int)std::min<long long>(SEG_MAX_OFFSET - 1, std::max(1024LL, ((long long)std::max(max_rows - 8, 1) * std::max(max_cols - 8, 1)) / 4));
+    if (max_cand >= SEG_MAX_OFFSET) {
+        delete c;
+        return fail(nullptr, YAVO_ERR_INVALID, "max_cand %d: the segment table addresses at most %d candidates per frame", max_cand, SEG_MAX_OFFSET - 1);
+    }
     c->max_cand = max_cand;
     c->pitch = ((max_cols + TW - 1) / TW) * TW;
     c->rows_alloc = max_rows;
-    c->mask_words = c->pitch / 32;
+    c->seg_cols = c->pitch / TW;
     c->frame_stride = (size_t)c->pitch * c->rows_alloc;
     c->slot_rows.assign(n_slots, 0);
     c->slot_cols.assign(n_slots, 0);
@@ -544,9 +557,9 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     const size_t S = n_slots;
     CKC(dalloc(&c->d_frames, S * c->frame_stride));
-    CKC(dalloc(&c->d_blur, S * c->frame_stride));
-    CKC(dalloc(&c->d_mask, S * c->rows_alloc * c->mask_words));
-    CKC(dalloc(&c->d_rowcnt, S * c->rows_alloc));
+    CKC(dalloc(&c->d_blur, S * c->frame_stride + 16));  // the BRIEF kernel's word loads may touch the 4 bytes after a row
+    CKC(dalloc(&c->d_pool, S * c->max_cand));
+    CKC(dalloc(&c->d_seg, S * c->rows_alloc * c->seg_cols));
     CKC(dalloc(&c->d_cand, S * c->max_cand));
     CKC(dalloc(&c->d_ncand, S));
     CKC(dalloc(&c->d_scratch, S * (c->max_cand + 4)));
@@ -573,6 +586,11 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_offs, 256));
     CKC(dalloc(&c->d_spos, 256));
     CKC(cudaMemset(c->d_frames, 0, S * c->frame_stride));
+    if (encode_slot_map(c, &c->frames_map, c->d_frames, SROW, SH) != 0 || encode_slot_map(c, &c->blur_map, c->d_blur, BP_ROWB, BP_ROWS) != 0) {
+        g_create_error = c->err;
+        yavo_destroy(c);
+        return YAVO_ERR_CUDA;
+    }
     CKC(cudaMemset(c->d_status, 0, STATUS_WORDS * sizeof(int)));
     CKC(cudaMemset(c->d_nbk, 0, S * sizeof(int)));
     CKC(cudaMemset(c->d_nkp, 0, S * sizeof(int)));
@@ -591,7 +609,7 @@ void yavo_destroy(yavo_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    void *bufs[] = {c->d_frames, c->d_blur,    c->d_mask,    c->d_rowcnt,   c->d_cand,     c->d_ncand,  c->d_scratch,
+    void *bufs[] = {c->d_frames, c->d_blur,    c->d_pool,    c->d_seg,      c->d_cand,     c->d_ncand,  c->d_scratch,
                     c->d_kp_row, c->d_kp_col,  c->d_kp_score, c->d_nkp,     c->d_bk_row,   c->d_bk_col, c->d_bk_score,
                     c->d_bk_id,  c->d_nbk,     c->d_desc,    c->d_midx,     c->d_mdist,    c->d_status, c->d_noob,
                     c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
@@ -710,7 +728,12 @@ int yavo_fast_candidates(yavo_ctx *ctx, int slot, int cap, int32_t *out_rows, in
     if (int r = check_slot(ctx, slot)) return r;
     if (int r = check_uploaded(ctx, slot, 1)) return r;
     CK(cudaSetDevice(ctx->device));
-    if (int r = launch_detect(ctx, slot, 1, true, true, /*score=*/true)) return r;
+    if (int r = launch_detect(ctx, slot, 1, true, true)) return r;
+    PROF(KC_COMPACT, gather_kernel<<<1, K2_THREADS, 0, ctx->stream>>>(
+        ctx->d_seg + (size_t)slot * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, ctx->slot_rows[slot],
+        (ctx->slot_cols[slot] + TW - 1) / TW, ctx->d_pool + (size_t)slot * ctx->max_cand,
+        ctx->d_cand + (size_t)slot * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot));
+    CK_LAUNCH();
     CK(cudaMemcpyAsync(ctx->h_small, ctx->d_ncand + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int n = ctx->h_small[0];
@@ -741,7 +764,7 @@ int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int
     if (max_kp > ctx->max_kp)
         return fail(ctx, YAVO_ERR_CAPACITY, "max_kp %d exceeds the context's %d", max_kp, ctx->max_kp);
     CK(cudaSetDevice(ctx->device));
-    if (int r = launch_detect(ctx, slot, 1, true, true, score_in_k2(1))) return r;
+    if (int r = launch_detect(ctx, slot, 1, true, true)) return r;
     if (int r = launch_select(ctx, slot, 1, max_kp)) return r;
     CK(cudaMemcpyAsync(ctx->h_small + 1, ctx->d_ncand + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->h_small + 2, ctx->d_nkp + slot, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -773,9 +796,9 @@ int yavo_set_brief_offsets(yavo_ctx *ctx, const int32_t *offsets) {
             w |= (uint32_t)(uint8_t)(int8_t)v << (8 * k);
         }
         packed[j] = w;
-        // the same test as byte positions inside the 17 x 20-byte patch the kernel stages per keypoint
-        const int p1 = (offsets[4 * j + 0] + 8) * (BP_WORDS * 4) + offsets[4 * j + 1] + 8;
-        const int p2 = (offsets[4 * j + 2] + 8) * (BP_WORDS * 4) + offsets[4 * j + 3] + 8;
+        // the same test as byte positions inside the 17 x 32-byte patch the kernel stages per keypoint
+        const int p1 = (offsets[4 * j + 0] + 8) * BP_ROWB + offsets[4 * j + 1] + 8;
+        const int p2 = (offsets[4 * j + 2] + 8) * BP_ROWB + offsets[4 * j + 3] + 8;
         spos[j] = (uint32_t)p1 | ((uint32_t)p2 << 16);
     }
     CK(cudaSetDevice(ctx->device));
@@ -837,7 +860,7 @@ int yavo_brief_describe(yavo_ctx *ctx, int slot, const int32_t *rows, const int3
     CK(cudaMemsetAsync(ctx->d_noob, 0, sizeof(int), ctx->stream));
     const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
     dim3 grid((n + kp_per_block - 1) / kp_per_block, 1);
-    PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(ctx->d_blur + ctx->frame_stride * slot, ctx->frame_stride,
+    PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(ctx->blur_map, slot, ctx->d_blur + ctx->frame_stride * slot, ctx->frame_stride,
                                                        ctx->pitch, H, W, ctx->d_offs, ctx->d_spos, ctx->d_pt_row, ctx->d_pt_col,
                                                        nullptr, n, n, ctx->d_pt_desc, ctx->d_pt_valid, ctx->d_noob));
     CK_LAUNCH();
@@ -965,14 +988,14 @@ int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *kee
 // link_prev also matches (slot0-1, slot0), whose query descriptors an earlier call left in place.
 static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool link_prev) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
-    if (int r = launch_detect(ctx, slot0, n, true, true, score_in_k2(n))) return r;
+    if (int r = launch_detect(ctx, slot0, n, true, true)) return r;
     if (int r = launch_select(ctx, slot0, n, ctx->max_kp)) return r;
     const size_t o = (size_t)slot0 * ctx->max_kp;
     {
         const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
         dim3 grid((ctx->max_kp + kp_per_block - 1) / kp_per_block, n);
         PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(
-            ctx->d_blur + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, H, W, ctx->d_offs, ctx->d_spos,
+            ctx->blur_map, slot0, ctx->d_blur + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, H, W, ctx->d_offs, ctx->d_spos,
             ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_nbk + slot0, 0, ctx->max_kp, ctx->d_desc + o * 8, nullptr,
             nullptr));
         CK_LAUNCH();

@@ -3,6 +3,7 @@
 // staged through shared memory; the tensor-core matchers that replace K5 by default live in match_tc4.cuh /
 // match_tc.cuh.  See DESIGN.md for the data layout and the roofline that bounds each kernel.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -31,13 +32,18 @@ __global__ void repitch_kernel(const uint8_t *__restrict__ src, size_t src_pitch
 }
 
 // ================================================================================================
-// K1  detect + blur
+// K1  detect + score + blur
 // One CTA per 128x32 pixel tile of one frame.  The tile plus its halo is staged in shared memory by
 // bulk asynchronous copies (cp.async.bulk, one 160-byte row each, completion on an mbarrier); frame
 // rows are stored with a pitch that is a multiple of 128 so every staged row is 16-byte aligned.
-// Two products come out of the single read of the pixels:
-//   * the FAST segment-test bitmask (1 bit per pixel, one word per 32 pixels) and per-row corner
-//     counts (reference src/FastDetector.cc:298-320); 4 pixels per thread with byte-SIMD
+// Three products come out of the single read of the pixels:
+//   * the FAST corners of the tile (reference src/FastDetector.cc:298-320; 4 pixels per thread with
+//     byte-SIMD), listed in tile row-major order,
+//   * their Harris responses (:244-273) from the 5x5 windows that are already in shared memory —
+//     scored densely, 256 corners per pass of the CTA.  The (response, position) entries go to a
+//     per-frame pool (one atomicAdd per tile reserves the tile's span; pool order is irrelevant) and
+//     a segment table [row][tile column] -> (pool offset, count) lets the select kernel read them
+//     back in the reference's scan order without a corner bitmask or a second pass over the pixels,
 //   * the 9x9 sigma-2.5 fixed-point Gaussian of the tile (reference src/BriefDescriptor.cc:90),
 //     horizontal pass by IDP.4A into 16-bit vertical pairs, vertical pass by IDP.2A
 // ================================================================================================
@@ -51,6 +57,12 @@ constexpr int SROW_W = SROW / 4;         // 40 words
 constexpr int SPX = SLEAD / 4;           // word index of the tile's first pixel inside a staged row
 constexpr int SH = TH + 2 * HALO;        // 40 staged rows
 constexpr int K1_THREADS = 256;
+#ifndef YAVO_K1_MIN_CTAS
+#define YAVO_K1_MIN_CTAS 8  // 32 registers per thread: eight CTAs per SM keep the issue slots of this issue-bound kernel full
+#endif
+constexpr int K1_LIST = 1024;            // corners of a tile listed (and scored densely) per round; a tile with more takes more rounds
+constexpr int SEG_CNT_BITS = 8;          // segment table entry = pool offset << 8 | count (count <= 128 per tile row)
+constexpr int SEG_MAX_OFFSET = 1 << 24;  // pool offsets (and so max_cand) stay below this
 
 // ---- bulk asynchronous copy (TMA engine, cp.async.bulk -> SASS UBLKCP) with an mbarrier for completion ----
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -65,6 +77,14 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_addr(dst)),
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+// one tensor copy (TMA, cp.async.bulk.tensor -> SASS UTMALDG) of a box of a 3-D tensor (x = byte in row, y = row, z = frame slot);
+// coordinates may lie outside the tensor, the out-of-range part of the box is zero-filled
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, int x, int y, int z, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar))
                  : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
@@ -88,13 +108,19 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 }
 
 template <bool DO_FAST, bool DO_BLUR>
-__global__ void __launch_bounds__(K1_THREADS)
-detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
-                   uint8_t *__restrict__ blur, uint32_t *__restrict__ mask, int mask_words,
-                   int *__restrict__ rowcnt, int rows_alloc) {
+__global__ void __launch_bounds__(K1_THREADS, YAVO_K1_MIN_CTAS)
+detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base,
+                   const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
+                   uint8_t *__restrict__ blur, yavo_ent *__restrict__ pool, int max_cand, int *__restrict__ ncand,
+                   uint32_t *__restrict__ seg, int seg_cols, int rows_alloc) {
     __shared__ __align__(128) uint32_t tile[SH][SROW_W];  // staged rows: cols x0-16 .. x0+143
     __shared__ __align__(8) uint64_t tile_bar;
     __shared__ uint4 hpair[SH / 2][TW / 4];        // [row pair][quad] -> 4 x (h[even] | h[odd] << 16)
+    // corners of the tile: per-row bit masks and counts, the row-major corner list, the tile's span in the pool
+    __shared__ uint32_t rmask[TH][TW / 32];
+    __shared__ int rcnt[TH];
+    __shared__ uint16_t clist[DO_FAST ? K1_LIST : 1];
+    __shared__ int s_base, s_total;
 
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
@@ -102,16 +128,23 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     const int tid = threadIdx.x;
 
     // ---- stage tile rows y0-4 .. y0+35 (reflected into the image), cols x0-16 .. x0+143 -------------
-    // One bulk asynchronous copy (TMA engine) per staged row, issued by the lanes of warp 0 and tracked by an
-    // mbarrier: no per-thread address arithmetic or register staging.  Source and destination are 16-byte
-    // aligned because the frame pitch and the tile origin are multiples of 128.
-    {
-        const int src_col = max(x0 - SLEAD, 0);
-        const int dst_off = src_col - (x0 - SLEAD);                    // 16 for the first tile column, else 0
-        const uint32_t row_bytes = (uint32_t)min(SROW - dst_off, pitch - src_col);
+    // Tiles whose 40 staged rows all lie inside the image (every tile row but the first and the last): ONE tensor copy
+    // (TMA) of the 160 x 40 byte box, issued and awaited by thread 0; columns left of the image are zero-filled and not
+    // used (the blur's reflected columns are patched in below).  First / last tile row: one bulk copy per staged row
+    // (reflected row index), issued by the lanes of warp 0.  Either way the other warps park at the CTA barrier
+    // below (a barrier stall issues nothing; a try_wait loop in every warp would take issue slots this issue-bound
+    // kernel needs).
+    if (tid < 32) {
         if (tid == 0) mbar_init(&tile_bar, 1);
-        __syncthreads();
-        if (tid < 32) {
+        if (y0 - HALO >= 0 && y0 + TH + HALO <= H) {  // CTA-uniform
+            if (tid == 0) {
+                mbar_expect_tx(&tile_bar, SROW * SH);
+                tma_load_3d(&tile[0][0], &frames_map, x0 - SLEAD, y0 - HALO, slot_base + f, &tile_bar);
+            }
+        } else {
+            const int src_col = max(x0 - SLEAD, 0);
+            const int dst_off = src_col - (x0 - SLEAD);                    // 16 for the first tile column, else 0
+            const uint32_t row_bytes = (uint32_t)min(SROW - dst_off, pitch - src_col);
             if (tid == 0) mbar_expect_tx(&tile_bar, row_bytes * SH);
             __syncwarp();
             for (int tr = tid; tr < SH; tr += 32) {
@@ -120,9 +153,7 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
                          &tile_bar);
             }
         }
-        // only warp 0 polls the mbarrier; the other warps park at the CTA barrier below (a barrier stall issues
-        // nothing, a try_wait loop in every warp takes issue slots this issue-bound kernel needs)
-        if (tid < 32) mbar_wait(&tile_bar, 0);
+        if (tid == 0) mbar_wait(&tile_bar, 0);
     }
     const bool edge_cols = DO_BLUR && (x0 == 0 || x0 + TW + HALO > W);
     if (edge_cols) {
@@ -193,25 +224,79 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
             fnib[warp][k][q] = (uint8_t)nib;
         }
         __syncwarp();
-        // pass C: lane l < 4*RPW packs the eight nibbles of mask word (row l/4, word l%4) in one go
+        // pass C: lane l < 4*RPW packs the eight nibbles of mask word (row l/4, word l%4) in one go; the words and the
+        // per-row corner counts stay in shared memory
         if (lane < 4 * RPW) {
             const int k = lane >> 2, w = lane & 3;
-            const int gr = y0 + warp + NW * k;
             const uint2 nb = *reinterpret_cast<const uint2 *>(&fnib[warp][k][8 * w]);  // 8 bytes, low nibble used
             // [n0,n1,n2,n3] -> n0 | n1<<4 in byte 0, n2 | n3<<4 in byte 2; then gather the four packed bytes
             const uint32_t lo = (nb.x & 0x000f000fu) | ((nb.x & 0x0f000f00u) >> 4);
             const uint32_t hi = (nb.y & 0x000f000fu) | ((nb.y & 0x0f000f00u) >> 4);
             const uint32_t v = __byte_perm(lo, hi, 0x6420);
             int c = __popc(v);
-            if (gr < H) mask[((size_t)f * rows_alloc + gr) * mask_words + (x0 >> 5) + w] = v;
+            rmask[warp + NW * k][w] = v;
             c += __shfl_xor_sync((1u << (4 * RPW)) - 1u, c, 1);
             c += __shfl_xor_sync((1u << (4 * RPW)) - 1u, c, 2);
-            if (w == 0 && c && gr < H) atomicAdd(&rowcnt[(size_t)f * rows_alloc + gr], c);
+            if (w == 0) rcnt[warp + NW * k] = c;
+        }
+    }
+
+    // Corner list of the tile in row-major order (tile row t, then column): thread j < 128 owns mask word (row j/4,
+    // word j%4) and writes its corners at [start of row + corners in the earlier words of the row].  Entries
+    // [round * K1_LIST, (round+1) * K1_LIST) are kept; every one of the four warps computes the row starts itself.
+    auto build_list = [&](int round, int *total_out, int *row_start_out, int *row_cnt_out) {
+        const int lane = tid & 31;
+        const int c = rcnt[lane];
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        *total_out = __shfl_sync(0xffffffffu, incl, 31);
+        *row_start_out = incl - c;  // of tile row `lane`
+        *row_cnt_out = c;
+        const int t = tid >> 2, w = tid & 3;
+        uint32_t m = rmask[t][w];
+        const int cw = __popc(m);
+        int pre = cw;  // inclusive prefix over the row's four words (lanes 4i .. 4i+3)
+        int u = __shfl_up_sync(0xffffffffu, pre, 1, 4);
+        if (w >= 1) pre += u;
+        u = __shfl_up_sync(0xffffffffu, pre, 2, 4);
+        if (w >= 2) pre += u;
+        int off = __shfl_sync(0xffffffffu, incl - c, t & 31) + pre - cw - round * K1_LIST;
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            if (off >= 0 && off < K1_LIST) clist[off] = (uint16_t)((t << 7) | (w * 32 + b));
+            off++;
+        }
+    };
+
+    if (DO_FAST) {
+        __syncthreads();  // masks, counts (and the horizontal blur pass) are complete
+        if (tid < 128) {
+            int total, row_start, row_cnt;
+            build_list(0, &total, &row_start, &row_cnt);
+            if (tid < 32) {
+                // reserve the tile's span of the frame's pool; publish where each of the tile's rows starts in it
+                int base = 0;
+                if (tid == 0 && total > 0) base = atomicAdd(&ncand[blockIdx.z], total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (tid == 0) {
+                    s_base = base;
+                    s_total = total;
+                }
+                const int gr = y0 + tid;
+                if (gr < H)
+                    seg[((size_t)f * rows_alloc + gr) * seg_cols + blockIdx.x] =
+                        ((uint32_t)(base + row_start) << SEG_CNT_BITS) | (uint32_t)row_cnt;
+            }
         }
     }
 
     if (DO_BLUR) {
-        __syncthreads();
+        if (!DO_FAST) __syncthreads();
         // vertical pass: output row pairs (tile rows 2j, 2j+1) x 32 quads
         for (int i = tid; i < (TH / 2) * (TW / 4); i += K1_THREADS) {
             const int j = i >> 5, q = i & 31;
@@ -249,86 +334,101 @@ detect_blur_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
             }
         }
     }
+
+    if (DO_FAST) {
+        // Harris response of every corner from the staged pixels (reference src/FastDetector.cc:244-273; the 5x5 window
+        // of an interior pixel lies inside the tile + halo), densely: thread i takes corner i of the list
+        __syncthreads();
+        const int total = s_total, base = s_base;
+        const bool fits = base + total <= max_cand;  // otherwise the select kernel reports the overflow (ncand > max_cand)
+        const uint8_t *tb = reinterpret_cast<const uint8_t *>(&tile[0][0]);
+        for (int r0 = 0; r0 < total; r0 += K1_LIST) {
+            if (r0 > 0) {  // more than K1_LIST corners in one tile: list the next K1_LIST (CTA-uniform, rare)
+                __syncthreads();
+                if (tid < 128) {
+                    int a, b, c;
+                    build_list(r0 / K1_LIST, &a, &b, &c);
+                }
+                __syncthreads();
+            }
+            const int n = min(K1_LIST, total - r0);
+            for (int i = tid; i < n; i += K1_THREADS) {
+                const int e = clist[i], t = e >> 7, c = e & 127;
+                const uint8_t *ctr = tb + (t + HALO) * SROW + SLEAD + c;
+                int a, bb, cc;
+                yavo_structure_tensor([&](int dr, int dc) { return (int)ctr[dr * SROW + dc]; }, 0, 0, &a, &bb, &cc);
+                if (fits)
+                    pool[(size_t)f * max_cand + base + r0 + i] =
+                        yavo_make_ent(yavo_harris_from_tensor(a, bb, cc), ((uint32_t)(y0 + t) << 16) | (uint32_t)(x0 + c));
+            }
+        }
+    }
 }
 
 // ================================================================================================
-// K2  compact + score
-// Turns the corner bitmask into the candidate list in scan (row-major) order — the order the
-// reference appends to retCorners (src/FastDetector.cc:298-324) — and computes the Harris response
-// (:244-273) of each candidate from the raw pixels (5x5 window, L2-resident).
-// grid (row slabs, frames); one warp per row.
+// K2  candidate gather (device function + stand-alone kernel)
+// The detect kernel leaves a frame's corners in its pool in no particular tile order; the segment table
+// [row][tile column] -> (pool offset, count) gives the reference's scan order back (row-major over the image,
+// src/FastDetector.cc:298-324): an exclusive scan of the counts over the table in row-major order is each
+// segment's position in the candidate list.  The select kernel calls this while it loads its sort buffer; the
+// stand-alone kernel serves yavo_fast_candidates.  All threads of the CTA take part.
 // ================================================================================================
-constexpr int K2_THREADS = 256;
-constexpr int K2_ROWS = K2_THREADS / 32;
-
-template <bool SCORE>
-__global__ void __launch_bounds__(K2_THREADS)
-compact_score_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
-                     const uint32_t *__restrict__ mask, int mask_words, const int *__restrict__ rowcnt,
-                     int rows_alloc, yavo_ent *__restrict__ cand, int max_cand, int *__restrict__ ncand) {
-    __shared__ int red[K2_THREADS / 32];
-    __shared__ int rowoff[K2_ROWS + 1];
-    const int f = blockIdx.y;
-    const int r0 = blockIdx.x * K2_ROWS;
+template <int NTHREADS>
+__device__ int gather_candidates(const uint32_t *__restrict__ seg_f, int seg_cols, int H, int ntx,
+                                 const yavo_ent *__restrict__ pool_f, yavo_ent *dst, int dst_cap, int *s_wtot /* NTHREADS / 32 ints */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int *rc = rowcnt + (size_t)f * rows_alloc;
-
-    // candidates in rows above this slab
-    int s = 0;
-    for (int r = tid; r < r0; r += K2_THREADS) s += rc[r];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) red[warp] = s;
-    __syncthreads();
-    if (tid == 0) {
-        int base = 0;
-        for (int w = 0; w < K2_THREADS / 32; w++) base += red[w];
-        rowoff[0] = base;
-        for (int k = 0; k < K2_ROWS; k++) {
-            const int r = r0 + k;
-            rowoff[k + 1] = rowoff[k] + (r < H ? rc[r] : 0);
-        }
-        if (blockIdx.x == gridDim.x - 1) ncand[f] = rowoff[K2_ROWS];
-    }
-    __syncthreads();
-
-    const int row = r0 + warp;
-    if (row >= H) return;
-    int pos = rowoff[warp];
-    if (rowoff[warp + 1] == pos) return;  // empty row
-    const uint8_t *img = frames + (size_t)f * frame_stride;
-    const uint32_t *mrow = mask + ((size_t)f * rows_alloc + row) * mask_words;
-    const int nwords = (W + 31) >> 5;
-    for (int w0 = 0; w0 < nwords; w0 += 32) {
-        const int wi = w0 + lane;
-        uint32_t m = (wi < nwords) ? mrow[wi] : 0u;
-        const int c = __popc(m);
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        int p = pos + incl - c;
-        pos += __shfl_sync(0xffffffffu, incl, 31);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            const int col = wi * 32 + b;
-            if (p < max_cand) {
-                float score = 0.f;  // !SCORE: positions only, the select kernel scores while it loads
-                if (SCORE) {
-                    int a, bb, cc;
-                    yavo_structure_tensor(
-                        [&](int r, int cidx) { return (int)__ldg(img + (size_t)r * pitch + cidx); }, row, col, &a,
-                        &bb, &cc);
-                    score = yavo_harris_from_tensor(a, bb, cc);
-                }
-                cand[(size_t)f * max_cand + p] = yavo_make_ent(score, ((uint32_t)row << 16) | (uint32_t)col);
-            }
-            p++;
+    const int S = H * ntx, per = (S + NTHREADS - 1) / NTHREADS;
+    const int e0 = min(S, tid * per), e1 = min(S, e0 + per);
+    int mine = 0;
+    {
+        int row = e0 / ntx, tx = e0 - row * ntx;
+        for (int e = e0; e < e1; e++) {
+            mine += (int)(seg_f[(size_t)row * seg_cols + tx] & ((1u << SEG_CNT_BITS) - 1u));
+            if (++tx == ntx) { tx = 0; row++; }
         }
     }
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    int pre = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < NTHREADS / 32; w++) {
+        const int t = s_wtot[w];
+        if (w < warp) pre += t;
+        total += t;
+    }
+    if (total <= dst_cap) {
+        int o = pre + incl - mine;
+        int row = e0 / ntx, tx = e0 - row * ntx;
+        for (int e = e0; e < e1; e++) {
+            const uint32_t sg = seg_f[(size_t)row * seg_cols + tx];
+            const int cnt = (int)(sg & ((1u << SEG_CNT_BITS) - 1u));
+            const yavo_ent *src = pool_f + (sg >> SEG_CNT_BITS);
+            for (int k = 0; k < cnt; k++) dst[o + k] = src[k];
+            o += cnt;
+            if (++tx == ntx) { tx = 0; row++; }
+        }
+    }
+    __syncthreads();
+    return total;
+}
+
+constexpr int K2_THREADS = 512;
+
+// one CTA per frame: cand[f][0 .. ncand) = the frame's candidates in scan order
+__global__ void __launch_bounds__(K2_THREADS)
+gather_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, int H, int ntx,
+              const yavo_ent *__restrict__ pool, yavo_ent *__restrict__ cand, int max_cand, const int *__restrict__ ncand) {
+    __shared__ int wtot[K2_THREADS / 32];
+    const int f = blockIdx.x;
+    if (ncand[f] > max_cand) return;  // overflowed pool: the caller reports it
+    gather_candidates<K2_THREADS>(seg + (size_t)f * rows_alloc * seg_cols, seg_cols, H, ntx, pool + (size_t)f * max_cand,
+                                  cand + (size_t)f * max_cand, max_cand, wtot);
 }
 
 // ================================================================================================
@@ -729,9 +829,9 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
 }
 
 __global__ void __launch_bounds__(SEL_THREADS, YAVO_SEL_MIN_CTAS)
-select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int pitch,
-                   yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
-                   uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride, int score_on_load,
+select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, int ntx,
+                   const yavo_ent *__restrict__ pool, yavo_ent *__restrict__ cand_all, int max_cand,
+                   const int *__restrict__ ncand, uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
                    int32_t *__restrict__ kp_row, int32_t *__restrict__ kp_col, float *__restrict__ kp_score,
                    int *__restrict__ nkp,
                    // compacted (checkBoundry-admitted) list that BRIEF / the matcher consume
@@ -763,26 +863,13 @@ select_topk_kernel(const uint8_t *__restrict__ frames, size_t frame_stride, int 
     if (tid == 0) { S.nbig[0] = S.nbig[1] = 0; S.q_head = S.q_tail = 0; S.pending = 0; S.watchdog = 0; }
     __syncthreads();
 
-    // load the candidate list (positions in scan order) and score it on the way in: Harris response from
-    // the 5x5 pixel window (reference src/FastDetector.cc:244-273); this kernel is latency-bound, so the
-    // arithmetic rides in otherwise idle issue slots
+    // load the candidate list in scan order: the detect kernel scored the corners and left them in the frame's pool;
+    // the segment table puts them back in the order the reference appends retCorners (src/FastDetector.cc:298-324)
     const bool in_smem_at_start = N <= SEL_SMEM_ENTS;
     yavo_ent *A = in_smem_at_start ? sbuf : G;
     bool in_smem = in_smem_at_start;
-    if (!score_on_load) {  // the list arrives scored (few frames in flight: K2 spreads the scoring over more SMs)
-        if (in_smem)
-            for (int i = tid; i < N; i += SEL_THREADS) sbuf[i] = G[i];
-    } else {
-        const uint8_t *img = frames + (size_t)f * frame_stride;
-        for (int i = tid; i < N; i += SEL_THREADS) {
-            const uint32_t rc = (uint32_t)G[i];
-            const int row = (int)(rc >> 16), col = (int)(rc & 0xffffu);
-            int a, bb, cc;
-            yavo_structure_tensor([&](int r, int cidx) { return (int)__ldg(img + (size_t)r * pitch + cidx); }, row, col,
-                                  &a, &bb, &cc);
-            A[i] = yavo_make_ent(yavo_harris_from_tensor(a, bb, cc), rc);
-        }
-    }
+    gather_candidates<SEL_THREADS>(seg + (size_t)f * rows_alloc * seg_cols, seg_cols, H, ntx, pool + (size_t)f * max_cand, A,
+                                   in_smem ? SEL_SMEM_ENTS : max_cand, S.wtot);
     if (tid == 0 && N > 1) {
         const SelRange r0 = {0, N, 2 * (31 - __clz(N))};
         if (N > SEL_WARP_MAX) S.big[0][S.nbig[0]++] = r0;
@@ -940,68 +1027,101 @@ __device__ __forceinline__ int brief_sample(const uint8_t *S, int pitch, int H, 
 }
 
 // offsets packed one test per word: byte0 = drow1, byte1 = dcol1, byte2 = drow2, byte3 = dcol2 (int8);
-// spos: the same tests as byte positions inside a staged 17 x 20 patch (lo16 = first sample, hi16 = second),
+// spos: the same tests as byte positions inside a staged 17 x 32-byte patch (lo16 = first sample, hi16 = second),
 // both tables prepared by the host when the offset table is set.
-constexpr int BP_WORDS = 5;              // words per staged patch row: 17 columns + alignment phase <= 20 bytes
+constexpr int BP_ROWB = 48;              // bytes per staged patch row: the tensor copy starts at a 16-byte aligned column (measured on
+                                         // B200, tools/microbench/tma_probe.cu: any other innermost coordinate raises "illegal
+                                         // instruction"), so the 17 columns col-8 .. col+8 start 0..15 bytes into the row
 constexpr int BP_ROWS = 17;              // rows row-8 .. row+8
-constexpr int BP_KPW = 4;                // keypoints per warp (amortises the per-warp set-up)
+constexpr int BP_BYTES = BP_ROWS * BP_ROWB;                  // 816 bytes arrive per patch
+constexpr int BP_ENTRY = (BP_BYTES + 127) & ~127;            // ring entries are 128-byte aligned (tensor-copy destination)
+constexpr int BP_KPW = 8;                // keypoints per warp
+constexpr int BP_D = 4;                  // patches in flight per warp (ring of tensor copies)
 
+// The patch of an interior keypoint arrives by ONE tensor copy (TMA: box of 48 x 17 bytes at ((col-8) & ~15, row-8) of
+// the blurred plane), tracked by an mbarrier per ring entry: no per-lane gather loads, and a warp keeps BP_D patches
+// in flight.  The keypoint's phase (col-8) & 15 is warp-uniform (built from ballots, so it lives in a uniform
+// register) and is added to the lane's fixed sample addresses.  What bounds the kernel is then the shared-memory sampling
+// itself (16 byte loads per lane and keypoint at table-defined, i.e. random, bank positions).
 __global__ void __launch_bounds__(K4_THREADS)
-brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, int H, int W,
+brief_kernel(const __grid_constant__ CUtensorMap blur_map, int slot_base,
+             const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, int H, int W,
              const uint32_t *__restrict__ offs, const uint32_t *__restrict__ spos, const int32_t *__restrict__ rows,
              const int32_t *__restrict__ cols, const int *__restrict__ n_per_frame, int n_fixed,
              int kp_stride, uint32_t *__restrict__ desc, uint8_t *__restrict__ valid,
              int *__restrict__ n_oob) {
-    __shared__ uint32_t patch[K4_THREADS / 32][BP_ROWS * BP_WORDS];
+    __shared__ __align__(128) uint8_t patch[K4_THREADS / 32][BP_D][BP_ENTRY];
+    __shared__ __align__(8) uint64_t pbar[K4_THREADS / 32][BP_D];
     const int f = blockIdx.y;
     const int n = n_per_frame ? n_per_frame[f] : n_fixed;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int kp0 = (blockIdx.x * (K4_THREADS / 32) + warp) * BP_KPW;
     if (kp0 >= n) return;
-    // this lane's eight tests (j = 32 w + lane), the same for every keypoint
-    uint32_t ps[8];
+    const int nk = min(BP_KPW, n - kp0);
+    if (lane < BP_D) mbar_init(&pbar[warp][lane], 1);
+    // this lane's eight tests (j = 32 w + lane) as shared-memory byte addresses inside ring entry 0 of this warp
+    uint32_t sa[8], sb[8];
+    {
+        const uint32_t pbase = smem_addr(&patch[warp][0][0]);
 #pragma unroll
-    for (int w = 0; w < 8; w++) ps[w] = __ldg(spos + 32 * w + lane);
-    // this lane's three patch words (idx = lane + 32 k -> patch row r, word w)
-    int pr[3], pw[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        const int idx = lane + 32 * k;
-        pr[k] = idx / BP_WORDS;
-        pw[k] = idx - pr[k] * BP_WORDS;
-    }
-    const uint8_t *S = blur + (size_t)f * frame_stride;
-    uint32_t *P = patch[warp];
-    bool oob = false;
-    for (int kp = kp0; kp < min(kp0 + BP_KPW, n); kp++) {
-        const int row = rows[(size_t)f * kp_stride + kp], col = cols[(size_t)f * kp_stride + kp];
-        uint32_t *d = desc + ((size_t)f * kp_stride + kp) * 8;
-        const bool ok = brief_admits(row, col, H, W);
-        if (valid && lane == 0) valid[(size_t)f * kp_stride + kp] = ok ? 1 : 0;
-        if (!ok) {
-            if (lane < 8) d[lane] = 0u;
-            continue;
+        for (int w = 0; w < 8; w++) {
+            const uint32_t ps = __ldg(spos + 32 * w + lane);
+            sa[w] = pbase + (ps & 0xffffu);
+            sb[w] = pbase + (ps >> 16);
         }
-        uint32_t mine = 0;
-        if (row + 8 < H && col + 8 < W) {
-            // interior keypoint (warp-uniform): no sample can wrap or leave the buffer.  Stage the 17 x 17
-            // neighbourhood with aligned word loads (85 words, 3 rounds), then sample bytes from shared memory:
-            // 512 scattered single-byte global loads per keypoint become ~17 cache lines.
-            const int c0 = (col - 8) & ~3, phase = (col - 8) & 3;
-            const uint32_t *src = reinterpret_cast<const uint32_t *>(S + (size_t)(row - 8) * pitch + c0);
-            const int pitch_w = pitch >> 2;
-            __syncwarp();  // the previous keypoint's samples are done with the patch
+    }
+    // coordinates of this warp's keypoints (lanes 0..nk-1 load, shuffles broadcast)
+    int my_row = 0, my_col = 0;
+    if (lane < nk) {
+        my_row = rows[(size_t)f * kp_stride + kp0 + lane];
+        my_col = cols[(size_t)f * kp_stride + kp0 + lane];
+    }
+    // admitted by checkBoundry / interior (no sample can wrap to the next row or leave the buffer): bit i = keypoint i
+    const unsigned adm = __ballot_sync(0xffffffffu, lane < nk && brief_admits(my_row, my_col, H, W));
+    const unsigned inter = __ballot_sync(0xffffffffu, lane < nk && my_row + 8 < H && my_col + 8 < W) & adm;
+    // phase bits of every keypoint as ballots: bit i of phb[b] = bit b of (col_i - 8) & 15
+    unsigned phb[4];
 #pragma unroll
-            for (int k = 0; k < 3; k++)
-                if (lane + 32 * k < BP_ROWS * BP_WORDS) P[lane + 32 * k] = __ldg(src + pr[k] * pitch_w + pw[k]);
+    for (int b = 0; b < 4; b++) phb[b] = __ballot_sync(0xffffffffu, ((my_col - 8) >> b) & 1);
+    __syncwarp();  // barriers initialised
+    auto issue = [&](int i) {  // lane i issues the copy of keypoint i's patch
+        if (lane == i && ((inter >> i) & 1u)) {
+            uint64_t *bar = &pbar[warp][i % BP_D];
+            mbar_expect_tx(bar, BP_BYTES);
+            tma_load_3d(&patch[warp][i % BP_D][0], &blur_map, (my_col - 8) & ~15, my_row - 8, slot_base + f, bar);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < BP_D; i++) issue(i);
+    const uint8_t *S = blur + (size_t)f * frame_stride;
+    bool oob = false;
+#pragma unroll
+    for (int i = 0; i < BP_KPW; i++) {
+        if (i >= nk) break;
+        const int kp = kp0 + i;
+        uint32_t *d = desc + ((size_t)f * kp_stride + kp) * 8;
+        const bool ok = (adm >> i) & 1u;
+        if (valid && lane == 0) valid[(size_t)f * kp_stride + kp] = ok ? 1 : 0;
+        uint32_t mine = 0;
+        if ((inter >> i) & 1u) {
+            // parity of the entry's barrier = earlier copies into the same entry (keypoints i-BP_D, i-2*BP_D, ... that took this path)
+            constexpr uint32_t same_entry = 0x11111111u;  // BP_D == 4
+            static_assert(BP_D == 4, "same_entry mask");
+            const uint32_t par = __popc(inter & (same_entry << (i % BP_D)) & ((1u << i) - 1u)) & 1u;
+            if (lane == 0) mbar_wait(&pbar[warp][i % BP_D], par);
             __syncwarp();
-            const uint8_t *Pb = reinterpret_cast<const uint8_t *>(P) + phase;
+            const uint32_t so = (uint32_t)((i % BP_D) * BP_ENTRY) +  // compile-time after unrolling: an immediate offset
+                                (((phb[0] >> i) & 1u) | (((phb[1] >> i) & 1u) << 1) | (((phb[2] >> i) & 1u) << 2) | (((phb[3] >> i) & 1u) << 3));
 #pragma unroll
             for (int w = 0; w < 8; w++) {
-                const unsigned word = __ballot_sync(0xffffffffu, Pb[ps[w] & 0xffff] > Pb[ps[w] >> 16]);
+                uint32_t va, vb;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(va) : "r"(sa[w] + so) : "memory");
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(vb) : "r"(sb[w] + so) : "memory");
+                const unsigned word = __ballot_sync(0xffffffffu, va > vb);  // consumes the samples of every lane
                 if (lane == w) mine = word;
             }
-        } else {
+        } else if (ok) {
+            const int row = __shfl_sync(0xffffffffu, my_row, i), col = __shfl_sync(0xffffffffu, my_col, i);
 #pragma unroll
             for (int w = 0; w < 8; w++) {
                 const uint32_t o = __ldg(offs + 32 * w + lane);
@@ -1018,7 +1138,9 @@ brief_kernel(const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, i
                 oob = false;
             }
         }
-        if (lane < 8) d[lane] = mine;
+        if (lane < 8) d[lane] = mine;  // not admitted: zeros
+        // every lane's samples of this ring entry have been used (the ballots consumed them): it may be overwritten
+        if (i + BP_D < BP_KPW) issue(i + BP_D);
     }
 }
 
