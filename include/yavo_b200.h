@@ -169,6 +169,12 @@ int yavo_filter_pairs(yavo_ctx *ctx, int slot0, int n, int threshold, int32_t *n
 /* frames per copy/compute pipeline stage of the host-batch entry points (0 = automatic, the default:
  * a quarter of the batch, clamped to 16..128 frames) */
 int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames);
+/* overlapped feature pipeline of the batch entry points: chunks of `chunk_frames` frames rotate over `n_streams`
+ * (2..4) internal streams so that the detect kernel of one chunk runs beside the select / BRIEF kernels of the previous
+ * ones; chunk_frames = 0 or n_streams = 1 runs the kernels of a batch back to back on one stream (the default: on
+ * B200 the overlap measured within 1 % of the serial order, profiles/r2_overlap_sweep.md).
+ * Results do not depend on the setting. */
+int yavo_set_overlap(yavo_ctx *ctx, int chunk_frames, int n_streams);
 /* frames per set of kernel launches inside yavo_frontend_batch (0 = the whole batch at once, the default) */
 
 int yavo_set_sub_batch(yavo_ctx *ctx, int frames);

@@ -27,7 +27,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
-    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free", "yavo_set_matcher",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free", "yavo_set_matcher", "yavo_set_overlap",
 ]
 
 
@@ -266,6 +266,10 @@ class Context:
         """'tc' / 0 = tensor-core matcher on packed 4-bit operands (default), 'tc8' / 2 = on FP8 operands,
         'popc' / 1 = integer-pipe matcher; identical results."""
         self._ck(self._L.yavo_set_matcher(self._h, {"tc": 0, "popc": 1, "tc8": 2}.get(kind, kind)))
+
+    def set_overlap(self, chunk_frames, n_streams=3):
+        """Overlapped feature pipeline of the batch entry points (include/yavo_b200.h: yavo_set_overlap); 0 = serial."""
+        self._ck(self._L.yavo_set_overlap(self._h, int(chunk_frames), int(n_streams)))
 
     def set_sub_batch(self, frames):
         self._ck(self._L.yavo_set_sub_batch(self._h, int(frames)))

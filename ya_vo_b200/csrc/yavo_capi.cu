@@ -25,6 +25,13 @@ thread_local std::string g_create_error;
 struct yavo_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t ls = nullptr;  // stream the feature-kernel launch helpers use: `stream`, or one of `aux` inside the overlapped batch path
+    // overlapped feature pipeline (yavo_set_overlap): chunks of a batch rotate over the auxiliary streams so that the
+    // issue-bound detect kernel of chunk i+1 runs beside the latency-bound select / BRIEF kernels of chunk i
+    enum { MAX_AUX = 4 };
+    cudaStream_t aux[MAX_AUX] = {};
+    cudaEvent_t ev_fork = nullptr, ev_k1[MAX_AUX] = {}, ev_join[MAX_AUX] = {};
+    int ov_chunk = 0, ov_streams = 3;    // frames per chunk (0 = no overlap, the default: measured no gain on B200), streams in rotation
     int n_slots = 0, max_rows = 0, max_cols = 0, max_kp = 0, max_cand = 0;
     int pitch = 0;       // device row pitch in bytes (multiple of 128)
     int rows_alloc = 0;  // rows per slot
@@ -159,9 +166,9 @@ int fail(yavo_ctx *c, int code, const char *fmt, ...) {
     do {                                                                  \
         cudaEvent_t e0_ = nullptr, e1_ = nullptr;                         \
         if (ctx->profiling) prof_events(ctx, cls, &e0_, &e1_);            \
-        if (e0_) cudaEventRecord(e0_, ctx->stream);                       \
+        if (e0_) cudaEventRecord(e0_, ctx->ls);                           \
         __VA_ARGS__;                                                      \
-        if (e1_) cudaEventRecord(e1_, ctx->stream);                       \
+        if (e1_) cudaEventRecord(e1_, ctx->ls);                           \
     } while (0)
 
 #define CK_LAUNCH()                                                                                          \
@@ -295,15 +302,15 @@ int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
     uint32_t *seg = ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols;
     int *ncand = ctx->d_ncand + slot0;
     dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, n);
-    if (do_fast) CK(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)n, ctx->stream));
+    if (do_fast) CK(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)n, ctx->ls));
     if (do_fast && do_blur)
-        PROF(KC_DETECT, detect_blur_kernel<true, true><<<grid, K1_THREADS, 0, ctx->stream>>>(
+        PROF(KC_DETECT, detect_blur_kernel<true, true><<<grid, K1_THREADS, 0, ctx->ls>>>(
             ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
     else if (do_fast)
-        PROF(KC_DETECT, detect_blur_kernel<true, false><<<grid, K1_THREADS, 0, ctx->stream>>>(
+        PROF(KC_DETECT, detect_blur_kernel<true, false><<<grid, K1_THREADS, 0, ctx->ls>>>(
             ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
     else
-        PROF(KC_DETECT, detect_blur_kernel<false, true><<<grid, K1_THREADS, 0, ctx->stream>>>(
+        PROF(KC_DETECT, detect_blur_kernel<false, true><<<grid, K1_THREADS, 0, ctx->ls>>>(
             ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
     CK_LAUNCH();
     if (do_blur)
@@ -315,7 +322,7 @@ int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
 int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t o = (size_t)slot0 * ctx->max_kp;
-    PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->stream>>>(
+    PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->ls>>>(
         ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW,
         ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
         ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp,
@@ -555,6 +562,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
         }                                                                                              \
     } while (0)
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->ls = c->stream;
     const size_t S = n_slots;
     CKC(dalloc(&c->d_frames, S * c->frame_stride));
     CKC(dalloc(&c->d_blur, S * c->frame_stride + 16));  // the BRIEF kernel's word loads may touch the 4 bytes after a row
@@ -630,6 +638,12 @@ void yavo_destroy(yavo_ctx *c) {
         if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
         if (c->ev_repitched[i]) cudaEventDestroy(c->ev_repitched[i]);
     }
+    for (int i = 0; i < yavo_ctx::MAX_AUX; i++) {
+        if (c->aux[i]) cudaStreamDestroy(c->aux[i]);
+        if (c->ev_k1[i]) cudaEventDestroy(c->ev_k1[i]);
+        if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -986,19 +1000,59 @@ int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *kee
 
 // detect -> select -> describe on slots [slot0, slot0+n); match pairs (p, p+1) that END inside the range.
 // link_prev also matches (slot0-1, slot0), whose query descriptors an earlier call left in place.
-static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool link_prev) {
+// K1 -> K3 -> K4 on slots [slot0, slot0+n), on the current launch stream
+static int features_range(yavo_ctx *ctx, int slot0, int n, cudaEvent_t after_detect = nullptr) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     if (int r = launch_detect(ctx, slot0, n, true, true)) return r;
+    if (after_detect) CK(cudaEventRecord(after_detect, ctx->ls));
     if (int r = launch_select(ctx, slot0, n, ctx->max_kp)) return r;
     const size_t o = (size_t)slot0 * ctx->max_kp;
-    {
-        const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
-        dim3 grid((ctx->max_kp + kp_per_block - 1) / kp_per_block, n);
-        PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(
-            ctx->blur_map, slot0, ctx->d_blur + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, H, W, ctx->d_offs, ctx->d_spos,
-            ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_nbk + slot0, 0, ctx->max_kp, ctx->d_desc + o * 8, nullptr,
-            nullptr));
-        CK_LAUNCH();
+    const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
+    dim3 grid((ctx->max_kp + kp_per_block - 1) / kp_per_block, n);
+    PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->ls>>>(
+        ctx->blur_map, slot0, ctx->d_blur + ctx->frame_stride * slot0, ctx->frame_stride, ctx->pitch, H, W, ctx->d_offs, ctx->d_spos,
+        ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_nbk + slot0, 0, ctx->max_kp, ctx->d_desc + o * 8, nullptr,
+        nullptr));
+    CK_LAUNCH();
+    return 0;
+}
+
+static int ensure_aux(yavo_ctx *ctx) {
+    if (ctx->ev_fork) return 0;
+    for (int i = 0; i < yavo_ctx::MAX_AUX; i++) {
+        CK(cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_k1[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    return 0;
+}
+
+static int frontend_range(yavo_ctx *ctx, int slot0, int n, bool do_match, bool link_prev) {
+    const int C = ctx->ov_chunk, NS = std::min<int>(std::max(ctx->ov_streams, 1), yavo_ctx::MAX_AUX);
+    if (C > 0 && NS > 1 && !ctx->profiling && n >= 2 * C) {
+        // Overlapped: chunk i runs K1 -> K3 -> K4 on auxiliary stream i % NS; its detect kernel waits for the detect kernel of
+        // chunk i-1, which staggers the chunks so that an issue-bound detect kernel always has latency-bound select / BRIEF
+        // kernels of earlier chunks beside it.  Results are identical (the chunks touch disjoint slots); per-kernel
+        // profiling (yavo_set_profiling) runs the serial path so that its event pairs time one kernel each.
+        if (int r = ensure_aux(ctx)) return r;
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        const int nchunks = (n + C - 1) / C;
+        for (int i = 0; i < nchunks; i++) {
+            const int s0 = slot0 + i * C, nc = std::min(C, slot0 + n - s0), si = i % NS;
+            if (i < NS) CK(cudaStreamWaitEvent(ctx->aux[si], ctx->ev_fork, 0));
+            if (i > 0) CK(cudaStreamWaitEvent(ctx->aux[si], ctx->ev_k1[(i - 1) % NS], 0));
+            ctx->ls = ctx->aux[si];
+            const int r = features_range(ctx, s0, nc, ctx->ev_k1[si]);
+            ctx->ls = ctx->stream;
+            if (r) return r;
+        }
+        for (int j = 0; j < std::min(NS, nchunks); j++) {
+            CK(cudaEventRecord(ctx->ev_join[j], ctx->aux[j]));
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[j], 0));
+        }
+    } else if (int r = features_range(ctx, slot0, n)) {
+        return r;
     }
     const int m0 = (link_prev && slot0 > 0) ? slot0 - 1 : slot0;  // first query slot
     const int pairs = slot0 + n - 1 - m0;
@@ -1280,6 +1334,13 @@ extern "C" int yavo_debug_select_timing(yavo_ctx *ctx, long long *out /* 64 x 8 
 int yavo_set_matcher(yavo_ctx *ctx, int kind) {
     if (!ctx || kind < 0 || kind > 2) return YAVO_ERR_INVALID;
     ctx->matcher = kind;
+    return 0;
+}
+
+int yavo_set_overlap(yavo_ctx *ctx, int chunk_frames, int n_streams) {
+    if (!ctx || chunk_frames < 0 || n_streams < 1 || n_streams > yavo_ctx::MAX_AUX) return YAVO_ERR_INVALID;
+    ctx->ov_chunk = chunk_frames;
+    ctx->ov_streams = n_streams;
     return 0;
 }
 
