@@ -150,7 +150,8 @@ int yavo_remove_outliers(const int32_t *dist, int n, int threshold, uint8_t *kee
  * in device memory; nothing is copied to the host.  Frames must all have the same size. */
 int yavo_frontend_batch(yavo_ctx *ctx, int slot0, int n, int do_match);
 
-/* Copies the results of yavo_frontend_batch for n slots to host arrays (any may be NULL):
+/* Copies the results of yavo_frontend_batch for n slots to caller arrays — host memory, or device memory of the context's
+ * GPU (the copies use unified addressing; a multi-GPU caller gathers device buffers over NVLink) — any may be NULL:
  *   n_kp[n]; rows/cols/scores [n x max_kp]; desc [n x max_kp x 32]; only keypoints admitted by
  *   checkBoundry are kept, compacted in order, as Brief::computeBrief appends them;
  *   match_idx/match_dist [n x max_kp]: entry (f, i) is the match of keypoint i of slot f-1 in slot f

@@ -82,3 +82,49 @@ def test_filter_pairs_empty_train_set(cuda_lib, oracle, offsets):
         assert n_pairs[1] == 0
         assert not cuda_lib.remove_outliers(out["match_dist"][1, :k], 20).any()
         assert not oracle.remove_outliers(out["match_dist"][1, :k], 20).any()
+
+
+def test_two_shards_on_real_contexts_equal_one(cuda_lib, offsets):
+    """The seq-00 sharding (bench.py --config seq00) with real contexts: two shards with the seam frame, results fetched
+    into torch CUDA tensors (device pointers through the C ABI) — concatenated they equal the single-context run bit for
+    bit, the seam pair included."""
+    import torch
+    from ya_vo_b200 import sharding
+    F, world = 23, 2
+    frames = synth.synth_batch(F, "G30", 1000, 120, 320)
+    frames[12] = synth.shifted_pair(frames[11], 5)  # true matches across the seam (shard 1 starts at frame 11)
+    dev = torch.device("cuda", 0)
+    parts = []
+    for rank in range(world):
+        first, lo, hi = sharding.shard_plan(F, world)[rank]
+        with cuda_lib.Context(device=0, n_slots=hi - first, max_rows=120, max_cols=320, max_kp=300) as ctx:
+            ctx.set_brief_offsets(offsets)
+            ctx.upload_batch(0, np.ascontiguousarray(frames[first:hi]))
+            assert sharding.run_resident_shard(ctx, F, rank, world) == (first, lo, hi)
+            res = sharding.fetch_owned(ctx, first, lo, hi, sharding.alloc_result_tensors(hi - lo, 300, dev))
+            parts.append({k: v.cpu() for k, v in res.items()})
+    full = {k: torch.cat([p[k] for p in parts]) for k in sharding.RESULT_KEYS}
+    with cuda_lib.Context(device=0, n_slots=F, max_rows=120, max_cols=320, max_kp=300) as ctx:
+        ctx.set_brief_offsets(offsets)
+        ctx.upload_batch(0, frames)
+        ctx.frontend_batch(0, F, True)
+        one = ctx.fetch_batch(0, F)
+    assert sharding.results_digest(full, F) == sharding.results_digest(one, F)
+    kq = int(one["n_kp"][11])
+    assert kq > 0 and np.array_equal(full["match_idx"][12, :kq].numpy(), one["match_idx"][12, :kq])
+
+
+def test_overlapped_feature_pipeline_gives_identical_results(cuda_lib, offsets):
+    """yavo_set_overlap: chunks rotating over internal streams change the schedule, not the results."""
+    frames = synth.synth_batch(48, "B4", 77, 120, 320)
+    outs = []
+    for chunk, streams in ((0, 1), (8, 3), (16, 2), (5, 4)):
+        with cuda_lib.Context(device=0, n_slots=48, max_rows=120, max_cols=320, max_kp=300) as ctx:
+            ctx.set_brief_offsets(offsets)
+            ctx.set_overlap(chunk, streams)
+            ctx.upload_batch(0, frames)
+            for _ in range(2):
+                ctx.frontend_batch(0, 48, True)
+            outs.append(ctx.fetch_batch(0, 48))
+    for o in outs[1:]:
+        _same_results(o, outs[0], 48)

@@ -92,3 +92,64 @@ def test_two_ranks_gloo(n_frames, batch):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+class FakeResidentCtx(FakeCtx):
+    """Stand-in for the device-resident path: frontend_batch over uploaded slots, fetch_batch_ptrs into torch tensors."""
+
+    def __init__(self, frames):
+        self.frames = frames
+
+    def frontend_batch(self, slot0, n, do_match=True):
+        self.out = self.process_host_batch(self.frames[slot0:slot0 + n], do_match)
+
+    def fetch_batch_ptrs(self, slot0, n, ptrs):
+        import ctypes as C
+        for k, p in ptrs.items():
+            src = np.ascontiguousarray(self.out[k][slot0:slot0 + n])
+            C.memmove(int(p), src.ctypes.data, src.nbytes)
+
+
+def _tensor_worker(rank, world, port, n_frames, q):
+    import torch
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    frames = make_frames(n_frames)
+    first, lo, hi = sharding.shard_plan(n_frames, world)[rank]
+    ctx = FakeResidentCtx(frames[first:hi])
+    assert sharding.run_resident_shard(ctx, n_frames, rank, world) == (first, lo, hi)
+    res = sharding.fetch_owned(ctx, first, lo, hi, sharding.alloc_result_tensors(hi - lo, ctx.max_kp, torch.device("cpu")))
+    full = sharding.gather_tensors_to_rank0(res, n_frames, rank, world)
+    if rank == 0:
+        sig, md = expected(frames)
+        ok = np.array_equal(full["rows"][:, 0].numpy(), sig) and np.array_equal(full["match_dist"][:, 0].numpy(), md)
+        # the digest of the gathered result equals the digest of a single-rank run
+        one = FakeResidentCtx(frames)
+        one.frontend_batch(0, n_frames)
+        ref = sharding.fetch_owned(one, 0, 0, n_frames, sharding.alloc_result_tensors(n_frames, one.max_kp, torch.device("cpu")))
+        ok = ok and sharding.results_digest(full, n_frames) == sharding.results_digest(ref, n_frames)
+        q.put(bool(ok))
+    else:
+        assert full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_frames", [17, 64, 3])
+def test_two_ranks_tensor_gather_gloo(n_frames):
+    """The seq-00 path of bench.py (--config seq00): resident shard incl. the seam frame, results fetched into fixed-shape
+    tensors and gathered with dist.gather (no pickling); rank 0's result is bit-identical to a single-rank run."""
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_tensor_worker, args=(r, 2, port, n_frames, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

@@ -253,6 +253,13 @@ class Context:
                                           _p(out["match_dist"])))
         return out
 
+    def fetch_batch_ptrs(self, slot0, n, ptrs):
+        """fetch_batch into caller memory given as raw addresses (host, or device memory of this GPU — e.g. torch CUDA
+        tensors' data_ptr()): dict with any of n_kp, rows, cols, scores, desc, match_idx, match_dist."""
+        a = [C.c_void_p(int(ptrs[k])) if ptrs.get(k) else None
+             for k in ("n_kp", "rows", "cols", "scores", "desc", "match_idx", "match_dist")]
+        self._ck(self._L.yavo_fetch_batch(self._h, int(slot0), int(n), *a))
+
     def filter_pairs(self, slot0, n, threshold=20):
         """removeOutliers + point pairs on the device for the matches of the last frontend_batch."""
         n_pairs = np.zeros(n, np.int32)

@@ -1103,13 +1103,13 @@ int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *ro
     if (n == 0) return 0;
     CK(cudaSetDevice(ctx->device));
     const size_t o = (size_t)slot0 * ctx->max_kp, cnt = (size_t)n * ctx->max_kp;
-    if (n_kp) CK(cudaMemcpyAsync(n_kp, ctx->d_nbk + slot0, 4 * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (rows) CK(cudaMemcpyAsync(rows, ctx->d_bk_row + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    if (cols) CK(cudaMemcpyAsync(cols, ctx->d_bk_col + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    if (scores) CK(cudaMemcpyAsync(scores, ctx->d_bk_score + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    if (desc) CK(cudaMemcpyAsync(desc, ctx->d_desc + o * 8, 32 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    if (match_idx) CK(cudaMemcpyAsync(match_idx, ctx->d_midx + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    if (match_dist) CK(cudaMemcpyAsync(match_dist, ctx->d_mdist + o, 4 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_kp) CK(cudaMemcpyAsync(n_kp, ctx->d_nbk + slot0, 4 * (size_t)n, cudaMemcpyDefault, ctx->stream));
+    if (rows) CK(cudaMemcpyAsync(rows, ctx->d_bk_row + o, 4 * cnt, cudaMemcpyDefault, ctx->stream));
+    if (cols) CK(cudaMemcpyAsync(cols, ctx->d_bk_col + o, 4 * cnt, cudaMemcpyDefault, ctx->stream));
+    if (scores) CK(cudaMemcpyAsync(scores, ctx->d_bk_score + o, 4 * cnt, cudaMemcpyDefault, ctx->stream));
+    if (desc) CK(cudaMemcpyAsync(desc, ctx->d_desc + o * 8, 32 * cnt, cudaMemcpyDefault, ctx->stream));
+    if (match_idx) CK(cudaMemcpyAsync(match_idx, ctx->d_midx + o, 4 * cnt, cudaMemcpyDefault, ctx->stream));
+    if (match_dist) CK(cudaMemcpyAsync(match_dist, ctx->d_mdist + o, 4 * cnt, cudaMemcpyDefault, ctx->stream));
     return check_status(ctx);  // synchronises; reports a candidate-list overflow
 }
 
@@ -1117,13 +1117,13 @@ int yavo_fetch_batch(yavo_ctx *ctx, int slot0, int n, int32_t *n_kp, int32_t *ro
 static int fetch_async(yavo_ctx *ctx, cudaStream_t st, int base, int slot0, int n, int32_t *n_kp, int32_t *rows,
                        int32_t *cols, float *scores, uint8_t *desc, int32_t *match_idx, int32_t *match_dist) {
     const size_t o = (size_t)slot0 * ctx->max_kp, cnt = (size_t)n * ctx->max_kp, h = (size_t)(slot0 - base) * ctx->max_kp;
-    if (n_kp) CK(cudaMemcpyAsync(n_kp + (slot0 - base), ctx->d_nbk + slot0, 4 * (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (rows) CK(cudaMemcpyAsync(rows + h, ctx->d_bk_row + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
-    if (cols) CK(cudaMemcpyAsync(cols + h, ctx->d_bk_col + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
-    if (scores) CK(cudaMemcpyAsync(scores + h, ctx->d_bk_score + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
-    if (desc) CK(cudaMemcpyAsync(desc + h * 32, ctx->d_desc + o * 8, 32 * cnt, cudaMemcpyDeviceToHost, st));
-    if (match_idx) CK(cudaMemcpyAsync(match_idx + h, ctx->d_midx + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
-    if (match_dist) CK(cudaMemcpyAsync(match_dist + h, ctx->d_mdist + o, 4 * cnt, cudaMemcpyDeviceToHost, st));
+    if (n_kp) CK(cudaMemcpyAsync(n_kp + (slot0 - base), ctx->d_nbk + slot0, 4 * (size_t)n, cudaMemcpyDefault, st));
+    if (rows) CK(cudaMemcpyAsync(rows + h, ctx->d_bk_row + o, 4 * cnt, cudaMemcpyDefault, st));
+    if (cols) CK(cudaMemcpyAsync(cols + h, ctx->d_bk_col + o, 4 * cnt, cudaMemcpyDefault, st));
+    if (scores) CK(cudaMemcpyAsync(scores + h, ctx->d_bk_score + o, 4 * cnt, cudaMemcpyDefault, st));
+    if (desc) CK(cudaMemcpyAsync(desc + h * 32, ctx->d_desc + o * 8, 32 * cnt, cudaMemcpyDefault, st));
+    if (match_idx) CK(cudaMemcpyAsync(match_idx + h, ctx->d_midx + o, 4 * cnt, cudaMemcpyDefault, st));
+    if (match_dist) CK(cudaMemcpyAsync(match_dist + h, ctx->d_mdist + o, 4 * cnt, cudaMemcpyDefault, st));
     return 0;
 }
 

@@ -66,8 +66,86 @@ def process_shard(ctx, load_frames, n_frames, rank, world, batch, do_match=True)
     return res
 
 
+RESULT_KEYS = ("n_kp", "rows", "cols", "scores", "desc", "match_idx", "match_dist")
+
+
+def alloc_result_tensors(n_own, max_kp, device):
+    """Fixed-shape torch tensors for the results of `n_own` owned frames (what yavo_fetch_batch fills)."""
+    import torch
+    K = max_kp
+    return dict(n_kp=torch.zeros(n_own, dtype=torch.int32, device=device),
+                rows=torch.zeros((n_own, K), dtype=torch.int32, device=device),
+                cols=torch.zeros((n_own, K), dtype=torch.int32, device=device),
+                scores=torch.zeros((n_own, K), dtype=torch.float32, device=device),
+                desc=torch.zeros((n_own, K, 32), dtype=torch.uint8, device=device),
+                match_idx=torch.full((n_own, K), -1, dtype=torch.int32, device=device),
+                match_dist=torch.full((n_own, K), -1, dtype=torch.int32, device=device))
+
+
+def gather_tensors_to_rank0(res, n_frames, rank, world, group=None):
+    """Gathers per-rank result TENSORS (first dimension = the rank's owned frames [lo, hi)) on rank 0 with
+    torch.distributed.gather of fixed-shape buffers, padded to the largest shard: NCCL over NVLink for CUDA tensors,
+    gloo for CPU tensors.  Nothing is pickled (a seq-00-length run returns ~470 MB).  Returns the concatenated tensors
+    on rank 0 (frame order), None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return res
+    plan = shard_plan(n_frames, world)
+    own = [hi - lo for _, lo, hi in plan]
+    max_own = max(own)
+    out = {}
+    for k in RESULT_KEYS:
+        t = res[k]
+        assert t.shape[0] == own[rank], (k, t.shape, own[rank])
+        pad = t if t.shape[0] == max_own else torch.cat(
+            [t, torch.zeros((max_own - t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)])
+        parts = [torch.empty_like(pad) for _ in range(world)] if rank == 0 else None
+        dist.gather(pad.contiguous(), parts, dst=0, group=group)
+        if rank == 0:
+            out[k] = torch.cat([parts[r][:own[r]] for r in range(world)])
+    return out if rank == 0 else None
+
+
+def run_resident_shard(ctx, n_frames, rank, world, do_match=True):
+    """Front end over this rank's shard, already uploaded to slots [0, hi - first) (slot 0 = frame `first`, the seam frame
+    when the shard does not start the sequence).  Returns (first, lo, hi)."""
+    first, lo, hi = shard_plan(n_frames, world)[rank]
+    if hi > first:
+        ctx.frontend_batch(0, hi - first, do_match)
+    return first, lo, hi
+
+
+def fetch_owned(ctx, first, lo, hi, out):
+    """Device results of the owned frames [lo, hi) into `out` (alloc_result_tensors, on the context's GPU or on the
+    host): the seam frame's own results belong to the previous rank and are skipped; row 0 of the owned block holds the
+    match of the seam pair (lo-1, lo)."""
+    if hi > lo:
+        ctx.fetch_batch_ptrs(lo - first, hi - lo, {k: out[k].data_ptr() for k in RESULT_KEYS})
+    return out
+
+
+def results_digest(res, n_frames):
+    """sha256 over the defined part of a full result set (entries beyond n_kp are unspecified): what makes a sharded
+    run comparable with a single-GPU run bit for bit."""
+    import hashlib
+    h = hashlib.sha256()
+    g = {k: (v.cpu().numpy() if hasattr(v, "cpu") else np.asarray(v)) for k, v in res.items()}
+    h.update(np.ascontiguousarray(g["n_kp"][:n_frames]).tobytes())
+    for f in range(n_frames):
+        k = int(g["n_kp"][f])
+        for key in ("rows", "cols", "scores", "desc"):
+            h.update(np.ascontiguousarray(g[key][f, :k]).tobytes())
+        if f > 0:
+            kq = int(g["n_kp"][f - 1])
+            h.update(np.ascontiguousarray(g["match_idx"][f, :kq]).tobytes())
+            h.update(np.ascontiguousarray(g["match_dist"][f, :kq]).tobytes())
+    return h.hexdigest()
+
+
 def gather_to_rank0(res, rank, world, group=None):
-    """Gathers the per-rank result dicts on rank 0 (no collective runs on the kernels' data path)."""
+    """Gathers the per-rank result dicts on rank 0 by pickling them (small runs and tests; a full-length run uses
+    gather_tensors_to_rank0)."""
     if world == 1:
         return res
     import torch.distributed as dist
