@@ -128,3 +128,29 @@ def test_overlapped_feature_pipeline_gives_identical_results(cuda_lib, offsets):
             outs.append(ctx.fetch_batch(0, 48))
     for o in outs[1:]:
         _same_results(o, outs[0], 48)
+
+
+@pytest.mark.parametrize("n1,n2", [(1, 1), (5, 1), (7, 3), (128, 224), (129, 225), (128, 448), (500, 449), (2000, 2000), (1950, 1949),
+                                   (333, 4097), (4096, 129), (300, 0), (9000, 7000)])
+def test_second_best_from_the_tensor_core_epilogue(cuda_lib, oracle, n1, n2):
+    """Ratio-test extension (north_star; no reference counterpart, parity pinned to the oracle's definition only): the
+    second smallest distance of every query comes out of the tcgen05 matcher's own epilogue (two smallest keys per
+    row), the cross-check index from the same kernel with the roles swapped.  Duplicated train descriptors make
+    second == best; single-column train sets leave it at INT_MAX."""
+    d1 = synth.synth_descriptors(n1, n1 * 131 + n2)
+    d2 = synth.planted_descriptors(d1, n2, 7) if (n1 and n2) else synth.synth_descriptors(n2, 1)
+    if n2 > 300:
+        d2[290] = d2[10]   # duplicates in different tiles
+        d2[40] = d2[10]    # ... and inside one tile
+    if n1 > 5 and n2 > 5:
+        d1[3] = d2[5]
+        d1[4] = ~d2[5]
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=64, max_cols=128, max_kp=16) as ctx:
+        ctx.set_matcher("tc")
+        idx, dist, sec, rev = ctx.match(d1, d2, extensions=True)
+        kl = ctx.kernel_launches
+    eidx, edist, esec, erev = oracle.match(d1, d2, extensions=True)
+    assert np.array_equal(idx, eidx) and np.array_equal(dist, edist)
+    assert np.array_equal(sec, esec)
+    assert np.array_equal(rev, erev)
+    assert kl <= 2  # forward (with second) + reverse: no integer-pipe fallback, no reduce kernels

@@ -10,10 +10,11 @@ from ya_vo_b200 import capi, synth  # noqa: E402
 
 
 def main():
-    sizes = [1024, 2048, 4096, 8192, 16384, 32768, 65536]
+    sizes = [int(x) for x in sys.argv[1].split(",")] if len(sys.argv) > 1 else [1024, 2048, 4096, 8192, 16384, 32768, 65536]
     out = {"unit": "Gpairs/s", "note": "device time of the match kernels (match_tc, or match_partial + match_reduce), descriptors "
            "already on the device side of yavo_match's H2D; matcher = tc (tcgen05 kind::mxf4, default), tc8 (kind::f8f6f4) or "
-           "popc (integer pipes); ext=1: second-best distance (always the popc kernel) + cross-check (the selected matcher)",
+           "popc (integer pipes); ext=1: second-best distance (from the tcgen05 epilogue since round 2) + cross-check (a second "
+           "launch with the roles swapped: 2 x N1 x N2 pairs counted)",
            "rows": []}
     with capi.Context(device=0, n_slots=1, max_rows=64, max_cols=128, max_kp=16) as ctx:
         for n1 in sizes:

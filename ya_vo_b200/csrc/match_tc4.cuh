@@ -182,6 +182,35 @@ __device__ __forceinline__ void min_keys4(const uint32_t (&v)[32], float (&m)[NC
     }
 }
 
+// the two smallest keys of every chain (SECOND: ratio-test extension).  Per two new keys: lo / hi of the pair, then
+// m2 = min(m2, hi, max(m1, lo)), m1 = min(m1, lo) — five minimum / maximum operations instead of one.
+template <bool FULL>
+__device__ __forceinline__ void min2_keys4(const uint32_t (&v)[32], float (&m)[NCH], float (&m2)[NCH], int n, int col0, int nvalid) {
+    if (FULL) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 2 * NCH) {
+            if (i >= n) break;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const float a = __uint_as_float(v[i + 2 * c]), b = __uint_as_float(v[i + 2 * c + 1]);
+                const float lo = fminf(a, b), hi = fmaxf(a, b);
+                m2[c] = fminf(fminf(m2[c], hi), fmaxf(m[c], lo));
+                m[c] = fminf(m[c], lo);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            if (i >= n) break;
+            if (col0 + i < nvalid) {
+                const float a = __uint_as_float(v[i]);
+                m2[i & (NCH - 1)] = fminf(m2[i & (NCH - 1)], fmaxf(m[i & (NCH - 1)], a));
+                m[i & (NCH - 1)] = fminf(m[i & (NCH - 1)], a);
+            }
+        }
+    }
+}
+
 // every role walks the same list of work items: role branches outermost, one item loop per role (83 instead of 96
 // registers and 9 % less time than one shared item loop with the role branches inside)
 #define YAVO_TC4_FOR_ITEMS \
@@ -197,16 +226,18 @@ __device__ __forceinline__ void min_keys4(const uint32_t (&v)[32], float (&m)[NC
 
 // Arguments as match_tc_kernel.  dbg_acc (test tool only): the 128 x 224 accumulator values (key - 32768) of the
 // first tile of work item 0.
-template <bool DBG>
+template <bool DBG, bool SECOND = false>
 __global__ void __launch_bounds__(THREADS4, 1)
 match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq_all, int nq_fixed,
                  const uint32_t *__restrict__ dt_all, const int *__restrict__ nt_all, int nt_fixed,
                  size_t set_stride_words, int q_set_offset, int t_set_offset, int pairs, int q_tiles, int out_stride,
-                 int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_acc) {
+                 int32_t *__restrict__ out_idx, int32_t *__restrict__ out_dist, float *__restrict__ dbg_acc,
+                 int32_t *__restrict__ out_second = nullptr) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bars[2 * NSTAGE + 2 * NACC + 2 * NB4 + 2 * NR4];
     __shared__ uint32_t tmem_base_s;
     __shared__ int2 comb[2][Q4];
+    __shared__ int comb_sec[SECOND ? 2 : 1][SECOND ? Q4 : 1];
     // shared-window addresses, computed once (barriers are 8 bytes apart)
     uint32_t bars_s, smem_s;  // through an opaque move: the compiler otherwise rematerialises the conversion (S2R + LEA) at every use
     asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(bars_s), "=r"(smem_s) : "r"(saddr(bars)), "r"(saddr(smem_raw)));
@@ -272,16 +303,20 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
         YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ epilogue (two groups on alternate accumulators)
             const int g = warp >> 2, row = (warp & 3) * 32 + lane;
-            int best_d = 0x7fffffff, best_j = -1;
+            int best_d = 0x7fffffff, best_j = -1, sec_d = 0x7fffffff;  // sec_d: second smallest distance (SECOND)
             for (int t = EPI_SPLIT ? 0 : (((t_cnt & 1) == (uint32_t)g) ? 0 : 1); t < n_tiles; t += EPI_SPLIT ? 1 : 2) {
                 const uint32_t acc = (t_cnt + t) % NACC, ph = ((t_cnt + t) / NACC) & 1;
                 bar_wait(acc_full + 8 * (acc), ph);
                 fence_after_sync();
                 const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + acc * T4;
                 const int nvalid = min(T4, nt - t * T4);
-                float m4[NCH];
+                float m4[NCH], s4[NCH];  // s4: chain seconds (SECOND only; dead code otherwise)
 #pragma unroll
                 for (int c = 0; c < NCH; c++) m4[c] = 3.0e38f;
+                if (SECOND) {
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) s4[c] = 3.0e38f;
+                }
                 uint32_t v0[32], v1[32], v2[32], v3[16];
                 const bool full = nvalid == T4;
                 // CW columns per pass = 32 + 32 | 32 + 16 (or | 8): the second group is loaded while the first is reduced
@@ -295,19 +330,36 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                     tmem_wait2(v0, v1);
 #endif
 #ifndef YAVO_TC_EXP_NO_EPI
-                    if (full) min_keys4<true>(v0, m4, 0, 0); else min_keys4<false>(v0, m4, c0, nvalid);
+                    if (SECOND) {
+                        if (full) min2_keys4<true>(v0, m4, s4, 32, 0, 0); else min2_keys4<false>(v0, m4, s4, 32, c0, nvalid);
+                    } else {
+                        if (full) min_keys4<true>(v0, m4, 0, 0); else min_keys4<false>(v0, m4, c0, nvalid);
+                    }
                     if (CW == 112) tmem_ld32(ta + 64, v2);
-                    if (full) min_keys4<true>(v1, m4, 0, 0); else min_keys4<false>(v1, m4, c0 + 32, nvalid);
+                    if (SECOND) {
+                        if (full) min2_keys4<true>(v1, m4, s4, 32, 0, 0); else min2_keys4<false>(v1, m4, s4, 32, c0 + 32, nvalid);
+                    } else {
+                        if (full) min_keys4<true>(v1, m4, 0, 0); else min_keys4<false>(v1, m4, c0 + 32, nvalid);
+                    }
                     constexpr int TAIL = CW == 112 ? 16 : 8, TOFF = CW - TAIL;
                     if (CW == 112) {
                         tmem_ld16(ta + TOFF, v3);
                         tmem_wait2b(v2, v3);
-                        if (full) min_keys4<true>(v2, m4, 0, 0); else min_keys4<false>(v2, m4, c0 + 64, nvalid);
+                        if (SECOND) {
+                            if (full) min2_keys4<true>(v2, m4, s4, 32, 0, 0); else min2_keys4<false>(v2, m4, s4, 32, c0 + 64, nvalid);
+                        } else {
+                            if (full) min_keys4<true>(v2, m4, 0, 0); else min_keys4<false>(v2, m4, c0 + 64, nvalid);
+                        }
                     } else {
                         tmem_ld8(ta + TOFF, v3);
                         tmem_wait16(v3);
                     }
-                    if (full) {
+                    if (SECOND) {
+                        uint32_t vt[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i++) vt[i] = i < TAIL ? v3[i & 15] : 0u;
+                        if (full) min2_keys4<true>(vt, m4, s4, TAIL, 0, 0); else min2_keys4<false>(vt, m4, s4, TAIL, c0 + TOFF, nvalid);
+                    } else if (full) {
 #pragma unroll
                         for (int i = 0; i < TAIL; i += 2) m4[(i >> 1) & (NCH - 1)] = fminf(m4[(i >> 1) & (NCH - 1)], fminf(__uint_as_float(v3[i]), __uint_as_float(v3[i + 1])));
                     } else {  // last tile of a train set
@@ -328,22 +380,50 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
 #endif
                 float m = fminf(fminf(m4[0], m4[1]), fminf(m4[2], m4[3]));
                 if (NCH == 8) m = fminf(m, fminf(fminf(m4[NCH - 4], m4[NCH - 3]), fminf(m4[NCH - 2], m4[NCH - 1])));
+                float m2 = 3.0e38f;
+                if (SECOND) {
+                    // second smallest key of the tile part: the smallest chain second, or the second smallest chain minimum
+                    float a = m4[0], b = 3.0e38f;  // a <= b: the two smallest chain minima
+#pragma unroll
+                    for (int c = 1; c < NCH; c++) {
+                        b = fminf(b, fmaxf(a, m4[c]));
+                        a = fminf(a, m4[c]);
+                    }
+                    m2 = b;
+#pragma unroll
+                    for (int c = 0; c < NCH; c++) m2 = fminf(m2, s4[c]);
+                }
                 fence_before_sync();
                 __syncwarp();
                 if (lane == 0) bar_arrive(acc_empty + 8 * (acc));
                 const int ki = (int)m + 32768;  // 256 * distance + column, exact
-                if (m < 1.0e30f /* this warp's columns may all lie beyond the train set */ && (ki >> 8) < best_d) {
+                const bool any = m < 1.0e30f;   // this warp's columns may all lie beyond the train set
+                if (SECOND && any) {
+                    // the running second: the old best when this tile part beats it, else this part's smallest; and its second
+                    const int d1 = ki >> 8, d2 = m2 < 1.0e30f ? (((int)m2 + 32768) >> 8) : 0x7fffffff;
+                    sec_d = min(sec_d, d1 < best_d ? min(best_d, d2) : d1);
+                }
+                if (any && (ki >> 8) < best_d) {
                     best_d = ki >> 8;
                     best_j = t * T4 + (ki & 255);
                 }
             }
             t_cnt += n_tiles;
             int2 *cb = comb[e_cnt & 1];
+            int *cs = comb_sec[SECOND ? (e_cnt & 1) : 0];
             e_cnt++;
-            if (g == 1) cb[row] = make_int2(best_d, best_j);
+            if (g == 1) {
+                cb[row] = make_int2(best_d, best_j);
+                if (SECOND) cs[row] = sec_d;
+            }
             asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
             if (g == 0) {
                 const int2 o = cb[row];
+                if (SECOND) {
+                    // two halves (best, second): overall second = min(the two seconds, the larger of the two bests)
+                    const int os = cs[row];
+                    sec_d = min(min(sec_d, os), max(best_d, o.x));
+                }
                 if (o.x < best_d || (o.x == best_d && o.y < best_j)) {
                     best_d = o.x;
                     best_j = o.y;
@@ -352,6 +432,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 if (q < nq) {
                     out_idx[(size_t)pair * out_stride + q] = best_j;  // empty train set: -1 / INT_MAX
                     out_dist[(size_t)pair * out_stride + q] = best_d;
+                    if (SECOND) out_second[(size_t)pair * out_stride + q] = sec_d;
                 }
             }
         }

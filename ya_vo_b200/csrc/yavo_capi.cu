@@ -607,6 +607,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
                              (int)select_smem_bytes()));
     CKC(cudaFuncSetAttribute(tcm::match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm::SMEM_BYTES));
     CKC(cudaFuncSetAttribute(tcm4::match_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm4::SMEM4_BYTES));
+    CKC(cudaFuncSetAttribute(tcm4::match_tc4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm4::SMEM4_BYTES));
     CKC(cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, device));
 #undef CKC
     *out = c;
@@ -889,12 +890,16 @@ int yavo_brief_describe(yavo_ctx *ctx, int slot, const int32_t *rows, const int3
 // K5t launch: pairs x q_tiles work items over one persistent CTA per SM
 static int launch_match_tc(yavo_ctx *ctx, const uint32_t *dq_all, const int *nq_all, int nq_fixed, const uint32_t *dt_all,
                            const int *nt_all, int nt_fixed, size_t set_stride_words, int q_off, int t_off, int pairs,
-                           int max_q, int out_stride, int32_t *o_idx, int32_t *o_dist) {
+                           int max_q, int out_stride, int32_t *o_idx, int32_t *o_dist, int32_t *o_sec = nullptr) {
     const int q_tiles = (max_q + tcm::TQ - 1) / tcm::TQ;
     const long long items = (long long)pairs * q_tiles;
     if (items <= 0) return 0;
     const int grid = (int)std::min<long long>(items, ctx->n_sms);
-    if (ctx->matcher == 2)
+    if (o_sec)  // ratio-test extension: the packed-4-bit kernel also keeps the second smallest distance of every query
+        PROF(KC_MATCH_TC, tcm4::match_tc4_kernel<false, true><<<grid, tcm4::THREADS4, tcm4::SMEM4_BYTES, ctx->stream>>>(
+                              dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
+                              out_stride, o_idx, o_dist, nullptr, o_sec));
+    else if (ctx->matcher == 2)
         PROF(KC_MATCH_TC, tcm::match_tc_kernel<false><<<grid, tcm::THREADS, tcm::SMEM_BYTES, ctx->stream>>>(
                               dq_all, nq_all, nq_fixed, dt_all, nt_all, nt_fixed, set_stride_words, q_off, t_off, pairs, q_tiles,
                               out_stride, o_idx, o_dist, nullptr));
@@ -908,9 +913,9 @@ static int launch_match_tc(yavo_ctx *ctx, const uint32_t *dq_all, const int *nq_
 
 static int match_device(yavo_ctx *ctx, const uint32_t *dq, int n1, const uint32_t *dt, int n2, int32_t *o_idx,
                         int32_t *o_dist, int32_t *o_sec) {
-    // tensor-core matcher unless the caller wants the second-best distance (ratio-test extension), which only
-    // the POPC kernel tracks
-    if (!o_sec && ctx->matcher != 1) return launch_match_tc(ctx, dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, 1, n1, n1, o_idx, o_dist);
+    // tensor-core matcher (its SECOND variant when the caller wants the second-best distance, the ratio-test extension);
+    // yavo_set_matcher(ctx, 1) selects the integer-pipe kernel
+    if (ctx->matcher != 1) return launch_match_tc(ctx, dq, nullptr, n1, dt, nullptr, n2, 0, 0, 0, 1, n1, n1, o_idx, o_dist, o_sec);
     const int chunks = choose_chunks(n1, n2, 1);
     const int chunk = std::max(1, (std::max(n2, 1) + chunks - 1) / chunks);
     if (int r = ensure_partials(ctx, (size_t)n1 * chunks)) return r;
