@@ -100,6 +100,23 @@ void yavo_ring_points(int xc, int yc, int32_t *out_xy);
  * same kernel and cached in the slot. */
 int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int32_t *out_cols,
                      float *out_scores, int *n_out, int *n_cand);
+/* The reference's per-frame sequence in ONE call (LoopHandler::insertFrameFeatures, src/LoopHandler.cc:468-485:
+ * FastDetector::getFastFeatures on a fresh frame, then Brief::computeBrief on the points it returned): uploads the host
+ * frame (rows x cols, row pitch `stride`) into `slot`, detects, orders and cuts to max_kp as yavo_fast_detect does, and
+ * describes the points checkBoundry admits as yavo_brief_describe would.  The whole sequence — copy in, kernels, copy
+ * out — is captured once per (slot, frame size, max_kp) as a CUDA graph between pinned staging buffers, so a call costs
+ * one graph launch and one synchronisation.  yavo_set_brief_offsets must have been called.
+ *   kp_rows / kp_cols / kp_scores [max_kp], *n_kp: the detector's output (kp_scores may be NULL)
+ *   d_rows / d_cols / d_ids [max_kp], desc [max_kp x 32], *n_desc: the admitted points in order; d_ids = index of the
+ *   point in the kp list (the `id` Brief::computeBrief gives the KeyPoint, src/BriefDescriptor.cc:95)
+ *   *n_cand: pixels that passed the segment test.  Any output pointer may be NULL. */
+int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows, int cols, int stride, int max_kp,
+                        int32_t *n_kp, int32_t *kp_rows, int32_t *kp_cols, float *kp_scores, int32_t *n_desc,
+                        int32_t *d_rows, int32_t *d_cols, int32_t *d_ids, uint8_t *desc, int *n_cand);
+/* 1 when `slot` was last filled by yavo_frame_features with exactly these pixels (compared byte for byte with the pinned
+ * host copy that call kept), 0 when not or unknown, < 0 on bad arguments.  Lets a caller that owns mutable host pixels
+ * (Image::rawImage is public in the reference) decide whether device-side results for the slot are still valid. */
+int yavo_slot_holds(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows, int cols, int stride);
 /* the unsorted candidate list in scan (row-major) order, as the reference's retCorners holds it
  * before the sort (src/FastDetector.cc:298-335); for parity tests. capacity `cap` entries. */
 int yavo_fast_candidates(yavo_ctx *ctx, int slot, int cap, int32_t *out_rows, int32_t *out_cols,

@@ -107,3 +107,133 @@ def test_brief_descriptor_test_pipeline(host_tests, oracle, offsets, tmp_path):
     keep = oracle.remove_outliers(dist, 20)
     assert nf == int(keep.sum()) and np.array_equal(m["matched"].astype(bool), keep)
     assert np.array_equal(fm["dist"], dist[keep])
+
+
+def test_reference_callers_compile_verbatim():
+    """Source compatibility: tests/BriefDescriptorTest.cc:10-47 and the body of LoopHandler::insertFrameFeatures
+    (src/LoopHandler.cc:469-484) are cut out of the reference checkout at build time and compiled unchanged against
+    ya_vo_b200/host/include (ya_vo_b200/host/test/ref_callers.cc).  Where the checkout is absent (the GPU box) the binary
+    built beside it must be there."""
+    subprocess.check_call(["make", "-C", HOST, "-s"])
+    assert os.access(os.path.join(HOST, "ref_callers"), os.X_OK)
+    if os.path.isdir("/root/reference/src"):
+        body = open(os.path.join(HOST, "test", "_gen", "insert_frame_features.inc")).read()
+        assert "fd.getFastFeatures(*_frame)" in body and "brief.computeBrief(features, *_frame)" in body
+        body = open(os.path.join(HOST, "test", "_gen", "brief_test_body.inc")).read()
+        assert "brief.matchFeatures(testObj1, testObj2)" in body and "brief.removeOutliers(matches, filterMatches, 20.0)" in body
+    # nothing of the reference is committed
+    assert "_gen" in open(os.path.join(ROOT, ".gitignore")).read()
+
+
+def _keypoints(buf, off):
+    kdt = np.dtype([("x", "<i4"), ("y", "<i4"), ("id", "<i4"), ("d", "u1", (32,))])
+    (nk,), off = _read(buf, off, "<i")
+    k = np.frombuffer(buf, dtype=kdt, count=nk, offset=off)
+    return k, off + kdt.itemsize * nk
+
+
+@pytest.mark.gpu
+def test_reference_callers_run_on_the_gpu(host_tests, oracle, tmp_path):
+    """The verbatim reference callers on the GPU: the Brief objects draw their offset tables from std::random_device as the
+    reference does, the harness dumps them, and the oracle replays the run with the same tables."""
+    a = synth.synth_frame("G30", 91)
+    b = synth.shifted_pair(a, 92)
+    H, W = a.shape
+    pa, pb, out = (tmp_path / n for n in ("a.bin", "b.bin", "out.bin"))
+    a.tofile(pa)
+    b.tofile(pb)
+    r = subprocess.run([os.path.join(HOST, "ref_callers"), str(pa), str(pb), str(H), str(W), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Time taken for FAST feature detection" in r.stdout and "Descriptor generation cost time" in r.stdout
+    buf = open(out, "rb").read()
+    off = 0
+    table = np.frombuffer(buf, dtype="<i4", count=1024, offset=off).reshape(256, 4)
+    off += 4096
+    feats = []
+    for _ in range(2):
+        (n,), off = _read(buf, off, "<i")
+        feats.append(np.frombuffer(buf, dtype=np.dtype([("x", "<i4"), ("y", "<i4")]), count=n, offset=off))
+        off += 8 * n
+    k1, off = _keypoints(buf, off)
+    k2, off = _keypoints(buf, off)
+    (nm,), off = _read(buf, off, "<i")
+    m = np.frombuffer(buf, dtype=np.dtype([("id1", "<i4"), ("id2", "<i4"), ("dist", "<i4")]), count=nm, offset=off)
+    off += 12 * nm
+    (nf,), off = _read(buf, off, "<i")
+    fm = np.frombuffer(buf, dtype=np.dtype([("id1", "<i4"), ("dist", "<i4")]), count=nf, offset=off)
+    off += 8 * nf
+    (cols,), off = _read(buf, off, "<i")
+    assert cols == 2 * W
+    exp = []
+    for img, f, k in ((a, feats[0], k1), (b, feats[1], k2)):
+        er, ec, _, _ = oracle.fast_detect(img, 2000)
+        assert np.array_equal(f["x"], er) and np.array_equal(f["y"], ec)
+        d, v, _ = oracle.brief(img, table, er, ec)
+        assert np.array_equal(k["id"], np.nonzero(v)[0]) and np.array_equal(k["d"], d[v])
+        exp.append((d[v], np.nonzero(v)[0]))
+    idx, dist = oracle.match(exp[0][0], exp[1][0])
+    assert nm == len(dist) and np.array_equal(m["dist"], dist) and np.array_equal(m["id2"], exp[1][1][idx])
+    keep = oracle.remove_outliers(dist, 20)
+    assert nf == int(keep.sum()) and np.array_equal(fm["dist"], dist[keep])
+    # LoopHandler::insertFrameFeatures on both frames, its own random table
+    table2 = np.frombuffer(buf, dtype="<i4", count=1024, offset=off).reshape(256, 4)
+    off += 4096
+    for img in (a, b):
+        k, off = _keypoints(buf, off)
+        er, ec, _, _ = oracle.fast_detect(img, 2000)
+        d, v, _ = oracle.brief(img, table2, er, ec)
+        assert np.array_equal(k["id"], np.nonzero(v)[0]) and np.array_equal(k["d"], d[v])
+        assert np.array_equal(k["x"], er[v]) and np.array_equal(k["y"], ec[v])
+    assert off == len(buf)
+
+
+@pytest.mark.gpu
+def test_cpp_frame_stream_matches_oracle(host_tests, oracle, offsets, tmp_path):
+    """yavo::FrameStream (ya_vo_b200/host/include/FrameStream.hpp): the C++ streaming caller over
+    yavo_submit_host_batch / yavo_wait_batch — decoder thread, batches with seam frames, per-frame callbacks in order."""
+    F = 11
+    frames = synth.synth_batch(F, "G30", 500)
+    frames[6] = synth.shifted_pair(frames[5], 3)
+    H, W = frames.shape[1:]
+    pf, po_, out = (tmp_path / n for n in ("f.bin", "off.bin", "out.bin"))
+    frames.tofile(pf)
+    offsets.astype(np.int32).tofile(po_)
+    r = subprocess.run([host_tests, "stream", str(pf), str(F), str(H), str(W), str(po_), "4", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    exp = oracle.pipeline(frames, offsets, 2000, True, nthreads=8)
+    buf = open(out, "rb").read()
+    off = 0
+    for f in range(F):
+        (fr, k), off = _read(buf, off, "<ii")
+        assert fr == f and k == exp["n_kp"][f]
+        rows = np.frombuffer(buf, "<i4", k, off); off += 4 * k
+        cols = np.frombuffer(buf, "<i4", k, off); off += 4 * k
+        desc = np.frombuffer(buf, "u1", 32 * k, off).reshape(k, 32); off += 32 * k
+        assert np.array_equal(rows, exp["rows"][f, :k]) and np.array_equal(cols, exp["cols"][f, :k])
+        assert np.array_equal(desc, exp["desc"][f, :k])
+        (kq,), off = _read(buf, off, "<i")
+        assert kq == (exp["n_kp"][f - 1] if f > 0 else 0)
+        if kq:
+            mi = np.frombuffer(buf, "<i4", kq, off); off += 4 * kq
+            md = np.frombuffer(buf, "<i4", kq, off); off += 4 * kq
+            assert np.array_equal(mi, exp["match_idx"][f, :kq]) and np.array_equal(md, exp["match_dist"][f, :kq])
+    assert off == len(buf)
+
+
+@pytest.mark.gpu
+def test_single_frame_latency_mode_and_trusted_identity(host_tests, offsets, tmp_path):
+    """host_tests latency: the reference's per-frame call shape through the drop-in classes (what bench.py reports as
+    `latency`), with the byte-for-byte residency check (default) and with YAVO_TRUST_IMAGE_IDENTITY=1."""
+    import json
+    frames = synth.synth_batch(6, "G30", 900)
+    H, W = frames.shape[1:]
+    pf, po_ = tmp_path / "f.bin", tmp_path / "off.bin"
+    frames.tofile(pf)
+    offsets.astype(np.int32).tofile(po_)
+    for env in ({}, {"YAVO_TRUST_IMAGE_IDENTITY": "1"}):
+        r = subprocess.run([host_tests, "latency", str(pf), "40", str(H), str(W), str(po_)], capture_output=True, text=True,
+                           env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout + r.stderr
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        assert d["frames"] == 40 and 1800 < d["mean_keypoints"] <= 2000 and d["getFastFeatures"]["calls"] == 40
+        assert d["computeBrief"]["p50"] < d["getFastFeatures"]["p50"]  # the descriptors came with the detection

@@ -27,7 +27,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
-    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free", "yavo_set_matcher", "yavo_set_overlap",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free", "yavo_set_matcher", "yavo_set_overlap", "yavo_frame_features", "yavo_slot_holds",
 ]
 
 
@@ -184,6 +184,23 @@ class Context:
         self._ck(self._L.yavo_fast_detect(self._h, int(slot), int(max_kp), _p(rows), _p(cols), _p(sc), C.byref(n),
                                           C.byref(nc)))
         return rows[:n.value].copy(), cols[:n.value].copy(), sc[:n.value].copy(), nc.value
+
+    def frame_features(self, slot, img, max_kp=0):
+        """getFastFeatures + computeBrief of one host frame in one call (include/yavo_b200.h: yavo_frame_features).
+        Returns dict(rows, cols, scores [n_kp]; d_rows, d_cols, d_ids [n_desc]; desc [n_desc, 32]; n_cand)."""
+        img = np.ascontiguousarray(img, np.uint8)
+        K = max_kp if max_kp > 0 else self.max_kp
+        r, c, s = np.empty(K, np.int32), np.empty(K, np.int32), np.empty(K, np.float32)
+        dr, dc, di = np.empty(K, np.int32), np.empty(K, np.int32), np.empty(K, np.int32)
+        desc = np.empty((K, 32), np.uint8)
+        n, nd, nc = C.c_int32(), C.c_int32(), C.c_int()
+        self._ck(self._L.yavo_frame_features(self._h, int(slot), _p(img), img.shape[0], img.shape[1], img.strides[0], int(max_kp),
+                                             C.byref(n), _p(r), _p(c), _p(s), C.byref(nd), _p(dr), _p(dc), _p(di), _p(desc),
+                                             C.byref(nc)))
+        self._shape[slot] = img.shape
+        n, nd = n.value, nd.value
+        return dict(rows=r[:n].copy(), cols=c[:n].copy(), scores=s[:n].copy(), d_rows=dr[:nd].copy(), d_cols=dc[:nd].copy(),
+                    d_ids=di[:nd].copy(), desc=desc[:nd].copy(), n_cand=nc.value)
 
     def fast_candidates(self, slot, cap=None):
         H, W = self._shape[slot]

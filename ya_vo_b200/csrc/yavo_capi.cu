@@ -117,6 +117,22 @@ struct yavo_ctx {
     float2 *d_trk_xy = nullptr;  // batch results, per slot max_kp
     uint8_t *d_trk_status = nullptr;
     float *d_trk_err = nullptr;
+    // single-frame path (yavo_frame_features): one CUDA graph per (slot, rows, cols, K) = upload + re-pitch + K1 + K3 + K4 +
+    // result copies, between pinned staging buffers whose addresses the graphs hold
+    struct FrameGraph {
+        int slot, rows, cols, K;
+        cudaGraphExec_t exec;
+    };
+    std::vector<FrameGraph> frame_graphs;
+    // per-slot pinned copy of the pixels yavo_frame_features uploaded (dense rows): the graph's H2D source, and what
+    // yavo_slot_holds compares a caller's pixels with
+    std::vector<uint8_t *> h_shadow;
+    std::vector<size_t> h_shadow_bytes;
+    std::vector<int> shadow_rows, shadow_cols;  // 0 = the slot's shadow does not describe its current contents
+    uint8_t *h_fout = nullptr;  // pinned: 4 ints + 6 x K ints + 32 x K bytes
+    uint32_t *d_fpack = nullptr;  // the same on the device (pack_frame_kernel)
+    uint8_t *h_mstage = nullptr;  // pinned staging of yavo_match: descriptors in, (idx, dist, second, rev) out
+    size_t h_mstage_bytes = 0;
     // optional per-kernel timing (CUDA events on the context's stream around every launch)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;
@@ -208,8 +224,14 @@ int encode_slot_map(yavo_ctx *ctx, CUtensorMap *map, void *base, int box_w, int 
 
 size_t select_smem_bytes() { return ((sizeof(SelShared) + 15) & ~size_t(15)) + sizeof(yavo_ent) * SEL_SMEM_ENTS; }
 
+void drop_frame_graphs(yavo_ctx *ctx) {
+    for (auto &g : ctx->frame_graphs) cudaGraphExecDestroy(g.exec);
+    ctx->frame_graphs.clear();
+}
+
 int ensure_stage(yavo_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->h_stage_bytes) return 0;
+    drop_frame_graphs(ctx);  // they hold the staging buffer's address
     if (ctx->h_stage) CK(cudaFreeHost(ctx->h_stage));
     ctx->h_stage = nullptr;
     ctx->h_stage_bytes = 0;
@@ -220,6 +242,7 @@ int ensure_stage(yavo_ctx *ctx, size_t bytes) {
 
 int ensure_raw(yavo_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->raw_bytes) return 0;
+    drop_frame_graphs(ctx);
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_raw) CK(cudaFree(ctx->d_raw));
     ctx->d_raw = nullptr;
@@ -250,6 +273,7 @@ int launch_repitch(yavo_ctx *ctx, const uint8_t *d_src, size_t src_pitch, int sl
         ctx->slot_cols[slot0 + i] = cols;
         ctx->slot_blur_valid[slot0 + i] = 0;
         ctx->slot_pyr[slot0 + i] = 0;
+        if (!ctx->shadow_rows.empty()) ctx->shadow_rows[slot0 + i] = 0;
     }
     return 0;
 }
@@ -622,12 +646,18 @@ void yavo_destroy(yavo_ctx *c) {
                     c->d_kp_row, c->d_kp_col,  c->d_kp_score, c->d_nkp,     c->d_bk_row,   c->d_bk_col, c->d_bk_score,
                     c->d_bk_id,  c->d_nbk,     c->d_desc,    c->d_midx,     c->d_mdist,    c->d_status, c->d_noob,
                     c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
-                    c->d_mo_idx, c->d_mo_dist, c->d_mo_sec,  c->d_part_key, c->d_part_sec, c->d_raw,
+                    c->d_mo_idx, c->d_part_key, c->d_part_sec, c->d_raw,
                     c->d_pairs,  c->d_npairs,  c->d_minDist, c->d_spos,
+                    c->d_fpack,
                     c->d_pyr,    c->d_klt_prev, c->d_klt_next, c->d_klt_status, c->d_klt_err, c->d_trk_xy,
                     c->d_trk_status, c->d_trk_err};
     for (void *b : bufs)
         if (b) cudaFree(b);
+    drop_frame_graphs(c);
+    for (uint8_t *p : c->h_shadow)
+        if (p) cudaFreeHost(p);
+    if (c->h_fout) cudaFreeHost(c->h_fout);
+    if (c->h_mstage) cudaFreeHost(c->h_mstage);
     if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->h_small) cudaFreeHost(c->h_small);
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -798,6 +828,143 @@ int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int
     return 0;
 }
 
+// One frame, one call, one synchronisation: the shape of the reference's per-frame use (LoopHandler::insertFrameFeatures,
+// src/LoopHandler.cc:468-485: getFastFeatures, then computeBrief on its points).  Upload, re-pitch, K1, K3, K4 and the
+// result copies are captured once per (slot, frame size, K) as a CUDA graph between pinned staging buffers; a call
+// packs the pixels into the staging buffer, launches the graph and waits once.
+int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows, int cols, int stride, int max_kp,
+                        int32_t *n_kp, int32_t *kp_rows, int32_t *kp_cols, float *kp_scores, int32_t *n_desc,
+                        int32_t *d_rows, int32_t *d_cols, int32_t *d_ids, uint8_t *desc, int *n_cand) {
+    if (int r = check_slot(ctx, slot)) return r;
+    if (!pixels || rows < 1 || cols < 1 || rows > ctx->max_rows || cols > ctx->max_cols || stride < cols)
+        return fail(ctx, YAVO_ERR_INVALID, "bad frame %dx%d stride %d (context max %dx%d)", rows, cols, stride, ctx->max_rows, ctx->max_cols);
+    if (max_kp <= 0) max_kp = ctx->max_kp;
+    if (max_kp > ctx->max_kp) return fail(ctx, YAVO_ERR_CAPACITY, "max_kp %d exceeds the context's %d", max_kp, ctx->max_kp);
+    if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
+    CK(cudaSetDevice(ctx->device));
+    const int K = max_kp;
+    const size_t fbytes = (size_t)rows * cols;
+    if (ctx->s_h2d) CK(cudaStreamSynchronize(ctx->s_h2d));  // the pipelined path shares d_raw
+    ctx->raw_used[0] = ctx->raw_used[1] = 0;
+    if (int r = ensure_raw(ctx, fbytes)) return r;
+    if (ctx->h_shadow.empty()) {
+        ctx->h_shadow.assign(ctx->n_slots, nullptr);
+        ctx->h_shadow_bytes.assign(ctx->n_slots, 0);
+        ctx->shadow_rows.assign(ctx->n_slots, 0);
+        ctx->shadow_cols.assign(ctx->n_slots, 0);
+    }
+    if (fbytes > ctx->h_shadow_bytes[slot]) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        // the slot's graphs hold the old buffer's address
+        for (size_t i = 0; i < ctx->frame_graphs.size();)
+            if (ctx->frame_graphs[i].slot == slot) {
+                cudaGraphExecDestroy(ctx->frame_graphs[i].exec);
+                ctx->frame_graphs.erase(ctx->frame_graphs.begin() + i);
+            } else i++;
+        if (ctx->h_shadow[slot]) CK(cudaFreeHost(ctx->h_shadow[slot]));
+        ctx->h_shadow[slot] = nullptr;
+        ctx->h_shadow_bytes[slot] = 0;
+        const size_t want = std::max(fbytes, (size_t)ctx->max_rows * ctx->max_cols);
+        CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_shadow[slot]), want));
+        ctx->h_shadow_bytes[slot] = want;
+    }
+    uint8_t *stage = ctx->h_shadow[slot];
+    const size_t out_ints = 4 + 6 * (size_t)ctx->max_kp, out_bytes = out_ints * 4 + 32 * (size_t)ctx->max_kp;
+    if (!ctx->h_fout) {
+        CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_fout), out_bytes));
+        CK(dalloc(&ctx->d_fpack, out_bytes / 4));
+    }
+    int32_t *hi = reinterpret_cast<int32_t *>(ctx->h_fout);
+    int32_t *h_kr = hi + 4, *h_kc = h_kr + ctx->max_kp, *h_br = h_kc + ctx->max_kp, *h_bc = h_br + ctx->max_kp, *h_bi = h_bc + ctx->max_kp;
+    float *h_ks = reinterpret_cast<float *>(h_bi + ctx->max_kp);
+    uint8_t *h_desc = ctx->h_fout + out_ints * 4;
+    // the previous call's graph has been waited for: the staging buffers are free
+    if (stride == cols) memcpy(stage, pixels, fbytes);
+    else
+        for (int r = 0; r < rows; r++) memcpy(stage + (size_t)r * cols, pixels + (size_t)r * stride, cols);
+    cudaGraphExec_t exec = nullptr;
+    for (auto &g : ctx->frame_graphs)
+        if (g.slot == slot && g.rows == rows && g.cols == cols && g.K == K) exec = g.exec;
+    if (!exec || ctx->profiling) {
+        const bool capture = !ctx->profiling;  // per-kernel profiling wants plain launches with event pairs
+        cudaGraph_t graph = nullptr;
+        if (capture) CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = 0;
+        do {
+            const size_t o = (size_t)slot * ctx->max_kp;
+            if (cudaMemcpyAsync(ctx->d_raw, stage, fbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = YAVO_ERR_CUDA; break; }
+            if ((rc = launch_repitch(ctx, ctx->d_raw, cols, slot, 1, rows, cols))) break;
+            if ((rc = launch_detect(ctx, slot, 1, true, true))) break;
+            if ((rc = launch_select(ctx, slot, 1, K))) break;
+            const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
+            dim3 grid((K + kp_per_block - 1) / kp_per_block, 1);
+            PROF(KC_BRIEF, brief_kernel<<<grid, K4_THREADS, 0, ctx->stream>>>(
+                               ctx->blur_map, slot, ctx->d_blur + ctx->frame_stride * slot, ctx->frame_stride, ctx->pitch, rows, cols,
+                               ctx->d_offs, ctx->d_spos, ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_nbk + slot, 0, ctx->max_kp,
+                               ctx->d_desc + o * 8, nullptr, nullptr));
+            ctx->launches++;
+            const int words = 8 * K;
+            pack_frame_kernel<<<(words + 255) / 256, 256, 0, ctx->stream>>>(
+                ctx->d_nkp + slot, ctx->d_nbk + slot, ctx->d_ncand + slot, ctx->d_status + STATUS_GENERAL, ctx->d_kp_row + o,
+                ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_bk_row + o, ctx->d_bk_col + o, ctx->d_bk_id + o, ctx->d_desc + o * 8,
+                ctx->max_kp, ctx->d_fpack);
+            ctx->launches++;
+            if (cudaMemcpyAsync(ctx->h_fout, ctx->d_fpack, out_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = YAVO_ERR_CUDA;
+        } while (0);
+        if (capture) {
+            const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+            if (rc || e != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                if (!rc) return fail(ctx, YAVO_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+                return rc;
+            }
+            const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ei != cudaSuccess) return fail(ctx, YAVO_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
+            ctx->frame_graphs.push_back({slot, rows, cols, K, exec});
+        } else if (rc) {
+            return rc;
+        }
+    } else {
+        // host-side bookkeeping the captured launch helpers did when the graph was recorded
+        ctx->slot_rows[slot] = rows;
+        ctx->slot_cols[slot] = cols;
+        ctx->slot_pyr[slot] = 0;
+        ctx->launches += 5;
+    }
+    if (exec && !ctx->profiling) CK(cudaGraphLaunch(exec, ctx->stream));
+    ctx->slot_blur_valid[slot] = 1;
+    ctx->shadow_rows[slot] = rows;
+    ctx->shadow_cols[slot] = cols;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (hi[3] != 0) {
+        CK(cudaMemsetAsync(ctx->d_status + STATUS_GENERAL, 0, sizeof(int), ctx->stream));
+        return status_error(ctx, hi[3]);
+    }
+    const int n = hi[0], nb = hi[1];
+    if (n_kp) *n_kp = n;
+    if (n_desc) *n_desc = nb;
+    if (n_cand) *n_cand = hi[2];
+    if (kp_rows) memcpy(kp_rows, h_kr, 4 * (size_t)n);
+    if (kp_cols) memcpy(kp_cols, h_kc, 4 * (size_t)n);
+    if (kp_scores) memcpy(kp_scores, h_ks, 4 * (size_t)n);
+    if (d_rows) memcpy(d_rows, h_br, 4 * (size_t)nb);
+    if (d_cols) memcpy(d_cols, h_bc, 4 * (size_t)nb);
+    if (d_ids) memcpy(d_ids, h_bi, 4 * (size_t)nb);
+    if (desc) memcpy(desc, h_desc, 32 * (size_t)nb);
+    return 0;
+}
+
+int yavo_slot_holds(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows, int cols, int stride) {
+    if (!ctx || slot < 0 || slot >= ctx->n_slots || !pixels || stride < cols) return YAVO_ERR_INVALID;
+    if (ctx->shadow_rows.empty() || ctx->shadow_rows[slot] != rows || ctx->shadow_cols[slot] != cols || rows < 1) return 0;
+    const uint8_t *sh = ctx->h_shadow[slot];
+    if (stride == cols) return memcmp(sh, pixels, (size_t)rows * cols) == 0 ? 1 : 0;
+    for (int r = 0; r < rows; r++)
+        if (memcmp(sh + (size_t)r * cols, pixels + (size_t)r * stride, cols) != 0) return 0;
+    return 1;
+}
+
 // ---- Brief ----------------------------------------------------------------------------------------
 
 int yavo_set_brief_offsets(yavo_ctx *ctx, const int32_t *offsets) {
@@ -940,49 +1107,73 @@ int yavo_match(yavo_ctx *ctx, const uint8_t *d1, int n1, const uint8_t *d2, int 
         return fail(ctx, YAVO_ERR_INVALID, "bad descriptor sets");
     if (n1 >= (1 << 22) || n2 >= (1 << 22)) return fail(ctx, YAVO_ERR_CAPACITY, "descriptor sets are limited to 2^22-1");
     CK(cudaSetDevice(ctx->device));
-    if (n1 > ctx->mq_cap) {
+    // device buffers and the pinned staging block are kept between calls and only ever grow (the reference matches one
+    // pair of ~2000-keypoint frames per call, src/LoopHandler.cc:189,534): a call is two H2D copies, the kernel(s), one
+    // D2H copy and ONE synchronisation
+    if (n1 > ctx->mq_cap || n2 > ctx->mt_cap || std::max(n1, n2) > ctx->mo_cap) {
         CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_mq) CK(cudaFree(ctx->d_mq));
-        ctx->d_mq = nullptr; ctx->mq_cap = 0;
-        CK(dalloc(&ctx->d_mq, (size_t)n1 * 8));
-        ctx->mq_cap = n1;
+        if (n1 > ctx->mq_cap) {
+            if (ctx->d_mq) CK(cudaFree(ctx->d_mq));
+            ctx->d_mq = nullptr; ctx->mq_cap = 0;
+            const int cap = std::max(n1, 4096);
+            CK(dalloc(&ctx->d_mq, (size_t)cap * 8));
+            ctx->mq_cap = cap;
+        }
+        if (n2 > ctx->mt_cap) {
+            if (ctx->d_mt) CK(cudaFree(ctx->d_mt));
+            ctx->d_mt = nullptr; ctx->mt_cap = 0;
+            const int cap = std::max(n2, 4096);
+            CK(dalloc(&ctx->d_mt, (size_t)cap * 8));
+            ctx->mt_cap = cap;
+        }
+        const int mo = std::max(n1, n2);
+        if (mo > ctx->mo_cap) {
+            if (ctx->d_mo_idx) CK(cudaFree(ctx->d_mo_idx));
+            ctx->d_mo_idx = ctx->d_mo_dist = ctx->d_mo_sec = nullptr; ctx->mo_cap = 0;
+            const int cap = std::max(mo, 4096);
+            CK(dalloc(&ctx->d_mo_idx, (size_t)cap * 5));  // idx | dist | second | reverse idx | reverse dist, contiguous
+            ctx->d_mo_dist = ctx->d_mo_idx + cap;
+            ctx->d_mo_sec = ctx->d_mo_idx + 2 * (size_t)cap;
+            ctx->mo_cap = cap;
+        }
     }
-    if (n2 > ctx->mt_cap) {
+    const size_t cap = ctx->mo_cap;
+    int32_t *d_rev = ctx->d_mo_idx + 3 * cap, *d_rev_dist = ctx->d_mo_idx + 4 * cap;
+    const size_t in_bytes = 32 * ((size_t)n1 + n2), out_bytes = 4 * 4 * cap, need = in_bytes + out_bytes;
+    if (need > ctx->h_mstage_bytes) {
         CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_mt) CK(cudaFree(ctx->d_mt));
-        ctx->d_mt = nullptr; ctx->mt_cap = 0;
-        CK(dalloc(&ctx->d_mt, (size_t)n2 * 8));
-        ctx->mt_cap = n2;
+        if (ctx->h_mstage) CK(cudaFreeHost(ctx->h_mstage));
+        ctx->h_mstage = nullptr;
+        ctx->h_mstage_bytes = 0;
+        const size_t want = std::max(need, (size_t)(32 * 2 * 4096 + 4 * 4 * 4096));
+        CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_mstage), want));
+        ctx->h_mstage_bytes = want;
     }
-    const int mo = std::max(n1, n2);
-    if (mo > ctx->mo_cap) {
-        CK(cudaStreamSynchronize(ctx->stream));
-        if (ctx->d_mo_idx) CK(cudaFree(ctx->d_mo_idx));
-        if (ctx->d_mo_dist) CK(cudaFree(ctx->d_mo_dist));
-        if (ctx->d_mo_sec) CK(cudaFree(ctx->d_mo_sec));
-        ctx->d_mo_idx = ctx->d_mo_dist = ctx->d_mo_sec = nullptr; ctx->mo_cap = 0;
-        CK(dalloc(&ctx->d_mo_idx, mo));
-        CK(dalloc(&ctx->d_mo_dist, mo));
-        CK(dalloc(&ctx->d_mo_sec, mo));
-        ctx->mo_cap = mo;
-    }
-    if (n1 > 0) CK(cudaMemcpyAsync(ctx->d_mq, d1, 32 * (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
-    if (n2 > 0) CK(cudaMemcpyAsync(ctx->d_mt, d2, 32 * (size_t)n2, cudaMemcpyHostToDevice, ctx->stream));
-    if (n1 > 0) {
+    uint8_t *h_in = ctx->h_mstage;
+    int32_t *h_out = reinterpret_cast<int32_t *>(ctx->h_mstage + ctx->h_mstage_bytes - out_bytes);  // the tail of the block
+    if (n1 > 0) memcpy(h_in, d1, 32 * (size_t)n1);
+    if (n2 > 0) memcpy(h_in + 32 * (size_t)n1, d2, 32 * (size_t)n2);
+    if (n1 > 0) CK(cudaMemcpyAsync(ctx->d_mq, h_in, 32 * (size_t)n1, cudaMemcpyHostToDevice, ctx->stream));
+    if (n2 > 0) CK(cudaMemcpyAsync(ctx->d_mt, h_in + 32 * (size_t)n1, 32 * (size_t)n2, cudaMemcpyHostToDevice, ctx->stream));
+    if (n1 > 0)
         if (int r = match_device(ctx, ctx->d_mq, n1, ctx->d_mt, n2, ctx->d_mo_idx, ctx->d_mo_dist,
                                  out_second ? ctx->d_mo_sec : nullptr))
             return r;
-        CK(cudaMemcpyAsync(out_idx, ctx->d_mo_idx, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(out_dist, ctx->d_mo_dist, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
-        if (out_second) CK(cudaMemcpyAsync(out_second, ctx->d_mo_sec, 4 * (size_t)n1, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+    const bool rev = out_rev_idx && n2 > 0;
+    if (rev) {
+        // cross-check extension: the same kernel with the roles swapped (a second pass over the N1 x N2 distances on the
+        // tensor pipe; the operands are already on the device)
+        if (int r = match_device(ctx, ctx->d_mt, n2, ctx->d_mq, n1, d_rev, d_rev_dist, nullptr)) return r;
     }
-    if (out_rev_idx && n2 > 0) {
-        // cross-check extension: the same kernel with the roles swapped
-        if (int r = match_device(ctx, ctx->d_mt, n2, ctx->d_mq, n1, ctx->d_mo_idx, ctx->d_mo_dist, nullptr)) return r;
-        CK(cudaMemcpyAsync(out_rev_idx, ctx->d_mo_idx, 4 * (size_t)n2, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+    // one copy back: [idx | dist | second | reverse idx] x cap
+    if (n1 > 0 || rev) CK(cudaMemcpyAsync(h_out, ctx->d_mo_idx, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n1 > 0) {
+        memcpy(out_idx, h_out, 4 * (size_t)n1);
+        memcpy(out_dist, h_out + cap, 4 * (size_t)n1);
+        if (out_second) memcpy(out_second, h_out + 2 * cap, 4 * (size_t)n1);
     }
+    if (rev) memcpy(out_rev_idx, h_out + 3 * cap, 4 * (size_t)n2);
     return 0;
 }
 

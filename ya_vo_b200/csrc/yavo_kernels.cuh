@@ -1145,6 +1145,41 @@ brief_kernel(const __grid_constant__ CUtensorMap blur_map, int slot_base,
 }
 
 // ================================================================================================
+// K4b  result pack of the single-frame path: everything a caller of getFastFeatures + computeBrief reads back, gathered
+// into one contiguous buffer so that it crosses PCIe as ONE copy:
+//   [n_kp, n_desc, n_cand, status | kp_row[K] | kp_col[K] | bk_row[K] | bk_col[K] | bk_id[K] | kp_score[K] | desc[8K words]]
+// ================================================================================================
+__global__ void pack_frame_kernel(const int *__restrict__ nkp, const int *__restrict__ nbk, const int *__restrict__ ncand,
+                                  const int *__restrict__ status, const int32_t *__restrict__ kp_row,
+                                  const int32_t *__restrict__ kp_col, const float *__restrict__ kp_score,
+                                  const int32_t *__restrict__ bk_row, const int32_t *__restrict__ bk_col,
+                                  const int32_t *__restrict__ bk_id, const uint32_t *__restrict__ desc, int K,
+                                  uint32_t *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        out[0] = (uint32_t)nkp[0];
+        out[1] = (uint32_t)nbk[0];
+        out[2] = (uint32_t)ncand[0];
+        out[3] = (uint32_t)status[0];
+    }
+    const int n = nkp[0], nb = nbk[0];
+    uint32_t *o = out + 4;
+    if (i < K) {
+        if (i < n) {
+            o[i] = (uint32_t)kp_row[i];
+            o[K + i] = (uint32_t)kp_col[i];
+            o[5 * K + i] = __float_as_uint(kp_score[i]);
+        }
+        if (i < nb) {
+            o[2 * K + i] = (uint32_t)bk_row[i];
+            o[3 * K + i] = (uint32_t)bk_col[i];
+            o[4 * K + i] = (uint32_t)bk_id[i];
+        }
+    }
+    if (i < 8 * K && i < 8 * nb) o[6 * K + i] = desc[i];
+}
+
+// ================================================================================================
 // K5  Hamming match  (reference src/BriefDescriptor.cc:139-183)
 // Brute force over 256-bit descriptors held as 8 x u32.  A CTA owns MQ queries (one per thread,
 // descriptor in registers) and one chunk of the train set, staged through shared memory in tiles

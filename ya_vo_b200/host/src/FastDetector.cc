@@ -19,14 +19,58 @@ std::vector<cv::Point> FastDetector::getFastFeatures(const Image &img) {
     const auto t1 = std::chrono::steady_clock::now();
     Device &dev = Device::instance(img.getH(), img.getW());
     std::lock_guard<std::mutex> lk(dev.mutex());
-    const int slot = dev.slotFor(img);
     const int cap = std::min(fastCornerNumThreshold > 0 ? fastCornerNumThreshold : Device::kMaxKeypoints,
                              (int)Device::kMaxKeypoints);
-    std::vector<int32_t> rows(cap), cols(cap);
-    lastScores_.assign(cap, 0.f);
+    std::vector<int32_t> rows, cols;
     int n = 0, ncand = 0;
-    dev.check(yavo_fast_detect(dev.ctx(), slot, cap, rows.data(), cols.data(), lastScores_.data(), &n, &ncand));
-    lastScores_.resize(n);
+    int slot = dev.findSlot(img);
+    if (slot >= 0 && dev.features(slot).valid && dev.features(slot).cap == cap) {
+        // the same pixels were detected before (same Image, untouched): the answer is on the host already
+        const Device::Features &f = dev.features(slot);
+        rows = f.rows;
+        cols = f.cols;
+        lastScores_ = f.scores;
+        n = (int)rows.size();
+        ncand = f.n_cand;
+    } else if (dev.hasBriefOffsets()) {
+        // One graph launch and one synchronisation for the reference's per-frame sequence (src/LoopHandler.cc:468-485:
+        // getFastFeatures, then computeBrief on its points): upload, detect + score + blur, exact top-K, BRIEF of the
+        // admitted points.  The descriptors stay with the slot record; Brief::computeBrief picks them up when it is
+        // handed these very points.
+        slot = dev.claimSlot(img);
+        Device::Features &f = dev.features(slot);
+        f.rows.assign(cap, 0);
+        f.cols.assign(cap, 0);
+        f.scores.assign(cap, 0.f);
+        f.ids.assign(cap, 0);
+        f.desc.assign((size_t)cap * 32, 0);
+        std::vector<int32_t> brows(cap), bcols(cap);
+        int nb = 0;
+        const cv::Mat &m = img.rawImage;
+        dev.check(yavo_frame_features(dev.ctx(), slot, m.data, m.rows, m.cols, (int)m.step, cap, &n, f.rows.data(), f.cols.data(),
+                                      f.scores.data(), &nb, brows.data(), bcols.data(), f.ids.data(), f.desc.data(), &ncand));
+        f.rows.resize(n);
+        f.cols.resize(n);
+        f.scores.resize(n);
+        f.ids.resize(nb);
+        f.desc.resize((size_t)nb * 32);
+        f.cap = cap;
+        f.n_cand = ncand;
+        f.offsets_epoch = dev.offsetsEpoch();
+        f.valid = true;
+        dev.markShadow(slot);
+        rows = f.rows;
+        cols = f.cols;
+        lastScores_ = f.scores;
+    } else {
+        // no BRIEF table on the device yet (no Brief::computeBrief has run): detect only
+        slot = dev.slotFor(img);
+        rows.assign(cap, 0);
+        cols.assign(cap, 0);
+        lastScores_.assign(cap, 0.f);
+        dev.check(yavo_fast_detect(dev.ctx(), slot, cap, rows.data(), cols.data(), lastScores_.data(), &n, &ncand));
+        lastScores_.resize(n);
+    }
     lastCandidates_ = ncand;
     std::vector<cv::Point> out;
     out.reserve(n);
@@ -69,9 +113,9 @@ bool FastDetector::checkContiguousPixels(uint8_t centPixel, const std::vector<cv
     return false;
 }
 
-void FastDetector::putPixel(Image &img, cv::Point pt) { img.rawImage.at<uint8_t>(pt) = 255; }
-void FastDetector::putPixel(Image &img, cv::Point pt, uint8_t pixVal) { img.rawImage.at<uint8_t>(pt) = pixVal; }
-void FastDetector::putPixelColor(Image &img, cv::Point pt) { img.rawImage.at<cv::Vec3b>(pt) = cv::Vec3b(255, 255, 0); }
+void FastDetector::putPixel(Image &img, cv::Point pt) { img.rawImage.at<uint8_t>(pt) = 255; img.touch(); }
+void FastDetector::putPixel(Image &img, cv::Point pt, uint8_t pixVal) { img.rawImage.at<uint8_t>(pt) = pixVal; img.touch(); }
+void FastDetector::putPixelColor(Image &img, cv::Point pt) { img.rawImage.at<cv::Vec3b>(pt) = cv::Vec3b(255, 255, 0); img.touch(); }
 
 void FastDetector::convolve2d(const Image &img, cv::Mat &kernel, cv::Mat &output) {
     // float correlation with a zero border; writes output(r, c) for r <= rows-1-2h, c <= cols-1-2h only,

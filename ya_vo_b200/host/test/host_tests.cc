@@ -18,8 +18,11 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "../include/BriefDescriptor.hpp"
 #include "../include/FastDetector.hpp"
+#include "../include/FrameStream.hpp"
 #include "../include/Tracking.hpp"
 #include "../include/Image.hpp"
 #include "../include/yavo_device.hpp"
@@ -242,8 +245,116 @@ static int track(char **a) {
     return g_fail ? 1 : 0;
 }
 
+// The call shape the reference really uses, timed: ONE frame at a time through FastDetector::getFastFeatures ->
+// Brief::computeBrief (LoopHandler::insertFrameFeatures, src/LoopHandler.cc:468-485) and Brief::matchFeatures on
+// consecutive frames (src/LoopHandler.cc:189,534; tests/BriefDescriptorTest.cc:21-44).  Every frame is a fresh Image, as
+// getNextFrame builds it (src/LoopHandler.cc:917-927).  Prints one JSON object: microseconds per call, p50 / p99 / mean.
+static int latency(char **a) {
+    const int n = std::atoi(a[1]), H = std::atoi(a[2]), W = std::atoi(a[3]);
+    std::vector<uint8_t> F = slurp(a[0]), O = slurp(a[4]);
+    const size_t fb = (size_t)H * W;
+    if (n < 2 || F.size() < fb * 2 || O.size() != 1024 * 4) { std::printf("bad inputs\n"); return 2; }
+    const int distinct = (int)(F.size() / fb);
+    std::vector<std::vector<int>> table(256, std::vector<int>(4));
+    const int32_t *o = reinterpret_cast<const int32_t *>(O.data());
+    for (int j = 0; j < 256; j++) for (int k = 0; k < 4; k++) table[j][k] = o[4 * j + k];
+    Brief brief(256);
+    brief.setOffsets(table);
+    FastDetector fd(12, 50);
+    typedef std::chrono::steady_clock clk;
+    auto us = [](clk::time_point t0, clk::time_point t1) { return std::chrono::duration<double, std::micro>(t1 - t0).count(); };
+    std::vector<double> t_fast, t_brief, t_match, t_frame, t_image;
+    std::unique_ptr<Image> prev;
+    size_t kp_total = 0, kept_total = 0;
+    for (int i = -8; i < n; i++) {  // 8 untimed frames first: context creation, graph capture, first launches
+        cv::Mat m(H, W, CV_8UC1, F.data() + (size_t)((i + 8) % distinct) * fb);
+        const auto t0 = clk::now();
+        std::unique_ptr<Image> cur(new Image(m));  // deep copy, like Frame(img) in getNextFrame
+        const auto t1 = clk::now();
+        auto features = fd.getFastFeatures(*cur);
+        const auto t2 = clk::now();
+        brief.computeBrief(features, *cur);
+        const auto t3 = clk::now();
+        double tm = 0;
+        if (prev) {
+            std::vector<Matches> matches = brief.matchFeatures(*prev, *cur);
+            const auto t4 = clk::now();
+            std::vector<Matches> kept;
+            brief.removeOutliers(matches, kept, 20);
+            tm = us(t3, t4);
+            if (i >= 0) kept_total += kept.size();
+        }
+        if (i >= 0) {
+            t_fast.push_back(us(t1, t2));
+            t_brief.push_back(us(t2, t3));
+            if (prev) t_match.push_back(tm);
+            t_frame.push_back(us(t1, t3));
+            t_image.push_back(us(t0, t1));
+            kp_total += cur->keypoints.size();
+        }
+        prev = std::move(cur);
+    }
+    auto stat = [](std::vector<double> v, const char *name) {
+        std::sort(v.begin(), v.end());
+        double mean = 0;
+        for (double x : v) mean += x;
+        mean /= std::max<size_t>(v.size(), 1);
+        std::printf("\"%s\": {\"p50\": %.1f, \"p99\": %.1f, \"mean\": %.1f, \"min\": %.1f, \"calls\": %zu}", name, v[v.size() / 2],
+                    v[std::min(v.size() - 1, (size_t)(v.size() * 0.99))], mean, v[0], v.size());
+    };
+    std::printf("{\"unit\": \"us per call\", \"frames\": %d, \"frame\": [%d, %d], \"mean_keypoints\": %.1f, \"mean_kept_matches\": %.1f, ", n, H, W,
+                (double)kp_total / n, (double)kept_total / std::max(n - 1, 1));
+    stat(t_fast, "getFastFeatures");
+    std::printf(", ");
+    stat(t_brief, "computeBrief");
+    std::printf(", ");
+    stat(t_match, "matchFeatures");
+    std::printf(", ");
+    stat(t_frame, "getFastFeatures+computeBrief");
+    std::printf(", ");
+    stat(t_image, "Image(cv::Mat) deep copy (host only, src/Image.cc:8-13)");
+    std::printf("}\n");
+    yavo_host::Device::shutdown();
+    return 0;
+}
+
+// yavo::FrameStream (include/FrameStream.hpp) over a sequence held in one file: per-frame results dumped for the pytest side
+static int stream_mode(char **a) {
+    const int n = std::atoi(a[1]), H = std::atoi(a[2]), W = std::atoi(a[3]), batch = std::atoi(a[5]);
+    std::vector<uint8_t> F = slurp(a[0]), O = slurp(a[4]);
+    const size_t fb = (size_t)H * W;
+    if (F.size() != fb * n || O.size() != 1024 * 4) { std::printf("bad inputs\n"); return 2; }
+    std::ofstream f(a[6], std::ios::binary);
+    int seen = 0, next = 0;
+    yavo::FrameStream fs(0, n, H, W, batch, reinterpret_cast<const int32_t *>(O.data()), 2000, 2);
+    const int delivered = fs.run(
+        [&](int frame, uint8_t *dst) { std::memcpy(dst, F.data() + (size_t)frame * fb, fb); },
+        [&](const yavo::FrameResult &r) {
+            EXPECT_EQ(r.frame, next);  // in order, each frame once
+            next++;
+            seen++;
+            put<int32_t>(f, r.frame);
+            put<int32_t>(f, r.n_kp);
+            f.write((const char *)r.rows, 4 * (size_t)r.n_kp);
+            f.write((const char *)r.cols, 4 * (size_t)r.n_kp);
+            f.write((const char *)r.desc, 32 * (size_t)r.n_kp);
+            put<int32_t>(f, r.n_prev);
+            if (r.n_prev) {
+                f.write((const char *)r.match_idx, 4 * (size_t)r.n_prev);
+                f.write((const char *)r.match_dist, 4 * (size_t)r.n_prev);
+            }
+        });
+    EXPECT_EQ(delivered, n);
+    EXPECT_EQ(seen, n);
+    f.close();
+    std::printf("stream: %d frames in batches of %d (%d failures)\n", delivered, batch, g_fail);
+    return g_fail ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
     try {
+        if (argc == 7 && !std::strcmp(argv[1], "latency")) return latency(argv + 2);
+        if (argc == 9 && !std::strcmp(argv[1], "stream")) return stream_mode(argv + 2);
         if (argc == 3 && !std::strcmp(argv[1], "known")) return known(argv[2]);
         if (argc == 8 && !std::strcmp(argv[1], "pipeline")) return pipeline(argv + 2);
         if (argc == 7 && !std::strcmp(argv[1], "track")) return track(argv + 2);
@@ -251,6 +362,7 @@ int main(int argc, char **argv) {
         std::printf("exception: %s\n", e.what());
         return 3;
     }
-    std::printf("usage: host_tests known <bres.bin> | pipeline <A.bin> <B.bin> <H> <W> <offsets.bin> <out.bin> | track <A.bin> <B.bin> <H> <W> <out.bin>\n");
+    std::printf("usage: host_tests known <bres.bin> | pipeline <A.bin> <B.bin> <H> <W> <offsets.bin> <out.bin> | track <A.bin> <B.bin> <H> <W> <out.bin>\n"
+                "       | latency <frames.bin> <n> <H> <W> <offsets.bin> | stream <frames.bin> <n> <H> <W> <offsets.bin> <batch> <out.bin>\n");
     return 2;
 }
