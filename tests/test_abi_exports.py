@@ -29,10 +29,16 @@ def test_header_cites_reference_interfaces(cuda_lib):
         assert cite in txt
 
 
-def test_sass_is_sm100a_without_tensor_ops(cuda_lib):
+def test_library_is_sm100a_and_blackwell_native(cuda_lib):
+    """The shipped library holds sm_100a code only, and its SASS shows what the design claims: tcgen05 tensor-core
+    instructions with TMEM loads / stores (the matcher), tensor copies (TMA: the detect kernel's tile, the BRIEF kernel's
+    patches) and bulk copies."""
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", cuda_lib.LIB_PATH], capture_output=True, text=True).stdout
-    assert "sm_100a" in out
+    assert "sm_100a" in out and "sm_90" not in out
+    sass = subprocess.run(["cuobjdump", "-sass", cuda_lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCQMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP"):
+        assert mnemonic in sass, mnemonic
 
 
 def test_no_cpu_fallback_without_device(cuda_lib):

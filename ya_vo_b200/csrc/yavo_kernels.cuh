@@ -449,7 +449,7 @@ gather_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, in
 // single lane (never reached on real score lists; kept for exactness).
 // ================================================================================================
 #ifndef YAVO_SEL_THREADS
-#define YAVO_SEL_THREADS 512
+#define YAVO_SEL_THREADS 384  // measured on B200 (round 2, scores arriving from K1): 384 x 2 CTAs/SM 0.386 ms per 1024 frames, 512 x 2 0.398, 256 x 3 0.424, 256 x 4 0.433
 #endif
 #ifndef YAVO_SEL_SLEEP
 #define YAVO_SEL_SLEEP 64
@@ -1035,7 +1035,10 @@ constexpr int BP_ROWB = 48;              // bytes per staged patch row: the tens
 constexpr int BP_ROWS = 17;              // rows row-8 .. row+8
 constexpr int BP_BYTES = BP_ROWS * BP_ROWB;                  // 816 bytes arrive per patch
 constexpr int BP_ENTRY = (BP_BYTES + 127) & ~127;            // ring entries are 128-byte aligned (tensor-copy destination)
-constexpr int BP_KPW = 8;                // keypoints per warp
+#ifndef YAVO_BP_KPW
+#define YAVO_BP_KPW 8
+#endif
+constexpr int BP_KPW = YAVO_BP_KPW;      // keypoints per warp
 constexpr int BP_D = 4;                  // patches in flight per warp (ring of tensor copies)
 
 // The patch of an interior keypoint arrives by ONE tensor copy (TMA: box of 48 x 17 bytes at ((col-8) & ~15, row-8) of
