@@ -154,3 +154,29 @@ def test_second_best_from_the_tensor_core_epilogue(cuda_lib, oracle, n1, n2):
     assert np.array_equal(sec, esec)
     assert np.array_equal(rev, erev)
     assert kl <= 2  # forward (with second) + reverse: no integer-pipe fallback, no reduce kernels
+
+
+@pytest.mark.parametrize("kind,seed,H,W,K,min_n", [("U", 3, 376, 1241, 2000, 2048), ("U", 4, 376, 1241, 2000, 8192),
+                                                    ("B4", 5, 376, 1241, 2000, 1024), ("G30", 6, 376, 1241, 500, 512),
+                                                    ("U", 7, 200, 333, 3000, 700)])
+def test_cluster_prepartition_of_large_lists_is_exact(cuda_lib, oracle, kind, seed, H, W, K, min_n):
+    """select_big_kernel: the top of the std::sort replay on a thread-block cluster (8 CTAs per frame), forced onto
+    moderate frames by lowering the candidate threshold; order, ties and scores must still be the oracle's, for single
+    frames and inside a batch."""
+    frames = synth.synth_batch(3, kind, seed, H, W)
+    with cuda_lib.Context(device=0, n_slots=3, max_rows=H, max_cols=W, max_kp=K) as ctx:
+        ctx.set_big_select(min_n)
+        for f in range(3):
+            ctx.upload(f, frames[f])
+            r, c, s, nc = ctx.fast_detect(f, K)
+            er, ec, es, enc = oracle.fast_detect(frames[f], K)
+            assert nc == enc and nc > min_n
+            assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
+        ctx.set_brief_offsets(synth.brief_offsets())
+        ctx.upload_batch(0, frames)
+        ctx.frontend_batch(0, 3, True)
+        on = ctx.fetch_batch(0, 3)
+        ctx.set_big_select(0)
+        ctx.frontend_batch(0, 3, True)
+        off = ctx.fetch_batch(0, 3)
+    _same_results(on, off, 3)

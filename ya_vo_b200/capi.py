@@ -27,7 +27,7 @@ EXPORTS = [
     "yavo_set_brief_offsets", "yavo_blurred", "yavo_brief_describe",
     "yavo_match", "yavo_remove_outliers",
     "yavo_frontend_batch", "yavo_fetch_batch", "yavo_process_host_batch", "yavo_submit_host_batch", "yavo_wait", "yavo_wait_batch", "yavo_filter_pairs", "yavo_set_pipeline_chunk", "yavo_set_sub_batch",
-    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free", "yavo_set_matcher", "yavo_set_overlap", "yavo_frame_features", "yavo_slot_holds",
+    "yavo_build_pyramid", "yavo_pyramid_level", "yavo_klt_track", "yavo_klt_track_batch", "yavo_klt_fetch", "yavo_epipolar_inliers", "yavo_stream_tracking", "yavo_stream_track_outputs", "yavo_pinned_alloc", "yavo_pinned_free", "yavo_set_matcher", "yavo_set_overlap", "yavo_frame_features", "yavo_slot_holds", "yavo_set_big_select",
 ]
 
 
@@ -294,6 +294,10 @@ class Context:
     def set_overlap(self, chunk_frames, n_streams=3):
         """Overlapped feature pipeline of the batch entry points (include/yavo_b200.h: yavo_set_overlap); 0 = serial."""
         self._ck(self._L.yavo_set_overlap(self._h, int(chunk_frames), int(n_streams)))
+
+    def set_big_select(self, min_candidates):
+        """Cluster pre-partition of large candidate lists (include/yavo_b200.h: yavo_set_big_select); -1 auto, 0 off."""
+        self._ck(self._L.yavo_set_big_select(self._h, int(min_candidates)))
 
     def set_sub_batch(self, frames):
         self._ck(self._L.yavo_set_sub_batch(self._h, int(frames)))

@@ -48,6 +48,10 @@ struct yavo_ctx {
     yavo_ent *d_cand = nullptr;  // per slot max_cand: the select kernel's sort buffer when the list exceeds its shared memory
     int *d_ncand = nullptr;
     uint32_t *d_scratch = nullptr;
+    // cluster pre-partition of large candidate lists (select_big_kernel): exchange block, handed-over ranges, their count
+    int *d_xchg = nullptr, *d_npre = nullptr;
+    SelRange *d_pre = nullptr;
+    int big_min = -1;  // candidates above which a frame's list takes the cluster path; 0 = never, -1 = automatic (16384, frames >= 2 Mpx)
     int32_t *d_kp_row = nullptr, *d_kp_col = nullptr;
     float *d_kp_score = nullptr;
     int *d_nkp = nullptr;
@@ -346,13 +350,26 @@ int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
 int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t o = (size_t)slot0 * ctx->max_kp;
+    // large lists (4K frames: 300 k candidates): the top of the partition tree runs on a thread-block cluster per frame
+    const int big_min = ctx->big_min > 0 ? ctx->big_min : (ctx->big_min < 0 && (long long)H * W >= 2000000 ? 16384 : 0);
+    const bool big = big_min > 0 && ctx->max_cand > big_min;
+    if (big) {
+        CK(cudaMemsetAsync(ctx->d_npre + slot0, 0, sizeof(int) * (size_t)n, ctx->ls));
+        PROF(KC_SELECT, select_big_kernel<<<n * BIG_CL, BIG_THREADS, 0, ctx->ls>>>(
+            ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW,
+            ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
+            ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), ctx->d_xchg + (size_t)slot0 * BIG_XCHG, K, H, big_min,
+            ctx->d_pre + (size_t)slot0 * BIG_PRE, ctx->d_npre + slot0));
+        CK_LAUNCH();
+    }
     PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->ls>>>(
         ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW,
         ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
         ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp,
         ctx->d_kp_row + o,
         ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
-        ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->cur_status));
+        ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->cur_status,
+        big ? ctx->d_pre + (size_t)slot0 * BIG_PRE : nullptr, big ? ctx->d_npre + slot0 : nullptr));
     CK_LAUNCH();
     return 0;
 }
@@ -595,6 +612,10 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_cand, S * c->max_cand));
     CKC(dalloc(&c->d_ncand, S));
     CKC(dalloc(&c->d_scratch, S * (c->max_cand + 4)));
+    CKC(dalloc(&c->d_xchg, S * BIG_XCHG));
+    CKC(dalloc(&c->d_pre, S * BIG_PRE));
+    CKC(dalloc(&c->d_npre, S));
+    CKC(cudaMemset(c->d_npre, 0, S * sizeof(int)));
     CKC(dalloc(&c->d_kp_row, S * max_kp));
     CKC(dalloc(&c->d_kp_col, S * max_kp));
     CKC(dalloc(&c->d_kp_score, S * max_kp));
@@ -648,7 +669,7 @@ void yavo_destroy(yavo_ctx *c) {
                     c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
                     c->d_mo_idx, c->d_part_key, c->d_part_sec, c->d_raw,
                     c->d_pairs,  c->d_npairs,  c->d_minDist, c->d_spos,
-                    c->d_fpack,
+                    c->d_fpack,  c->d_xchg,    c->d_pre,     c->d_npre,
                     c->d_pyr,    c->d_klt_prev, c->d_klt_next, c->d_klt_status, c->d_klt_err, c->d_trk_xy,
                     c->d_trk_status, c->d_trk_err};
     for (void *b : bufs)
@@ -1537,6 +1558,13 @@ int yavo_set_overlap(yavo_ctx *ctx, int chunk_frames, int n_streams) {
     if (!ctx || chunk_frames < 0 || n_streams < 1 || n_streams > yavo_ctx::MAX_AUX) return YAVO_ERR_INVALID;
     ctx->ov_chunk = chunk_frames;
     ctx->ov_streams = n_streams;
+    return 0;
+}
+
+int yavo_set_big_select(yavo_ctx *ctx, int min_candidates) {
+    if (!ctx || min_candidates < -1) return YAVO_ERR_INVALID;
+    ctx->big_min = min_candidates;
+    drop_frame_graphs(ctx);  // captured launches were made with the old setting
     return 0;
 }
 

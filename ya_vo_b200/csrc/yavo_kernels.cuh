@@ -4,6 +4,7 @@
 // match_tc.cuh.  See DESIGN.md for the data layout and the roofline that bounds each kernel.
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -823,6 +824,266 @@ __device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
     }
 }
 
+// ================================================================================================
+// K3a  the top of the partition tree of a LARGE candidate list, on a thread-block cluster
+// One CTA per frame is the right shape for KITTI-size frames (5 k candidates, hundreds of frames in flight); a 4K frame
+// has 300 k candidates and a batch only a handful of frames, so its first partitions — which scan hundreds of
+// thousands of elements in global memory — are spread over the BIG_CL CTAs of a cluster (one cluster per frame):
+//   gather  every CTA takes a slice of the segment table; slice totals are exchanged, then each copies its slice
+//   per partition of a range [f, l):  (the same parallel form of __unguarded_partition as sel_block_partition)
+//     rank 0: median-of-three to the front                                                     | cluster barrier
+//     pass 1: every CTA counts the left / right stoppers of its slice of the scan index range  | cluster barrier
+//     pass 2: ... and scatters their positions at [slice base + rank] into the stopper lists   | cluster barrier
+//     swaps: pair k (k-th left stopper, k-th right stopper) while L_k < R_k, spread over all threads; swap count
+//                                                                                              | cluster barrier
+//     cut = min(L_m, R_{m-1}); children above BIG_MIN elements go to the next level, the others (that start below K)
+//     are handed to the select kernel, which continues from this partially partitioned state.
+// Counts travel through a small global exchange block: the cluster barrier (release / acquire at cluster scope)
+// orders them, and the 8 CTAs of a cluster are co-scheduled by construction, so the barrier cannot deadlock.
+// ================================================================================================
+constexpr int BIG_CL = 8;          // CTAs per cluster (portable maximum)
+constexpr int BIG_THREADS = 512;
+constexpr int BIG_ITEMS = 8;
+constexpr int BIG_PRE = 64;        // ranges handed to the select kernel per frame
+constexpr int BIG_XCHG = 4 * BIG_CL;  // ints per frame in the exchange block: cntL | cntR | swaps | gather totals
+
+struct BigShared {
+    int wtot[BIG_THREADS / 32];
+    SelRange lvl[2][SEL_BIG];
+    int nlvl[2];
+    int bc[2];
+};
+
+// block-wide exclusive scan of a packed (low 16 bits | high 16 bits) per-thread count; returns this thread's exclusive
+// prefix and the block total (both packed)
+__device__ __forceinline__ void big_block_scan(BigShared &S, int packed, int *excl, int *total) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int incl = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    __syncthreads();  // the previous use of wtot is over
+    if (lane == 31) S.wtot[warp] = incl;
+    __syncthreads();
+    int pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < BIG_THREADS / 32; w++) {
+        const int t = S.wtot[w];
+        if (w < warp) pre += t;
+        tot += t;
+    }
+    *excl = pre + incl - packed;
+    *total = tot;
+}
+
+__device__ __forceinline__ int big_block_sum(BigShared &S, int v) {
+    int e, t;
+    big_block_scan(S, v, &e, &t);
+    return t;
+}
+
+__global__ void __cluster_dims__(BIG_CL, 1, 1) __launch_bounds__(BIG_THREADS)
+select_big_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, int ntx, const yavo_ent *__restrict__ pool,
+                  yavo_ent *__restrict__ cand_all, int max_cand, const int *__restrict__ ncand,
+                  uint32_t *__restrict__ scratch_all, int *__restrict__ xchg_all, int K, int H, int big_min,
+                  SelRange *__restrict__ pre_all, int *__restrict__ n_pre) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ BigShared S;
+    // cluster barrier + a device-scope fence on the way out: what other CTAs wrote to global memory before the barrier
+    // (entries, stopper lists, counts) must not be served from this SM's L1
+    auto csync = [&]() {
+        cluster.sync();
+        __threadfence();
+    };
+    const int rank = (int)cluster.block_rank(), f = blockIdx.x / BIG_CL;
+    const int tid = threadIdx.x;
+    const int N = ncand[f];
+    if (N <= big_min || N > max_cand) return;  // the select kernel does everything (uniform over the cluster)
+    yavo_ent *A = cand_all + (size_t)f * max_cand;
+    uint32_t *Lpos = scratch_all + (size_t)f * (size_t)(max_cand + 4);
+    uint32_t *Rpos = Lpos + (max_cand / 2 + 2);
+    volatile int *X = xchg_all + (size_t)f * BIG_XCHG;
+    const uint32_t *seg_f = seg + (size_t)f * rows_alloc * seg_cols;
+    const yavo_ent *pool_f = pool + (size_t)f * max_cand;
+
+    // ---- gather: this CTA's slice of the segment table, one contiguous run of segments per thread -----------------
+    {
+        const int Sg = H * ntx, per_cta = (Sg + BIG_CL - 1) / BIG_CL;
+        const int c0 = min(Sg, rank * per_cta), c1 = min(Sg, c0 + per_cta);
+        const int per = (c1 - c0 + BIG_THREADS - 1) / BIG_THREADS;
+        const int e0 = min(c1, c0 + tid * per), e1 = min(c1, e0 + per);
+        int mine = 0;
+        {
+            int row = e0 / ntx, tx = e0 - row * ntx;
+            for (int e = e0; e < e1; e++) {
+                mine += (int)(seg_f[(size_t)row * seg_cols + tx] & ((1u << SEG_CNT_BITS) - 1u));
+                if (++tx == ntx) { tx = 0; row++; }
+            }
+        }
+        int excl, total;
+        // counts can exceed 16 bits here: scan the plain value (the packed form is for the stopper counts)
+        big_block_scan(S, mine, &excl, &total);
+        if (tid == 0) X[3 * BIG_CL + rank] = total;
+        __threadfence();
+        csync();
+        int base = 0;
+        for (int c = 0; c < rank; c++) base += X[3 * BIG_CL + c];
+        int o = base + excl;
+        int row = e0 / ntx, tx = e0 - row * ntx;
+        for (int e = e0; e < e1; e++) {
+            const uint32_t sg = seg_f[(size_t)row * seg_cols + tx];
+            const int cnt = (int)(sg & ((1u << SEG_CNT_BITS) - 1u));
+            const yavo_ent *src = pool_f + (sg >> SEG_CNT_BITS);
+            for (int k = 0; k < cnt; k++) A[o + k] = src[k];
+            o += cnt;
+            if (++tx == ntx) { tx = 0; row++; }
+        }
+        __threadfence();
+        csync();
+    }
+
+    if (tid == 0) {
+        S.lvl[0][0] = {0, N, 2 * (31 - __clz(N))};
+        S.nlvl[0] = 1;
+        S.nlvl[1] = 0;
+    }
+    __syncthreads();
+    int npre = 0;  // handed-over ranges so far (every CTA counts; rank 0 writes them)
+    SelRange *pre = pre_all + (size_t)f * BIG_PRE;
+    int cur = 0;
+    while (S.nlvl[cur] > 0) {
+        const int nb = S.nlvl[cur], nxt = cur ^ 1;
+        for (int ri = 0; ri < nb; ri++) {
+            const SelRange r = S.lvl[cur][ri];
+            const int rf = r.f, rl = r.l, n = rl - rf;
+            if (r.d == 0) {  // depth limit (never reached on score lists): the select kernel's heapsort takes the range
+                if (rank == 0 && tid == 0 && npre < BIG_PRE) pre[npre] = r;
+                npre++;
+                continue;
+            }
+            if (rank == 0 && tid == 0) {
+                yavo_median_to_first(A, rf, rl);
+                __threadfence();
+            }
+            csync();
+            const yavo_ent piv = A[rf];
+            const int cap = n / 2 + 1;
+            const int per_cta = (n - 1 + BIG_CL - 1) / BIG_CL;
+            const int i_lo = min(n - 1, rank * per_cta), i_hi = min(n - 1, i_lo + per_cta);
+            // pass 1: stoppers in this CTA's slice of the scan index range
+            {
+                int cL = 0, cR = 0;
+                for (int i = i_lo + tid; i < i_hi; i += BIG_THREADS) {
+                    cL += !yavo_before(A[rf + 1 + i], piv);
+                    cR += !yavo_before(piv, A[rl - 1 - i]);
+                }
+                const int tL = big_block_sum(S, cL), tR = big_block_sum(S, cR);
+                if (tid == 0) {
+                    X[rank] = tL;
+                    X[BIG_CL + rank] = tR;
+                }
+                __threadfence();
+            }
+            csync();
+            int baseL = 0, baseR = 0, nL = 0, nR = 0;
+            for (int c = 0; c < BIG_CL; c++) {
+                const int a = X[c], b = X[BIG_CL + c];
+                if (c < rank) { baseL += a; baseR += b; }
+                nL += a;
+                nR += b;
+            }
+            // pass 2: positions of the stoppers at [base + rank inside the slice]
+            {
+                int runL = baseL, runR = baseR;
+                for (int base = i_lo; base < i_hi; base += BIG_THREADS * BIG_ITEMS) {
+                    const int i0 = base + tid * BIG_ITEMS;
+                    unsigned fL = 0, fR = 0;
+#pragma unroll
+                    for (int e = 0; e < BIG_ITEMS; e++) {
+                        const int i = i0 + e;
+                        if (i < i_hi) {
+                            fL |= (unsigned)(!yavo_before(A[rf + 1 + i], piv)) << e;
+                            fR |= (unsigned)(!yavo_before(piv, A[rl - 1 - i])) << e;
+                        }
+                    }
+                    int excl, tot;
+                    big_block_scan(S, __popc(fL) | (__popc(fR) << 16), &excl, &tot);
+                    int rL = runL + (excl & 0xffff), rR = runR + (excl >> 16);
+#pragma unroll
+                    for (int e = 0; e < BIG_ITEMS; e++) {
+                        if ((fL >> e) & 1u) {
+                            if (rL < cap) Lpos[rL] = (uint32_t)(1 + i0 + e);  // positions relative to rf
+                            rL++;
+                        }
+                        if ((fR >> e) & 1u) {
+                            if (rR < cap) Rpos[rR] = (uint32_t)(n - 1 - (i0 + e));
+                            rR++;
+                        }
+                    }
+                    runL += tot & 0xffff;
+                    runR += tot >> 16;
+                }
+                __threadfence();
+            }
+            csync();
+            // swaps: the pairs with L_k < R_k form a prefix of the pair list
+            const int nLc = min(nL, cap), nRc = min(nR, cap), npairs = min(nLc, nRc);
+            {
+                int cnt = 0;
+                for (int k = rank * BIG_THREADS + tid; k < npairs; k += BIG_CL * BIG_THREADS) {
+                    const uint32_t a = Lpos[k], b = Rpos[k];
+                    if (a < b) {
+                        const yavo_ent va = A[rf + a], vb = A[rf + b];
+                        A[rf + a] = vb;
+                        A[rf + b] = va;
+                        cnt++;
+                    }
+                }
+                const int t = big_block_sum(S, cnt);
+                if (tid == 0) X[2 * BIG_CL + rank] = t;
+                __threadfence();
+            }
+            csync();
+            if (tid == 0) {
+                int m = 0;
+                for (int c = 0; c < BIG_CL; c++) m += X[2 * BIG_CL + c];
+                uint32_t cut = 0xffffffffu;
+                if (m < nLc) cut = Lpos[m];
+                if (m >= 1) cut = min(cut, Rpos[m - 1]);
+                S.bc[0] = rf + (int)cut;
+            }
+            __syncthreads();
+            const int cut = S.bc[0];
+            if (tid == 0) {
+                const SelRange ch[2] = {{rf, cut, r.d - 1}, {cut, rl, r.d - 1}};
+                for (int c = 0; c < 2; c++) {
+                    if (ch[c].f >= K || ch[c].l - ch[c].f <= 1) continue;
+                    if (ch[c].l - ch[c].f > big_min && S.nlvl[nxt] < SEL_BIG) {
+                        S.lvl[nxt][S.nlvl[nxt]++] = ch[c];
+                    } else {
+                        if (rank == 0 && npre < BIG_PRE) pre[npre] = ch[c];
+                        npre++;
+                    }
+                }
+                S.bc[1] = npre;
+            }
+            __syncthreads();
+            npre = S.bc[1];
+        }
+        __syncthreads();
+        if (tid == 0) S.nlvl[cur] = 0;
+        cur = nxt;
+        __syncthreads();
+    }
+    if (rank == 0 && tid == 0) {
+        __threadfence();
+        n_pre[f] = min(npre, BIG_PRE);
+    }
+}
+
 // checkBoundry of reference src/BriefDescriptor.cc:128-136 as computeBrief calls it (:97)
 __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
     return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
@@ -836,7 +1097,8 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
                    int *__restrict__ nkp,
                    // compacted (checkBoundry-admitted) list that BRIEF / the matcher consume
                    int32_t *__restrict__ bk_row, int32_t *__restrict__ bk_col, float *__restrict__ bk_score,
-                   int32_t *__restrict__ bk_id, int *__restrict__ nbk, int *__restrict__ status) {
+                   int32_t *__restrict__ bk_id, int *__restrict__ nbk, int *__restrict__ status,
+                   const SelRange *__restrict__ pre_all = nullptr, const int *__restrict__ n_pre = nullptr) {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelShared &S = *reinterpret_cast<SelShared *>(sel_smem_raw);
     yavo_ent *sbuf = reinterpret_cast<yavo_ent *>(sel_smem_raw + ((sizeof(SelShared) + 15) & ~size_t(15)));
@@ -865,12 +1127,22 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
 
     // load the candidate list in scan order: the detect kernel scored the corners and left them in the frame's pool;
     // the segment table puts them back in the order the reference appends retCorners (src/FastDetector.cc:298-324)
-    const bool in_smem_at_start = N <= SEL_SMEM_ENTS;
+    // a large list arrives gathered and partitioned at the top by the cluster kernel (K3a): continue from its ranges
+    const int np = n_pre ? n_pre[f] : 0;
+    const bool in_smem_at_start = np == 0 && N <= SEL_SMEM_ENTS;
     yavo_ent *A = in_smem_at_start ? sbuf : G;
     bool in_smem = in_smem_at_start;
-    gather_candidates<SEL_THREADS>(seg + (size_t)f * rows_alloc * seg_cols, seg_cols, H, ntx, pool + (size_t)f * max_cand, A,
-                                   in_smem ? SEL_SMEM_ENTS : max_cand, S.wtot);
-    if (tid == 0 && N > 1) {
+    if (np == 0)
+        gather_candidates<SEL_THREADS>(seg + (size_t)f * rows_alloc * seg_cols, seg_cols, H, ntx, pool + (size_t)f * max_cand, A,
+                                       in_smem ? SEL_SMEM_ENTS : max_cand, S.wtot);
+    if (tid == 0 && np > 0) {
+        const SelRange *pre = pre_all + (size_t)f * BIG_PRE;
+        for (int i = 0; i < np; i++) {
+            const SelRange r = pre[i];
+            if (r.l - r.f > SEL_WARP_MAX && S.nbig[0] < SEL_BIG) S.big[0][S.nbig[0]++] = r;
+            else if (r.l - r.f > SEL_WARP_MAX || !sel_push(S, r)) yavo_serial_introsort(A, r.f, r.l, r.d, K);  // lists full: exact, serial
+        }
+    } else if (tid == 0 && N > 1) {
         const SelRange r0 = {0, N, 2 * (31 - __clz(N))};
         if (N > SEL_WARP_MAX) S.big[0][S.nbig[0]++] = r0;
         else sel_push(S, r0);
