@@ -37,7 +37,7 @@ def main():
                       "kernel_ms_per_step": {k: v[0] / steps for k, v in prof.items()},
                       "algorithmic_bytes_per_frame": W * H + 44 * K,
                       "achieved_gbs_detect_describe": B * (W * H + 44 * K) / 1e9 /
-                      (sum(prof[k][0] for k in ("detect_blur", "compact_score", "select_topk", "brief")) / steps / 1e3)}))
+                      (sum(prof[k][0] for k in ("detect_blur", "compact_score", "select_topk", "select_big", "brief")) / steps / 1e3)}))
 
 
 if __name__ == "__main__":

@@ -135,7 +135,7 @@ class Context:
         return int(self._L.yavo_get_stream(self._h) or 0)
 
     KERNEL_CLASSES = ("repitch", "detect_blur", "compact_score", "select_topk", "brief", "match_partial", "match_reduce",
-                      "filter_pairs", "pyr_down", "klt_track", "epipolar_inliers", "match_tc")
+                      "filter_pairs", "pyr_down", "klt_track", "epipolar_inliers", "match_tc", "select_big")
 
     def set_profiling(self, on):
         self._ck(self._L.yavo_set_profiling(self._h, int(bool(on))))

@@ -49,7 +49,7 @@ struct yavo_ctx {
     int *d_ncand = nullptr;
     uint32_t *d_scratch = nullptr;
     // cluster pre-partition of large candidate lists (select_big_kernel): exchange block, handed-over ranges, their count
-    int *d_xchg = nullptr, *d_npre = nullptr;
+    int *d_xchg = nullptr, *d_npre = nullptr, *d_team_done = nullptr;
     SelRange *d_pre = nullptr;
     int big_min = -1;  // candidates above which a frame's list takes the cluster path; 0 = never, -1 = automatic (16384, frames >= 2 Mpx)
     int32_t *d_kp_row = nullptr, *d_kp_col = nullptr;
@@ -146,7 +146,7 @@ struct yavo_ctx {
 };
 
 enum { STATUS_TICKETS = 16, STATUS_GENERAL = 16, STATUS_WORDS = 17 };
-enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_PYR, KC_KLT, KC_EPI, KC_MATCH_TC, KC_COUNT };
+enum { KC_REPITCH = 0, KC_DETECT, KC_COMPACT, KC_SELECT, KC_BRIEF, KC_MATCH, KC_MATCH_REDUCE, KC_FILTER, KC_PYR, KC_KLT, KC_EPI, KC_MATCH_TC, KC_SELECT_BIG, KC_COUNT };
 
 namespace {
 
@@ -355,21 +355,24 @@ int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
     const bool big = big_min > 0 && ctx->max_cand > big_min;
     if (big) {
         CK(cudaMemsetAsync(ctx->d_npre + slot0, 0, sizeof(int) * (size_t)n, ctx->ls));
-        PROF(KC_SELECT, select_big_kernel<<<n * BIG_CL, BIG_THREADS, 0, ctx->ls>>>(
+        CK(cudaMemsetAsync(ctx->d_team_done + slot0, 0, sizeof(int) * (size_t)n, ctx->ls));
+        PROF(KC_SELECT_BIG, select_big_kernel<<<n * BIG_CL, BIG_THREADS, 0, ctx->ls>>>(
             ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW,
             ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
-            ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), ctx->d_xchg + (size_t)slot0 * BIG_XCHG, K, H, big_min,
+            ctx->d_scratch + (size_t)slot0 * (2 * (size_t)ctx->max_cand + 8), ctx->d_xchg + (size_t)slot0 * BIG_XCHG, K, H, big_min,
             ctx->d_pre + (size_t)slot0 * BIG_PRE, ctx->d_npre + slot0));
         CK_LAUNCH();
     }
-    PROF(KC_SELECT, select_topk_kernel<<<n, SEL_THREADS, select_smem_bytes(), ctx->ls>>>(
+    const int team = big ? BIG_CL : 1;
+    PROF(KC_SELECT, select_topk_kernel<<<n * team, SEL_THREADS, select_smem_bytes(), ctx->ls>>>(
         ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW,
         ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
-        ctx->d_scratch + (size_t)slot0 * (ctx->max_cand + 4), K, H, W, ctx->max_kp,
+        ctx->d_scratch + (size_t)slot0 * (2 * (size_t)ctx->max_cand + 8), K, H, W, ctx->max_kp,
         ctx->d_kp_row + o,
         ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
         ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->cur_status,
-        big ? ctx->d_pre + (size_t)slot0 * BIG_PRE : nullptr, big ? ctx->d_npre + slot0 : nullptr));
+        big ? ctx->d_pre + (size_t)slot0 * BIG_PRE : nullptr, big ? ctx->d_npre + slot0 : nullptr, team,
+        big ? ctx->d_team_done + slot0 : nullptr));
     CK_LAUNCH();
     return 0;
 }
@@ -611,10 +614,11 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_seg, S * c->rows_alloc * c->seg_cols));
     CKC(dalloc(&c->d_cand, S * c->max_cand));
     CKC(dalloc(&c->d_ncand, S));
-    CKC(dalloc(&c->d_scratch, S * (c->max_cand + 4)));
+    CKC(dalloc(&c->d_scratch, S * (2 * (size_t)c->max_cand + 8)));  // stopper lists: a range [f, l) uses [2f, 2f + n + 4)
     CKC(dalloc(&c->d_xchg, S * BIG_XCHG));
     CKC(dalloc(&c->d_pre, S * BIG_PRE));
     CKC(dalloc(&c->d_npre, S));
+    CKC(dalloc(&c->d_team_done, S));
     CKC(cudaMemset(c->d_npre, 0, S * sizeof(int)));
     CKC(dalloc(&c->d_kp_row, S * max_kp));
     CKC(dalloc(&c->d_kp_col, S * max_kp));
@@ -669,7 +673,7 @@ void yavo_destroy(yavo_ctx *c) {
                     c->d_offs,   c->d_pt_row,  c->d_pt_col,  c->d_pt_desc,  c->d_pt_valid, c->d_mq,     c->d_mt,
                     c->d_mo_idx, c->d_part_key, c->d_part_sec, c->d_raw,
                     c->d_pairs,  c->d_npairs,  c->d_minDist, c->d_spos,
-                    c->d_fpack,  c->d_xchg,    c->d_pre,     c->d_npre,
+                    c->d_fpack,  c->d_xchg,    c->d_pre,     c->d_npre,    c->d_team_done,
                     c->d_pyr,    c->d_klt_prev, c->d_klt_next, c->d_klt_status, c->d_klt_err, c->d_trk_xy,
                     c->d_trk_status, c->d_trk_err};
     for (void *b : bufs)

@@ -903,7 +903,7 @@ select_big_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc
     const int N = ncand[f];
     if (N <= big_min || N > max_cand) return;  // the select kernel does everything (uniform over the cluster)
     yavo_ent *A = cand_all + (size_t)f * max_cand;
-    uint32_t *Lpos = scratch_all + (size_t)f * (size_t)(max_cand + 4);
+    uint32_t *Lpos = scratch_all + (size_t)f * (size_t)(2 * max_cand + 8);
     uint32_t *Rpos = Lpos + (max_cand / 2 + 2);
     volatile int *X = xchg_all + (size_t)f * BIG_XCHG;
     const uint32_t *seg_f = seg + (size_t)f * rows_alloc * seg_cols;
@@ -1098,12 +1098,16 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
                    // compacted (checkBoundry-admitted) list that BRIEF / the matcher consume
                    int32_t *__restrict__ bk_row, int32_t *__restrict__ bk_col, float *__restrict__ bk_score,
                    int32_t *__restrict__ bk_id, int *__restrict__ nbk, int *__restrict__ status,
-                   const SelRange *__restrict__ pre_all = nullptr, const int *__restrict__ n_pre = nullptr) {
+                   const SelRange *__restrict__ pre_all = nullptr, const int *__restrict__ n_pre = nullptr,
+                   int team = 1 /* CTAs per frame (> 1 only together with the cluster pre-partition) */,
+                   int *__restrict__ team_done = nullptr) {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
     SelShared &S = *reinterpret_cast<SelShared *>(sel_smem_raw);
     yavo_ent *sbuf = reinterpret_cast<yavo_ent *>(sel_smem_raw + ((sizeof(SelShared) + 15) & ~size_t(15)));
 
-    const int f = blockIdx.x;
+    // team > 1: the frame's handed-over ranges (disjoint spans of the list) are dealt round-robin to `team` independent
+    // CTAs, each of which replays its ranges to the leaves in global memory; the CTA that finishes last writes the outputs
+    const int f = blockIdx.x / team, member = blockIdx.x - f * team;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #ifdef YAVO_SEL_TIMING
     long long tmark[6];
@@ -1118,8 +1122,12 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
         return;
     }
     yavo_ent *G = cand_all + (size_t)f * max_cand;
-    uint32_t *Lpos = scratch_all + (size_t)blockIdx.x * (size_t)(max_cand + 4);
-    uint32_t *Rpos = Lpos + (max_cand / 2 + 2);
+    // stopper lists of CTA-wide partitions in global memory: per frame 2 * max_cand + 8 entries; a range [rf, rl) uses
+    // [2 rf, 2 rf + n + 4), so concurrent partitions of disjoint ranges (team members) never share entries
+    uint32_t *Lbase = scratch_all + (size_t)f * (size_t)(2 * max_cand + 8);
+    const int np = n_pre ? n_pre[f] : 0;
+    if (member > 0 && np == 0) return;  // a short list: member 0 does everything
+    const bool solo = team == 1 || np == 0;
 
     for (int i = tid; i < SEL_QCAP; i += SEL_THREADS) S.ready[i] = 0;
     if (tid == 0) { S.nbig[0] = S.nbig[1] = 0; S.q_head = S.q_tail = 0; S.pending = 0; S.watchdog = 0; }
@@ -1128,7 +1136,6 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
     // load the candidate list in scan order: the detect kernel scored the corners and left them in the frame's pool;
     // the segment table puts them back in the order the reference appends retCorners (src/FastDetector.cc:298-324)
     // a large list arrives gathered and partitioned at the top by the cluster kernel (K3a): continue from its ranges
-    const int np = n_pre ? n_pre[f] : 0;
     const bool in_smem_at_start = np == 0 && N <= SEL_SMEM_ENTS;
     yavo_ent *A = in_smem_at_start ? sbuf : G;
     bool in_smem = in_smem_at_start;
@@ -1137,7 +1144,7 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
                                        in_smem ? SEL_SMEM_ENTS : max_cand, S.wtot);
     if (tid == 0 && np > 0) {
         const SelRange *pre = pre_all + (size_t)f * BIG_PRE;
-        for (int i = 0; i < np; i++) {
+        for (int i = member; i < np; i += team) {
             const SelRange r = pre[i];
             if (r.l - r.f > SEL_WARP_MAX && S.nbig[0] < SEL_BIG) S.big[0][S.nbig[0]++] = r;
             else if (r.l - r.f > SEL_WARP_MAX || !sel_push(S, r)) yavo_serial_introsort(A, r.f, r.l, r.d, K);  // lists full: exact, serial
@@ -1154,7 +1161,7 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
     int cur = 0;
     while (S.nbig[cur] > 0) {
         const int nb = S.nbig[cur], nxt = cur ^ 1;
-        if (!in_smem) {  // move the active prefix into shared memory as soon as it fits
+        if (!in_smem && solo) {  // move the active prefix into shared memory as soon as it fits
             int E = min(N, K);
             for (int i = 0; i < nb; i++) E = max(E, S.big[cur][i].l);
             const int qt = S.q_tail;
@@ -1175,7 +1182,8 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
                 continue;
             }
             cut = in_smem ? sel_block_partition<uint16_t>(S, A, r.f, r.l, S.bscratch[0], S.bscratch[1])
-                          : sel_block_partition<uint32_t>(S, A, r.f, r.l, Lpos, Rpos);
+                          : sel_block_partition<uint32_t>(S, A, r.f, r.l, Lbase + 2 * (size_t)r.f,
+                                                          Lbase + 2 * (size_t)r.f + ((r.l - r.f) / 2 + 2));
             if (tid == 0) {
                 const SelRange ch[2] = {{r.f, cut, r.d - 1}, {cut, r.l, r.d - 1}};
                 for (int c = 0; c < 2; c++) {
@@ -1193,7 +1201,7 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
     }
     SEL_MARK(2);
     // move the active prefix into shared memory if it fits (phase 2 then never touches global memory)
-    if (!in_smem) {
+    if (!in_smem && solo) {
         int E = min(N, K);
         const int qt = S.q_tail;
         for (int i = 0; i < qt && i < SEL_QCAP; i++) E = max(E, S.ring[i].l);
@@ -1234,6 +1242,14 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
     if (tid == 0 && S.watchdog) atomicExch(status, 2);
     SEL_MARK(4);
 
+    if (!solo) {
+        // the member that finishes last sees every member's ranges in place and writes the outputs
+        __threadfence();
+        if (tid == 0) S.bcast[1] = atomicAdd(&team_done[f], 1);
+        __syncthreads();
+        if (S.bcast[1] != team - 1) return;
+        __threadfence();  // lines shared with neighbouring ranges may sit in this SM's L1 with other members' old entries
+    }
     // ---- outputs: first min(N,K) in order, plus the checkBoundry-compacted list -------------------
     const int nout = min(N, K);
     int run = 0;
