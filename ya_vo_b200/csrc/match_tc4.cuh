@@ -44,12 +44,23 @@ constexpr int RPW = T4 > 128 ? 64 : 32;  // train rows per expander warp
 // epilogue split: true = both warps of a TMEM lane quarter drain EVERY tile, 112 columns each (two tcgen05.ld round trips per
 // tile and warp); false = warps 0-3 / 4-7 take alternate tiles whole (four round trips)
 constexpr bool EPI_SPLIT = YAVO_TC4_EPI_SPLIT && (T4 == 224 || T4 == 144);
-constexpr int THREADS4 = THREADS;
+#ifndef YAVO_TC4_EPI_GROUPS
+#define YAVO_TC4_EPI_GROUPS 2
+#endif
+// epilogue groups: every TMEM lane quarter is drained by EG warps (warp & 3 = quarter, warp >> 2 = group), each taking
+// T4 / EG columns of every tile: 2 groups of 112 columns (8 warps), or 4 groups of 56 (16 warps: half the drain latency
+// per tile, which is what the MMA warp waits on when both accumulators are full)
+constexpr int EG = YAVO_TC4_EPI_GROUPS;
+static_assert(EG == 2 || (EG == 4 && YAVO_TC4_N == 224 && YAVO_TC4_EPI_SPLIT), "4 epilogue groups: 224-column tiles, split mode");
+constexpr int EPI4_WARPS = 4 * EG;
+constexpr int MMA4_WARP = EPI4_WARPS;                       // then EXP_WARPS expander warps, then the loader warp
+constexpr int LOAD4_WARP = EPI4_WARPS + 1 + EXP_WARPS;
+constexpr int THREADS4 = 32 * (EPI4_WARPS + 2 + EXP_WARPS);
 #ifndef YAVO_TC4_NCH
 #define YAVO_TC4_NCH 4
 #endif
 constexpr int NCH = YAVO_TC4_NCH;        // independent minimum chains per epilogue thread (4 or 8)
-constexpr int CW = T4 == 144 ? 72 : 112;  // accumulator columns per epilogue pass: 32 + 32 + 8 or 32 + 32 + 32 + 16
+constexpr int CW = EG == 4 ? 56 : (T4 == 144 ? 72 : 112);  // accumulator columns per epilogue pass: 32 + 16 + 8, 32 + 32 + 8 or 32 + 32 + 32 + 16
 static_assert(T4 % CW == 0, "tile width");
 constexpr int ROWB = 128;                // operand bytes per descriptor (two e2m1 per byte)
 constexpr int A4_BYTES = Q4 * ROWB;      // 16 KB
@@ -236,8 +247,8 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ uint64_t bars[2 * NSTAGE + 2 * NACC + 2 * NB4 + 2 * NR4];
     __shared__ uint32_t tmem_base_s;
-    __shared__ int2 comb[2][Q4];
-    __shared__ int comb_sec[SECOND ? 2 : 1][SECOND ? Q4 : 1];
+    __shared__ int2 comb[2][EG - 1][Q4];
+    __shared__ int comb_sec[SECOND ? 2 : 1][EG - 1][SECOND ? Q4 : 1];
     // shared-window addresses, computed once (barriers are 8 bytes apart)
     uint32_t bars_s, smem_s;  // through an opaque move: the compiler otherwise rematerialises the conversion (S2R + LEA) at every use
     asm volatile("mov.u32 %0, %2;\n\tmov.u32 %1, %3;" : "=r"(bars_s), "=r"(smem_s) : "r"(saddr(bars)), "r"(saddr(smem_raw)));
@@ -257,7 +268,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
         }
         for (int s = 0; s < NACC; s++) {
             bar_init(acc_full + 8 * (s), 1);
-            bar_init(acc_empty + 8 * (s), EPI_SPLIT ? EPI_WARPS : EPI_WARPS / 2);
+            bar_init(acc_empty + 8 * (s), EPI_SPLIT ? EPI4_WARPS : EPI4_WARPS / 2);
         }
         for (int s = 0; s < NB4; s++) {
             bar_init(b_full + 8 * (s), EXP_WARPS / 2);
@@ -278,7 +289,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
         *reinterpret_cast<uint4 *>(p + (q ? Q4 : T4) * 16) = make_uint4(0, 0, 0, 0);
     }
     fence_async_smem();
-    if (warp == MMA_WARP) {
+    if (warp == MMA4_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(saddr(&tmem_base_s)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -299,7 +310,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
     const int items = pairs * q_tiles;
     uint32_t e_cnt = 0, a_cnt = 0, t_cnt = 0;
 
-    if (warp < EPI_WARPS) {
+    if (warp < EPI4_WARPS) {
         YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ epilogue (two groups on alternate accumulators)
             const int g = warp >> 2, row = (warp & 3) * 32 + lane;
@@ -324,6 +335,46 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 for (int h = EPI_SPLIT ? g : 0; h < (EPI_SPLIT ? g + 1 : T4 / CW); h++) {
                     const uint32_t ta = taddr + h * CW;
                     const int c0 = h * CW;
+                    if (CW == 56) {  // four groups: 32 + 16 + 8 columns, one round trip
+                        uint32_t v4[16];
+                        tmem_ld32(ta, v0);
+                        tmem_ld16(ta + 32, v3);
+                        tmem_ld8(ta + 48, v4);
+                        tmem_wait2b(v0, v3);
+                        tmem_wait16(v4);
+                        uint32_t vt[32], vu[32];
+#pragma unroll
+                        for (int i = 0; i < 32; i++) {
+                            vt[i] = v3[i & 15];
+                            vu[i] = v4[i & 7];
+                        }
+                        if (SECOND) {
+                            if (full) {
+                                min2_keys4<true>(v0, m4, s4, 32, 0, 0);
+                                min2_keys4<true>(vt, m4, s4, 16, 0, 0);
+                                min2_keys4<true>(vu, m4, s4, 8, 0, 0);
+                            } else {
+                                min2_keys4<false>(v0, m4, s4, 32, c0, nvalid);
+                                min2_keys4<false>(vt, m4, s4, 16, c0 + 32, nvalid);
+                                min2_keys4<false>(vu, m4, s4, 8, c0 + 48, nvalid);
+                            }
+                        } else if (full) {
+                            min_keys4<true>(v0, m4, 0, 0);
+#pragma unroll
+                            for (int i = 0; i < 16; i += 2) m4[(i >> 1) & (NCH - 1)] = fminf(m4[(i >> 1) & (NCH - 1)], fminf(__uint_as_float(v3[i]), __uint_as_float(v3[i + 1])));
+#pragma unroll
+                            for (int i = 0; i < 8; i += 2) m4[(i >> 1) & (NCH - 1)] = fminf(m4[(i >> 1) & (NCH - 1)], fminf(__uint_as_float(v4[i]), __uint_as_float(v4[i + 1])));
+                        } else {
+                            min_keys4<false>(v0, m4, c0, nvalid);
+#pragma unroll
+                            for (int i = 0; i < 16; i++)
+                                if (c0 + 32 + i < nvalid) m4[i & (NCH - 1)] = fminf(m4[i & (NCH - 1)], __uint_as_float(v3[i]));
+#pragma unroll
+                            for (int i = 0; i < 8; i++)
+                                if (c0 + 48 + i < nvalid) m4[i & (NCH - 1)] = fminf(m4[i & (NCH - 1)], __uint_as_float(v4[i]));
+                        }
+                        continue;
+                    }
 #ifndef YAVO_TC_EXP_NO_LD
                     tmem_ld32(ta, v0);
                     tmem_ld32(ta + 32, v1);
@@ -409,24 +460,27 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 }
             }
             t_cnt += n_tiles;
-            int2 *cb = comb[e_cnt & 1];
-            int *cs = comb_sec[SECOND ? (e_cnt & 1) : 0];
+            int2 (*cb)[Q4] = comb[e_cnt & 1];
+            int (*cs)[SECOND ? Q4 : 1] = comb_sec[SECOND ? (e_cnt & 1) : 0];
             e_cnt++;
-            if (g == 1) {
-                cb[row] = make_int2(best_d, best_j);
-                if (SECOND) cs[row] = sec_d;
+            if (g >= 1) {
+                cb[g - 1][row] = make_int2(best_d, best_j);
+                if (SECOND) cs[g - 1][row] = sec_d;
             }
-            asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI4_WARPS * 32) : "memory");
             if (g == 0) {
-                const int2 o = cb[row];
-                if (SECOND) {
-                    // two halves (best, second): overall second = min(the two seconds, the larger of the two bests)
-                    const int os = cs[row];
-                    sec_d = min(min(sec_d, os), max(best_d, o.x));
-                }
-                if (o.x < best_d || (o.x == best_d && o.y < best_j)) {
-                    best_d = o.x;
-                    best_j = o.y;
+#pragma unroll
+                for (int og = 0; og < EG - 1; og++) {
+                    const int2 o = cb[og][row];
+                    if (SECOND) {
+                        // two parts (best, second): overall second = min(the two seconds, the larger of the two bests)
+                        const int os = cs[og][row];
+                        sec_d = min(min(sec_d, os), max(best_d, o.x));
+                    }
+                    if (o.x < best_d || (o.x == best_d && o.y < best_j)) {
+                        best_d = o.x;
+                        best_j = o.y;
+                    }
                 }
                 const int q = q0 + row;
                 if (q < nq) {
@@ -436,7 +490,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 }
             }
         }
-    } else if (warp == MMA_WARP) {
+    } else if (warp == MMA4_WARP) {
         YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ MMA issue: the whole warp runs the loop (uniform
             // control flow and operands), one elected lane issues tcgen05.mma / tcgen05.commit
@@ -471,7 +525,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 a_cnt++;
             }
         }
-    } else if (warp == LOAD_WARP) {
+    } else if (warp == LOAD4_WARP) {
         YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ loader: packed bits of the train tiles -> ring
             if (n_tiles > 0 && lane == 0) {
@@ -488,11 +542,11 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
                 t_cnt += n_tiles;
             }
         }
-    } else if (warp < LOAD_WARP) {
+    } else if (warp < LOAD4_WARP) {
         YAVO_TC4_FOR_ITEMS
             // ------------------------------------------------ expanders (two groups on alternate operand stages)
             if (n_tiles > 0) {
-                const int ew = warp - (EPI_WARPS + 1), ge = ew >> 2, k = ew & 3;
+                const int ew = warp - (EPI4_WARPS + 1), ge = ew >> 2, k = ew & 3;
                 const uint32_t as = a_cnt & 1, aph = (a_cnt >> 1) & 1;
                 const uint4 zero = make_uint4(0, 0, 0, 0);
                 if (ge == (int)as) {  // query tile: rows k*32 .. +31
@@ -541,7 +595,7 @@ match_tc4_kernel(const uint32_t *__restrict__ dq_all, const int *__restrict__ nq
 
     fence_before_sync();
     __syncthreads();
-    if (warp == MMA_WARP) {
+    if (warp == MMA4_WARP) {
         fence_after_sync();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
