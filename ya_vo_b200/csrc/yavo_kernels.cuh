@@ -1334,7 +1334,10 @@ constexpr int BP_D = 4;                  // patches in flight per warp (ring of 
 // in flight.  The keypoint's phase (col-8) & 15 is warp-uniform (built from ballots, so it lives in a uniform
 // register) and is added to the lane's fixed sample addresses.  What bounds the kernel is then the shared-memory sampling
 // itself (16 byte loads per lane and keypoint at table-defined, i.e. random, bank positions).
-__global__ void __launch_bounds__(K4_THREADS)
+#ifndef YAVO_K4_MIN_CTAS
+#define YAVO_K4_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(K4_THREADS, YAVO_K4_MIN_CTAS)
 brief_kernel(const __grid_constant__ CUtensorMap blur_map, int slot_base,
              const uint8_t *__restrict__ blur, size_t frame_stride, int pitch, int H, int W,
              const uint32_t *__restrict__ offs, const uint32_t *__restrict__ spos, const int32_t *__restrict__ rows,
