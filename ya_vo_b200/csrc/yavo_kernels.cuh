@@ -1089,7 +1089,11 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
     return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
 }
 
+#ifdef YAVO_SEL_MAXREG  // tuning experiments: cap the registers so that other kernels' CTAs fit beside two select CTAs
+__global__ void __maxnreg__(YAVO_SEL_MAXREG)
+#else
 __global__ void __launch_bounds__(SEL_THREADS, YAVO_SEL_MIN_CTAS)
+#endif
 select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, int ntx,
                    const yavo_ent *__restrict__ pool, yavo_ent *__restrict__ cand_all, int max_cand,
                    const int *__restrict__ ncand, uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
