@@ -1310,7 +1310,10 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
 // equal to W wraps to column 0 of the next row; a linear index >= H*W (undefined behaviour in the
 // reference) reads as 0 and is counted.
 // ================================================================================================
-constexpr int K4_THREADS = 256;
+#ifndef YAVO_K4_THREADS
+#define YAVO_K4_THREADS 256
+#endif
+constexpr int K4_THREADS = YAVO_K4_THREADS;
 
 __device__ __forceinline__ int brief_sample(const uint8_t *S, int pitch, int H, int W, int r, int c, bool *oob) {
     if (c >= W) { c -= W; r += 1; }
@@ -1331,7 +1334,10 @@ constexpr int BP_ENTRY = (BP_BYTES + 127) & ~127;            // ring entries are
 #define YAVO_BP_KPW 8
 #endif
 constexpr int BP_KPW = YAVO_BP_KPW;      // keypoints per warp
-constexpr int BP_D = 4;                  // patches in flight per warp (ring of tensor copies)
+#ifndef YAVO_BP_D
+#define YAVO_BP_D 4
+#endif
+constexpr int BP_D = YAVO_BP_D;          // patches in flight per warp (ring of tensor copies): 4 or 8
 
 // The patch of an interior keypoint arrives by ONE tensor copy (TMA: box of 48 x 17 bytes at ((col-8) & ~15, row-8) of
 // the blurred plane), tracked by an mbarrier per ring entry: no per-lane gather loads, and a warp keeps BP_D patches
@@ -1403,8 +1409,8 @@ brief_kernel(const __grid_constant__ CUtensorMap blur_map, int slot_base,
         uint32_t mine = 0;
         if ((inter >> i) & 1u) {
             // parity of the entry's barrier = earlier copies into the same entry (keypoints i-BP_D, i-2*BP_D, ... that took this path)
-            constexpr uint32_t same_entry = 0x11111111u;  // BP_D == 4
-            static_assert(BP_D == 4, "same_entry mask");
+            constexpr uint32_t same_entry = BP_D == 4 ? 0x11111111u : 0x01010101u;
+            static_assert(BP_D == 4 || BP_D == 8, "same_entry mask");
             const uint32_t par = __popc(inter & (same_entry << (i % BP_D)) & ((1u << i) - 1u)) & 1u;
             if (lane == 0) mbar_wait(&pbar[warp][i % BP_D], par);
             __syncwarp();
