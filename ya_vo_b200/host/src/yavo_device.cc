@@ -15,7 +15,10 @@ std::mutex g_mu;
 Device::Device(int rows, int cols) : maxRows_(rows), maxCols_(cols), slots_(kSlots) {
     const char *v = std::getenv("YAVO_TRUST_IMAGE_IDENTITY");
     verify_pixels_ = !(v && *v && *v != '0');
-    const int rc = yavo_create(0, kSlots, rows, cols, kMaxKeypoints, 0, &ctx_);
+    // YAVO_DEVICE selects the GPU of this process's context (default 0); one process per GPU is the multi-GPU shape
+    const char *dv = std::getenv("YAVO_DEVICE");
+    const int device = dv && *dv ? std::atoi(dv) : 0;
+    const int rc = yavo_create(device, kSlots, rows, cols, kMaxKeypoints, 0, &ctx_);
     if (rc != 0) throw DeviceError(std::string("yavo_create failed: ") + yavo_last_error(nullptr));
 }
 
