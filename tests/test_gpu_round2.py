@@ -180,3 +180,64 @@ def test_cluster_prepartition_of_large_lists_is_exact(cuda_lib, oracle, kind, se
         ctx.frontend_batch(0, 3, True)
         off = ctx.fetch_batch(0, 3)
     _same_results(on, off, 3)
+
+
+@pytest.mark.parametrize("H,W,K", [(376, 1241, 2000), (120, 320, 300), (17, 33, 50), (9, 9, 10), (8, 40, 10), (200, 333, 3000)])
+def test_frame_features_matches_oracle(cuda_lib, oracle, offsets, H, W, K):
+    """yavo_frame_features (the reference's per-frame sequence as one CUDA graph): detector output, admitted list, ids and
+    descriptors against the oracle; repeated calls replay the captured graph, alternating slots and frames."""
+    frames = synth.synth_batch(3, "G30" if H > 50 else "U", 21, H, W)
+    with cuda_lib.Context(device=0, n_slots=2, max_rows=H, max_cols=W, max_kp=K) as ctx:
+        ctx.set_brief_offsets(offsets)
+        for rep in range(3):
+            for i, img in enumerate(frames):
+                ff = ctx.frame_features((i + rep) % 2, img, K)
+                er, ec, es, enc = oracle.fast_detect(img, K)
+                assert ff["n_cand"] == enc
+                assert np.array_equal(ff["rows"], er) and np.array_equal(ff["cols"], ec)
+                assert np.array_equal(ff["scores"].view(np.uint32), es.view(np.uint32))
+                d, v, _ = oracle.brief(img, offsets, er, ec)
+                assert np.array_equal(ff["d_ids"], np.nonzero(v)[0])
+                assert np.array_equal(ff["d_rows"], er[v]) and np.array_equal(ff["d_cols"], ec[v])
+                assert np.array_equal(ff["desc"], d[v])
+
+
+def test_frame_features_strided_rows_profiling_and_slot_reuse(cuda_lib, oracle, offsets):
+    """Row pitch larger than the width, per-kernel profiling on (plain launches instead of the graph), a smaller cap on
+    the same slot, and the other entry points on a slot that a graph filled."""
+    H, W = 96, 200
+    wide = synth.synth_frame("G30", 31, H, W + 56)
+    img = wide[:, :W]  # a view: stride 256, width 200
+    dense = np.ascontiguousarray(img)
+    with cuda_lib.Context(device=0, n_slots=2, max_rows=H, max_cols=W, max_kp=400) as ctx:
+        ctx.set_brief_offsets(offsets)
+        L = cuda_lib.lib()
+        import ctypes as C
+        K = 400
+        r, c = np.empty(K, np.int32), np.empty(K, np.int32)
+        dr, dc, di = np.empty(K, np.int32), np.empty(K, np.int32), np.empty(K, np.int32)
+        desc = np.empty((K, 32), np.uint8)
+        n, nd, nc = C.c_int32(), C.c_int32(), C.c_int()
+        ptr = C.c_void_p(img.ctypes.data)
+        for prof in (False, True, False):
+            ctx.set_profiling(prof)
+            rc = L.yavo_frame_features(ctx._h, 0, ptr, H, W, img.strides[0], K, C.byref(n), C.c_void_p(r.ctypes.data),
+                                       C.c_void_p(c.ctypes.data), None, C.byref(nd), C.c_void_p(dr.ctypes.data),
+                                       C.c_void_p(dc.ctypes.data), C.c_void_p(di.ctypes.data), C.c_void_p(desc.ctypes.data), C.byref(nc))
+            assert rc == 0
+            er, ec, _, enc = oracle.fast_detect(dense, K)
+            d, v, _ = oracle.brief(dense, offsets, er, ec)
+            assert nc.value == enc and n.value == len(er) and nd.value == int(v.sum())
+            assert np.array_equal(r[:n.value], er) and np.array_equal(desc[:nd.value], d[v])
+        ctx.set_profiling(False)
+        ff = ctx.frame_features(0, dense, 100)  # smaller cap: another graph for the same slot
+        er, ec, _, _ = oracle.fast_detect(dense, 100)
+        assert np.array_equal(ff["rows"], er)
+        ctx._shape[0] = dense.shape
+        assert np.array_equal(ctx.download(0), dense)          # the slot holds the frame
+        assert np.array_equal(ctx.blurred(0), oracle.gaussian_blur(dense))
+        assert L.yavo_slot_holds(ctx._h, 0, C.c_void_p(dense.ctypes.data), H, W, W) == 1
+        other = dense.copy()
+        other[5, 7] ^= 1
+        assert L.yavo_slot_holds(ctx._h, 0, C.c_void_p(other.ctypes.data), H, W, W) == 0
+        assert L.yavo_slot_holds(ctx._h, 1, C.c_void_p(dense.ctypes.data), H, W, W) == 0
