@@ -126,6 +126,7 @@ struct yavo_ctx {
     struct FrameGraph {
         int slot, rows, cols, K;
         cudaGraphExec_t exec;
+        int launches;  // kernels inside the graph
     };
     std::vector<FrameGraph> frame_graphs;
     // per-slot pinned copy of the pixels yavo_frame_features uploaded (dense rows): the graph's H2D source, and what
@@ -908,8 +909,13 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
     else
         for (int r = 0; r < rows; r++) memcpy(stage + (size_t)r * cols, pixels + (size_t)r * stride, cols);
     cudaGraphExec_t exec = nullptr;
+    int graph_launches = 0;
     for (auto &g : ctx->frame_graphs)
-        if (g.slot == slot && g.rows == rows && g.cols == cols && g.K == K) exec = g.exec;
+        if (g.slot == slot && g.rows == rows && g.cols == cols && g.K == K) {
+            exec = g.exec;
+            graph_launches = g.launches;
+        }
+    const long long launches_before = ctx->launches;
     if (!exec || ctx->profiling) {
         const bool capture = !ctx->profiling;  // per-kernel profiling wants plain launches with event pairs
         cudaGraph_t graph = nullptr;
@@ -946,7 +952,7 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
             const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
             cudaGraphDestroy(graph);
             if (ei != cudaSuccess) return fail(ctx, YAVO_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(ei));
-            ctx->frame_graphs.push_back({slot, rows, cols, K, exec});
+            ctx->frame_graphs.push_back({slot, rows, cols, K, exec, (int)(ctx->launches - launches_before)});
         } else if (rc) {
             return rc;
         }
@@ -955,7 +961,7 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
         ctx->slot_rows[slot] = rows;
         ctx->slot_cols[slot] = cols;
         ctx->slot_pyr[slot] = 0;
-        ctx->launches += 5;
+        ctx->launches += graph_launches;
     }
     if (exec && !ctx->profiling) CK(cudaGraphLaunch(exec, ctx->stream));
     ctx->slot_blur_valid[slot] = 1;
