@@ -241,3 +241,37 @@ def test_frame_features_strided_rows_profiling_and_slot_reuse(cuda_lib, oracle, 
         other[5, 7] ^= 1
         assert L.yavo_slot_holds(ctx._h, 0, C.c_void_p(other.ctypes.data), H, W, W) == 0
         assert L.yavo_slot_holds(ctx._h, 1, C.c_void_p(dense.ctypes.data), H, W, W) == 0
+
+
+DENSE_PATTERN = np.array([[0, 60, 0, 60], [0, 120, 255, 180], [60, 120, 60, 120], [180, 60, 60, 255]], np.uint8)
+
+
+def test_very_dense_corners_take_several_list_rounds(cuda_lib, oracle, offsets):
+    """A periodic texture on which every second pixel passes the segment test: 2048 corners per full 128x32 tile, twice
+    the detect kernel's per-round corner list (K1_LIST = 1024), 17 k candidates on a 120x320 frame, all of them tied in a
+    handful of Harris responses (the replay's worst case).  Candidates in scan order, responses, the ordered top-K and
+    the descriptors must still be the oracle's; the default candidate capacity (a quarter of the pixels) reports the
+    overflow instead."""
+    H, W = 120, 320
+    dense = np.tile(DENSE_PATTERN, (H // 4, W // 4))
+    mixed = dense.copy()
+    mixed[:, W // 2:] = synth.synth_frame("G30", 9, H, W)[:, W // 2:]
+    frames = np.stack([dense, mixed])
+    with cuda_lib.Context(device=0, n_slots=2, max_rows=H, max_cols=W, max_kp=2000, max_cand=20000) as ctx:
+        ctx.set_brief_offsets(offsets)
+        for f in range(2):
+            ctx.upload(f, frames[f])
+            r, c, s = ctx.fast_candidates(f)
+            er, ec, es = oracle.fast_candidates(frames[f])
+            assert er.size > (8000 if f else 17000)
+            assert np.array_equal(r, er) and np.array_equal(c, ec) and np.array_equal(s.view(np.uint32), es.view(np.uint32))
+            kr, kc, ks, nc = ctx.fast_detect(f, 2000)
+            okr, okc, oks, onc = oracle.fast_detect(frames[f], 2000)
+            assert nc == onc and np.array_equal(kr, okr) and np.array_equal(kc, okc)
+        out = ctx.process_host_batch(frames, True)
+        exp = oracle.pipeline(frames, offsets, 2000, True, nthreads=2)
+        _same_results(out, exp, 2)
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=H, max_cols=W, max_kp=2000) as ctx:  # default capacity: pixels / 4
+        ctx.upload(0, dense)
+        with pytest.raises(cuda_lib.YavoError):
+            ctx.fast_detect(0)
