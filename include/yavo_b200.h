@@ -50,7 +50,9 @@ typedef enum yavo_status {
 /* One context per GPU.  n_slots device-resident frames of at most max_rows x max_cols pixels;
  * max_kp keypoints kept per frame (the reference's fastCornerNumThreshold, include/FastDetector.hpp:36);
  * max_cand = capacity of the per-frame FAST candidate list (0 = (max_rows-8)*(max_cols-8)/4,
- * i.e. every fourth interior pixel).  */
+ * i.e. every fourth interior pixel; at most 2^24 - 1).  Uniform noise yields 3.7 % of the pixels, real frames under 1 %;
+ * periodic textures can reach 50 % (tests/test_gpu_round2.py: DENSE_PATTERN) — a frame with more candidates than max_cand
+ * is reported with YAVO_ERR_CAPACITY by the call (or the batch ticket) that saw it, never truncated silently.  */
 int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp, int max_cand,
                 yavo_ctx **out);
 void yavo_destroy(yavo_ctx *ctx);
