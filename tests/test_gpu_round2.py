@@ -275,3 +275,46 @@ def test_very_dense_corners_take_several_list_rounds(cuda_lib, oracle, offsets):
         ctx.upload(0, dense)
         with pytest.raises(cuda_lib.YavoError):
             ctx.fast_detect(0)
+
+
+_UMMA_SNIPPET = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r)
+from oracle import pyoracle as po
+from ya_vo_b200 import capi, synth
+off = synth.brief_offsets()
+bad = 0
+for kind, seed, H, W in (("G30", 5, 376, 1241), ("U", 6, 97, 211), ("B4", 7, 33, 130), ("G30", 8, 200, 1280)):
+    frames = synth.synth_batch(3, kind, seed, H, W)
+    if kind == "B4":
+        frames[1, 5:30, 20:100] = 255  # the largest 16-bit row sums
+    with capi.Context(device=0, n_slots=3, max_rows=H, max_cols=W, max_kp=700) as ctx:
+        ctx.set_brief_offsets(off)
+        ctx.upload_batch(0, frames)
+        blur = [ctx.blurred(f) for f in range(3)]
+        out = ctx.process_host_batch(frames, True)
+    exp = po.pipeline(frames, off, 700, True, nthreads=2)
+    for f in range(3):
+        bad += int(np.count_nonzero(blur[f] != po.gaussian_blur(frames[f])))
+        k = exp["n_kp"][f]
+        bad += int(out["n_kp"][f] != k) + int(np.count_nonzero(out["desc"][f, :k] != exp["desc"][f, :k]))
+        bad += int(np.count_nonzero(out["scores"][f, :k].view(np.uint32) != exp["scores"][f, :k].view(np.uint32)))
+print("UMMA_BLUR_MISMATCHES", bad)
+"""
+
+
+def test_blur_on_the_tensor_cores_variant_is_bit_exact(cuda_lib):
+    """build/libyavo_umma.so (-DYAVO_BLUR_UMMA=1, built by __graft_entry__.build()): the 9x9 Gaussian as two banded
+    tcgen05.mma kind::i8 products (blur_umma.cuh).  Not the default (measured slower), but kept exact: blurred planes,
+    descriptors and score bits against the oracle on interior, edge, tiny and saturated frames."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "build", "libyavo_umma.so")
+    if not os.path.exists(lib):
+        pytest.skip("variant library not built")
+    env = dict(os.environ, YAVO_LIB_PATH=lib)
+    r = subprocess.run([sys.executable, "-c", _UMMA_SNIPPET % {"root": root}], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "UMMA_BLUR_MISMATCHES 0" in r.stdout, r.stdout[-500:]

@@ -42,6 +42,7 @@ struct yavo_ctx {
     // device buffers (per slot)
     uint8_t *d_frames = nullptr, *d_blur = nullptr;
     CUtensorMap frames_map;  // d_frames as a 3-D tensor (byte in row, row, slot): K1 stages a tile with one tensor copy
+    uint8_t *d_blur_consts = nullptr;  // the blur's constant band matrices in their shared-memory layout (blur_umma.cuh)
     CUtensorMap blur_map;    // d_blur likewise, box = the 32 x 17 byte patch the BRIEF kernel stages per keypoint
     yavo_ent *d_pool = nullptr;  // per slot max_cand scored corners in tile order (written by K1)
     uint32_t *d_seg = nullptr;   // per slot rows_alloc x seg_cols: pool offset << 8 | count of each (row, tile column)
@@ -334,13 +335,13 @@ int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
     if (do_fast) CK(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)n, ctx->ls));
     if (do_fast && do_blur)
         PROF(KC_DETECT, detect_blur_kernel<true, true><<<grid, K1_THREADS, 0, ctx->ls>>>(
-            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
+            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
     else if (do_fast)
         PROF(KC_DETECT, detect_blur_kernel<true, false><<<grid, K1_THREADS, 0, ctx->ls>>>(
-            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
+            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
     else
         PROF(KC_DETECT, detect_blur_kernel<false, true><<<grid, K1_THREADS, 0, ctx->ls>>>(
-            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc));
+            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
     CK_LAUNCH();
     if (do_blur)
         for (int s = slot0; s < slot0 + n; s++) ctx->slot_blur_valid[s] = 1;
@@ -644,6 +645,15 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_offs, 256));
     CKC(dalloc(&c->d_spos, 256));
     CKC(cudaMemset(c->d_frames, 0, S * c->frame_stride));
+    {
+        std::vector<uint8_t> bc(bu::BU_CONST_BYTES);
+        bu::bu_fill_constants(bc.data());
+        CKC(dalloc(&c->d_blur_consts, bc.size()));
+        CKC(cudaMemcpy(c->d_blur_consts, bc.data(), bc.size(), cudaMemcpyHostToDevice));
+    }
+    // eight CTAs of the detect kernel per SM need the largest shared-memory carve-out
+    CKC(cudaFuncSetAttribute(detect_blur_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CKC(cudaFuncSetAttribute(detect_blur_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (encode_slot_map(c, &c->frames_map, c->d_frames, SROW, SH) != 0 || encode_slot_map(c, &c->blur_map, c->d_blur, BP_ROWB, BP_ROWS) != 0) {
         g_create_error = c->err;
         yavo_destroy(c);
@@ -676,7 +686,7 @@ void yavo_destroy(yavo_ctx *c) {
                     c->d_pairs,  c->d_npairs,  c->d_minDist, c->d_spos,
                     c->d_fpack,  c->d_xchg,    c->d_pre,     c->d_npre,    c->d_team_done,
                     c->d_pyr,    c->d_klt_prev, c->d_klt_next, c->d_klt_status, c->d_klt_err, c->d_trk_xy,
-                    c->d_trk_status, c->d_trk_err};
+                    c->d_trk_status, c->d_trk_err, c->d_blur_consts};
     for (void *b : bufs)
         if (b) cudaFree(b);
     drop_frame_graphs(c);

@@ -10,6 +10,7 @@
 
 #include "fast_core.h"
 #include "select_serial.h"
+#include "blur_umma.cuh"
 
 namespace yavo {
 
@@ -60,6 +61,9 @@ constexpr int SH = TH + 2 * HALO;        // 40 staged rows
 constexpr int K1_THREADS = 256;
 #ifndef YAVO_K1_MIN_CTAS
 #define YAVO_K1_MIN_CTAS 8  // 32 registers per thread: eight CTAs per SM keep the issue slots of this issue-bound kernel full
+#endif
+#ifndef YAVO_BLUR_UMMA
+#define YAVO_BLUR_UMMA 0  // 1: the blur on the tensor cores (blur_umma.cuh: bit-exact, measured slower); 0: IDP.4A / IDP.2A on the integer pipes
 #endif
 constexpr int K1_LIST = 1024;            // corners of a tile listed (and scored densely) per round; a tile with more takes more rounds
 constexpr int SEG_CNT_BITS = 8;          // segment table entry = pool offset << 8 | count (count <= 128 per tile row)
@@ -113,10 +117,20 @@ __global__ void __launch_bounds__(K1_THREADS, YAVO_K1_MIN_CTAS)
 detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base,
                    const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
                    uint8_t *__restrict__ blur, yavo_ent *__restrict__ pool, int max_cand, int *__restrict__ ncand,
-                   uint32_t *__restrict__ seg, int seg_cols, int rows_alloc) {
+                   uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, const uint8_t *__restrict__ blur_consts) {
     __shared__ __align__(128) uint32_t tile[SH][SROW_W];  // staged rows: cols x0-16 .. x0+143
     __shared__ __align__(8) uint64_t tile_bar;
+#if YAVO_BLUR_UMMA
+    constexpr bool UMMA = DO_BLUR;
+    __shared__ __align__(128) uint8_t ub[UMMA ? bu::BU_UB_BYTES : 16];      // the staged rows in core-matrix order
+    __shared__ __align__(128) uint8_t bcst[UMMA ? bu::BU_CONST_BYTES : 16];  // the two constant band matrices
+    __shared__ __align__(8) uint64_t bu_bars[2];
+    __shared__ uint32_t tmem_base_s;
+    if (UMMA) bu::bu_prologue(bcst, blur_consts, bu_bars, &tmem_base_s);
+#else
+    constexpr bool UMMA = false;
     __shared__ uint4 hpair[SH / 2][TW / 4];        // [row pair][quad] -> 4 x (h[even] | h[odd] << 16)
+#endif
     // corners of the tile: per-row bit masks and counts, the row-major corner list, the tile's span in the pool
     __shared__ uint32_t rmask[TH][TW / 32];
     __shared__ int rcnt[TH];
@@ -176,6 +190,15 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
 
     const int lane = tid & 31, warp = tid >> 5;
 
+#if YAVO_BLUR_UMMA
+    uint32_t tmem_base = 0;
+    if (UMMA) {
+        bu::bu_relayout(reinterpret_cast<const uint8_t *>(&tile[0][0]), ub);
+        __syncthreads();
+        tmem_base = tmem_base_s;
+        bu::bu_pass1_issue(ub, bcst, bu_bars, tmem_base);  // the horizontal pass runs under the segment test
+    }
+#else
     if (DO_BLUR) {
         // horizontal pass: (SH/2) row pairs x 32 quads; thread -> one quad of one row pair
         for (int i = tid; i < (SH / 2) * (TW / 4); i += K1_THREADS) {
@@ -189,6 +212,7 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
                                       ha[2] | (hb[2] << 16), ha[3] | (hb[3] << 16));
         }
     }
+#endif
 
     if (DO_FAST) {
         // Segment test, warp -> 4 tile rows, lane -> quad (4 pixels).  Pass A runs the cheap necessary
@@ -200,8 +224,7 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         __shared__ uint8_t flist[NW][RPW * 32];
         const unsigned lt = (1u << lane) - 1u;
         int cnt = 0;
-#pragma unroll
-        for (int k = 0; k < RPW; k++) {
+        auto pass_a = [&](int k) {
             const int tr = warp + NW * k, gr = y0 + tr, sr = tr + HALO;
             bool live = false;
             if (gr >= 4 && gr < H - 4)  // warp-uniform
@@ -210,7 +233,20 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
             const unsigned bl = __ballot_sync(0xffffffffu, live);
             if (live) flist[warp][cnt + __popc(bl & lt)] = (uint8_t)(k * 32 + lane);
             cnt += __popc(bl);
-        }
+        };
+        // With the blur on the tensor cores its steps are interleaved with the balanced parts of the segment test, so
+        // that every tcgen05.mma round trip has a few hundred instructions per warp to hide under.
+        pass_a(0);
+        pass_a(1);
+#if YAVO_BLUR_UMMA
+        if (UMMA) bu::bu_pass1_drain(bcst, bu_bars, tmem_base);  // row sums -> byte operands, first half of the vertical pass issued
+#endif
+        pass_a(2);
+        pass_a(3);
+        static_assert(RPW == 4, "pass A is written out for four rows per warp");
+#if YAVO_BLUR_UMMA
+        if (UMMA) bu::bu_pass2_drain(bcst, bu_bars, tmem_base, ub, 0);  // first half drained, second half issued
+#endif
         __syncwarp();
         for (int i = lane; i < cnt; i += 32) {
             const int e = flist[warp][i], k = e >> 5, q = e & 31;
@@ -274,8 +310,20 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         }
     };
 
+#if YAVO_BLUR_UMMA
+    if (UMMA) {
+        if (!DO_FAST) {
+            bu::bu_pass1_drain(bcst, bu_bars, tmem_base);
+            bu::bu_pass2_drain(bcst, bu_bars, tmem_base, ub, 0);
+        }
+        // second half of the vertical pass drained (its CTA barrier also publishes the masks and counts of the segment
+        // test), TMEM freed, the blurred tile written
+        bu::bu_pass2_drain(bcst, bu_bars, tmem_base, ub, 1);
+        bu::bu_finish(tmem_base, ub, blur + (size_t)f * frame_stride, pitch, H, x0, y0);
+    }
+#endif
     if (DO_FAST) {
-        __syncthreads();  // masks, counts (and the horizontal blur pass) are complete
+        if (!UMMA) __syncthreads();  // masks, counts (and the horizontal blur pass) are complete
         if (tid < 128) {
             int total, row_start, row_cnt;
             build_list(0, &total, &row_start, &row_cnt);
@@ -296,6 +344,7 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         }
     }
 
+#if !YAVO_BLUR_UMMA
     if (DO_BLUR) {
         if (!DO_FAST) __syncthreads();
         // vertical pass: output row pairs (tile rows 2j, 2j+1) x 32 quads
@@ -335,9 +384,11 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
             }
         }
     }
+#endif
 
     if (DO_FAST) {
-        // Harris response of every corner from the staged pixels (reference src/FastDetector.cc:244-273; the 5x5 window
+        // Harris response of every corner from the staged pixels (the kernel's unbalanced tail: a tile's ~45 corners
+        // occupy two warps) (reference src/FastDetector.cc:244-273; the 5x5 window
         // of an interior pixel lies inside the tile + halo), densely: thread i takes corner i of the list
         __syncthreads();
         const int total = s_total, base = s_base;
