@@ -515,7 +515,10 @@ constexpr int SEL_WARPS = SEL_THREADS / 32;
 #define YAVO_SEL_MIN_CTAS 2
 #endif
 constexpr int SEL_SMEM_ENTS = YAVO_SEL_SMEM_ENTS;  // candidates kept in shared memory once the active prefix fits
-constexpr int SEL_WARP_MAX = 512;       // ranges up to this size are partitioned by one warp
+#ifndef YAVO_SEL_WARP_MAX
+#define YAVO_SEL_WARP_MAX 1024  // measured on B200 (1024 frames): 512 0.389 ms, 768 0.371, 1024 0.365, 1536 0.361 (no longer two CTAs' worth of shared memory), 2048 0.53
+#endif
+constexpr int SEL_WARP_MAX = YAVO_SEL_WARP_MAX;  // ranges up to this size are partitioned by one warp
 constexpr int SEL_QCAP = 512;           // shared work queue (ring)
 constexpr int SEL_STACK = 48;           // per-warp private stack
 constexpr int SEL_LOCAL = 64;           // right children up to this size stay with the warp that produced them
@@ -592,9 +595,17 @@ template <typename PosT>
 __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, PosT *Lpos, PosT *Rpos) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = l - f;
-    if (tid == 0) yavo_median_to_first(A, f, l);
-    __syncthreads();
-    const yavo_ent piv = A[f];
+    // __move_median_to_first(first, first+1, mid, last-1): every thread works the pivot out for itself (four broadcast
+    // loads) and classifies against the list as it will look after the move — the entry at `mpos` read as the old
+    // first element — so no barrier and no single-thread section precede the classification; thread 0 performs the
+    // move itself after the first barrier below (every thread has read the four entries by then; the pair swaps, which
+    // may touch `mpos`, come after the loop's last barrier)
+    const int pa = f + 1, pb = f + n / 2, pc = l - 1;
+    const yavo_ent v0 = A[f], va = A[pa], vb = A[pb], vc = A[pc];
+    int mpos;
+    if (yavo_before(va, vb)) mpos = yavo_before(vb, vc) ? pb : (yavo_before(va, vc) ? pc : pa);
+    else mpos = yavo_before(va, vc) ? pa : (yavo_before(vb, vc) ? pc : pb);
+    const yavo_ent piv = mpos == pa ? va : (mpos == pb ? vb : vc);
     const int cap = n / 2 + 1;
     int runL = 0, runR = 0;
     for (int base = 0; base < n - 1; base += SEL_THREADS * SEL_ITEMS) {
@@ -604,8 +615,10 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, PosT
         for (int e = 0; e < SEL_ITEMS; e++) {
             const int i = i0 + e;
             if (i < n - 1) {
-                fL |= (unsigned)(!yavo_before(A[f + 1 + i], piv)) << e;
-                fR |= (unsigned)(!yavo_before(piv, A[l - 1 - i])) << e;
+                const int pl = f + 1 + i, pr = l - 1 - i;
+                const yavo_ent el = A[pl], er = A[pr];
+                fL |= (unsigned)(!yavo_before(pl == mpos ? v0 : el, piv)) << e;
+                fR |= (unsigned)(!yavo_before(piv, pr == mpos ? v0 : er)) << e;
             }
         }
         const int packed = __popc(fL) | (__popc(fR) << 16);
@@ -617,6 +630,10 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, PosT
         }
         if (lane == 31) S.wtot[warp] = incl;
         __syncthreads();
+        if (base == 0 && tid == 0) {  // the move of the median to the front
+            A[f] = piv;
+            A[mpos] = v0;
+        }
         int pre = 0, tot = 0;
 #pragma unroll
         for (int w = 0; w < SEL_WARPS; w++) {
@@ -679,58 +696,69 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, PosT
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) S.wtot[warp] = cnt;
     __syncthreads();
-    if (tid == 0) {
-        int m = 0;
-        for (int w = 0; w < SEL_WARPS; w++) m += S.wtot[w];
-        uint32_t cut = 0xffffffffu;
-        if (m < nL) cut = (uint32_t)Lpos[m];
-        if (m >= 1) cut = min(cut, (uint32_t)Rpos[m - 1]);
-        S.bcast[0] = f + (int)cut;
-    }
-    __syncthreads();
-    const int cut = S.bcast[0];
-    __syncthreads();
-    return cut;
+    int m = 0;  // every thread sums the swap counts and reads the two stopper positions that bound the cut
+#pragma unroll
+    for (int w = 0; w < SEL_WARPS; w++) m += S.wtot[w];
+    uint32_t cut = 0xffffffffu;
+    if (m < nL) cut = (uint32_t)Lpos[m];
+    if (m >= 1) cut = min(cut, (uint32_t)Rpos[m - 1]);
+    __syncthreads();  // the next partition reuses the counts and the stopper lists
+    return f + (int)cut;
 }
 
-// single-warp partition of [f,l), 16 < n <= SEL_WARP_MAX; positions relative to f in 16-bit scratch
+// single-warp partition of [f,l), 16 < n <= SEL_WARP_MAX; positions relative to f in 16-bit scratch.
+// Written for latency (a frame's phase 2 is ~400 of these, each a chain of dependent shared-memory round trips on a
+// warp that has nothing else to do): every lane reads the four median candidates itself (broadcast loads, no
+// shuffles) and classifies against the list as it will look after __move_median_to_first — the entry at `mpos` read
+// as the old first element — so the move itself (lane 0) happens off the critical path; two 32-element chunks are
+// loaded before either is classified.
 __device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *Lpos = S.wscratch[warp][0], *Rpos = S.wscratch[warp][1];
     const int n = l - f;
-    // __move_median_to_first(first, first+1, mid, last-1): lanes 0..3 fetch first / a / b / c in parallel
-    yavo_ent piv;
-    {
-        const int mid = f + n / 2;
-        const int pos = lane == 0 ? f : (lane == 1 ? f + 1 : (lane == 2 ? mid : l - 1));
-        const yavo_ent v = lane < 4 ? A[pos] : 0ull;
-        const yavo_ent v0 = __shfl_sync(0xffffffffu, v, 0), va = __shfl_sync(0xffffffffu, v, 1);
-        const yavo_ent vb = __shfl_sync(0xffffffffu, v, 2), vc = __shfl_sync(0xffffffffu, v, 3);
-        int m;  // which of a (1), b (2), c (3) is the median, by libstdc++'s comparison sequence
-        if (yavo_before(va, vb)) m = yavo_before(vb, vc) ? 2 : (yavo_before(va, vc) ? 3 : 1);
-        else m = yavo_before(va, vc) ? 1 : (yavo_before(vb, vc) ? 3 : 2);
-        piv = m == 1 ? va : (m == 2 ? vb : vc);
-        const int mpos = m == 1 ? f + 1 : (m == 2 ? mid : l - 1);
-        if (lane == 0) {
-            A[f] = piv;
-            A[mpos] = v0;
-        }
-        __syncwarp();
-    }
+    // __move_median_to_first(first, first+1, mid, last-1), libstdc++'s comparison sequence
+    const int pa = f + 1, pb = f + n / 2, pc = l - 1;
+    const yavo_ent v0 = A[f], va = A[pa], vb = A[pb], vc = A[pc];
+    int mpos;
+    if (yavo_before(va, vb)) mpos = yavo_before(vb, vc) ? pb : (yavo_before(va, vc) ? pc : pa);
+    else mpos = yavo_before(va, vc) ? pa : (yavo_before(vb, vc) ? pc : pb);
+    const yavo_ent piv = mpos == pa ? va : (mpos == pb ? vb : vc);
     const int cap = n / 2 + 1;
+    const unsigned lt = (1u << lane) - 1u;
     int runL = 0, runR = 0;
-    for (int base = 0; base < n - 1; base += 32) {
-        const int i = base + lane;
-        const bool in = i < n - 1;
-        const bool sL = in && !yavo_before(A[f + 1 + i], piv);
-        const bool sR = in && !yavo_before(piv, A[l - 1 - i]);
-        const unsigned bL = __ballot_sync(0xffffffffu, sL), bR = __ballot_sync(0xffffffffu, sR);
-        const unsigned lt = (1u << lane) - 1u;
-        const int rL = runL + __popc(bL & lt), rR = runR + __popc(bR & lt);
-        if (sL && rL < cap) Lpos[rL] = (uint16_t)(1 + i);
-        if (sR && rR < cap) Rpos[rR] = (uint16_t)(n - 1 - i);
-        runL += __popc(bL);
-        runR += __popc(bR);
+    for (int base = 0; base < n - 1; base += 64) {
+        const int i0 = base + lane, i1 = i0 + 32;
+        const bool in0 = i0 < n - 1, in1 = i1 < n - 1;
+        yavo_ent l0 = 0ull, r0 = 0ull, l1 = 0ull, r1 = 0ull;
+        if (in0) {
+            l0 = A[f + 1 + i0];
+            r0 = A[l - 1 - i0];
+        }
+        if (in1) {
+            l1 = A[f + 1 + i1];
+            r1 = A[l - 1 - i1];
+        }
+        if (f + 1 + i0 == mpos) l0 = v0;
+        if (l - 1 - i0 == mpos) r0 = v0;
+        if (f + 1 + i1 == mpos) l1 = v0;
+        if (l - 1 - i1 == mpos) r1 = v0;
+        const bool sL0 = in0 && !yavo_before(l0, piv), sR0 = in0 && !yavo_before(piv, r0);
+        const bool sL1 = in1 && !yavo_before(l1, piv), sR1 = in1 && !yavo_before(piv, r1);
+        const unsigned bL0 = __ballot_sync(0xffffffffu, sL0), bR0 = __ballot_sync(0xffffffffu, sR0);
+        const unsigned bL1 = __ballot_sync(0xffffffffu, sL1), bR1 = __ballot_sync(0xffffffffu, sR1);
+        const int cL0 = __popc(bL0), cR0 = __popc(bR0);
+        const int rL0 = runL + __popc(bL0 & lt), rR0 = runR + __popc(bR0 & lt);
+        const int rL1 = runL + cL0 + __popc(bL1 & lt), rR1 = runR + cR0 + __popc(bR1 & lt);
+        if (sL0 && rL0 < cap) Lpos[rL0] = (uint16_t)(1 + i0);
+        if (sR0 && rR0 < cap) Rpos[rR0] = (uint16_t)(n - 1 - i0);
+        if (sL1 && rL1 < cap) Lpos[rL1] = (uint16_t)(1 + i1);
+        if (sR1 && rR1 < cap) Rpos[rR1] = (uint16_t)(n - 1 - i1);
+        runL += cL0 + __popc(bL1);
+        runR += cR0 + __popc(bR1);
+    }
+    if (lane == 0) {  // the move of the median to the front (every lane holds the four entries it read above)
+        A[f] = piv;
+        A[mpos] = v0;
     }
     __syncwarp();
     const int nL = min(runL, cap), nR = min(runR, cap);
@@ -762,7 +790,8 @@ __device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
 }
 
 // stable sort of a range of <= 16 elements by one warp (what __final_insertion_sort does to it):
-// rank = elements that sort strictly before + equal elements that come earlier
+// rank = elements that sort strictly before + equal elements that come earlier.  (Sixteen unrolled shuffles instead of
+// the loop over the range's length: measured slower, 0.398 vs 0.366 ms per 1024 frames — the leaves are short.)
 __device__ __forceinline__ void sel_warp_leaf(yavo_ent *A, int f, int l) {
     const int lane = threadIdx.x & 31, n = l - f;
     const yavo_ent e = (lane < n) ? A[f + lane] : 0ull;
