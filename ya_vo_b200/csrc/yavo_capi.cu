@@ -7,6 +7,7 @@
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -42,6 +43,7 @@ struct yavo_ctx {
     // device buffers (per slot)
     uint8_t *d_frames = nullptr, *d_blur = nullptr;
     CUtensorMap frames_map;  // d_frames as a 3-D tensor (byte in row, row, slot): K1 stages a tile with one tensor copy
+    bool batch_select_only = false;    // YAVO_SELECT_SINGLE=0: the batch instance of the select kernel on single frames too (A/B runs)
     uint8_t *d_blur_consts = nullptr;  // the blur's constant band matrices in their shared-memory layout (blur_umma.cuh)
     CUtensorMap blur_map;    // d_blur likewise, box = the 32 x 17 byte patch the BRIEF kernel stages per keypoint
     yavo_ent *d_pool = nullptr;  // per slot max_cand scored corners in tile order (written by K1)
@@ -135,6 +137,7 @@ struct yavo_ctx {
     std::vector<uint8_t *> h_shadow;
     std::vector<size_t> h_shadow_bytes;
     std::vector<int> shadow_rows, shadow_cols;  // 0 = the slot's shadow does not describe its current contents
+    std::vector<int> stage_cols;                // width of the frame last staged in the slot's shadow (its row padding is zero for that width)
     uint8_t *h_fout = nullptr;  // pinned: 4 ints + 6 x K ints + 32 x K bytes
     uint32_t *d_fpack = nullptr;  // the same on the device (pack_frame_kernel)
     uint8_t *h_mstage = nullptr;  // pinned staging of yavo_match: descriptors in, (idx, dist, second, rev) out
@@ -228,7 +231,8 @@ int encode_slot_map(yavo_ctx *ctx, CUtensorMap *map, void *base, int box_w, int 
     return 0;
 }
 
-size_t select_smem_bytes() { return ((sizeof(SelShared) + 15) & ~size_t(15)) + sizeof(yavo_ent) * SEL_SMEM_ENTS; }
+template <int NT>
+size_t select_smem_bytes() { return ((sizeof(SelSharedT<NT>) + 15) & ~size_t(15)) + sizeof(yavo_ent) * SEL_SMEM_ENTS; }
 
 void drop_frame_graphs(yavo_ctx *ctx) {
     for (auto &g : ctx->frame_graphs) cudaGraphExecDestroy(g.exec);
@@ -366,15 +370,22 @@ int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
         CK_LAUNCH();
     }
     const int team = big ? BIG_CL : 1;
-    PROF(KC_SELECT, select_topk_kernel<<<n * team, SEL_THREADS, select_smem_bytes(), ctx->ls>>>(
-        ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW,
-        ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0,
-        ctx->d_scratch + (size_t)slot0 * (2 * (size_t)ctx->max_cand + 8), K, H, W, ctx->max_kp,
-        ctx->d_kp_row + o,
-        ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o,
-        ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->cur_status,
-        big ? ctx->d_pre + (size_t)slot0 * BIG_PRE : nullptr, big ? ctx->d_npre + slot0 : nullptr, team,
-        big ? ctx->d_team_done + slot0 : nullptr));
+    // one frame on an otherwise idle GPU: the instance with twice the warps (phase 2 is a work queue served by the warps)
+    const bool single = n == 1 && !big && !ctx->batch_select_only;
+#define YAVO_SELECT_ARGS \
+    ctx->d_seg + (size_t)slot0 * ctx->rows_alloc * ctx->seg_cols, ctx->seg_cols, ctx->rows_alloc, (W + TW - 1) / TW, \
+    ctx->d_pool + (size_t)slot0 * ctx->max_cand, ctx->d_cand + (size_t)slot0 * ctx->max_cand, ctx->max_cand, ctx->d_ncand + slot0, \
+    ctx->d_scratch + (size_t)slot0 * (2 * (size_t)ctx->max_cand + 8), K, H, W, ctx->max_kp, \
+    ctx->d_kp_row + o, \
+    ctx->d_kp_col + o, ctx->d_kp_score + o, ctx->d_nkp + slot0, ctx->d_bk_row + o, ctx->d_bk_col + o, \
+    ctx->d_bk_score + o, ctx->d_bk_id + o, ctx->d_nbk + slot0, ctx->cur_status, \
+    big ? ctx->d_pre + (size_t)slot0 * BIG_PRE : nullptr, big ? ctx->d_npre + slot0 : nullptr, team, \
+    big ? ctx->d_team_done + slot0 : nullptr
+    if (single)
+        PROF(KC_SELECT, select_topk_kernel<SEL_THREADS_SINGLE><<<n * team, SEL_THREADS_SINGLE, select_smem_bytes<SEL_THREADS_SINGLE>(), ctx->ls>>>(YAVO_SELECT_ARGS));
+    else
+        PROF(KC_SELECT, select_topk_kernel<SEL_THREADS_BATCH><<<n * team, SEL_THREADS_BATCH, select_smem_bytes<SEL_THREADS_BATCH>(), ctx->ls>>>(YAVO_SELECT_ARGS));
+#undef YAVO_SELECT_ARGS
     CK_LAUNCH();
     return 0;
 }
@@ -645,6 +656,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(dalloc(&c->d_offs, 256));
     CKC(dalloc(&c->d_spos, 256));
     CKC(cudaMemset(c->d_frames, 0, S * c->frame_stride));
+    if (const char *e = getenv("YAVO_SELECT_SINGLE")) c->batch_select_only = atoi(e) == 0;  // A/B runs of the single-frame instance
     {
         std::vector<uint8_t> bc(bu::BU_CONST_BYTES);
         bu::bu_fill_constants(bc.data());
@@ -663,8 +675,10 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(cudaMemset(c->d_nbk, 0, S * sizeof(int)));
     CKC(cudaMemset(c->d_nkp, 0, S * sizeof(int)));
     CKC(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), 64 * sizeof(int)));
-    CKC(cudaFuncSetAttribute(select_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)select_smem_bytes()));
+    CKC(cudaFuncSetAttribute(select_topk_kernel<SEL_THREADS_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)select_smem_bytes<SEL_THREADS_BATCH>()));
+    CKC(cudaFuncSetAttribute(select_topk_kernel<SEL_THREADS_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)select_smem_bytes<SEL_THREADS_SINGLE>()));
     CKC(cudaFuncSetAttribute(tcm::match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm::SMEM_BYTES));
     CKC(cudaFuncSetAttribute(tcm4::match_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm4::SMEM4_BYTES));
     CKC(cudaFuncSetAttribute(tcm4::match_tc4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tcm4::SMEM4_BYTES));
@@ -879,15 +893,15 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
     if (!ctx->offs_set) return fail(ctx, YAVO_ERR_STATE, "yavo_set_brief_offsets has not been called");
     CK(cudaSetDevice(ctx->device));
     const int K = max_kp;
-    const size_t fbytes = (size_t)rows * cols;
-    if (ctx->s_h2d) CK(cudaStreamSynchronize(ctx->s_h2d));  // the pipelined path shares d_raw
-    ctx->raw_used[0] = ctx->raw_used[1] = 0;
-    if (int r = ensure_raw(ctx, fbytes)) return r;
+    // The frame is staged in pinned memory in the slot's own layout (rows at the device pitch, padding zero) and
+    // copied straight into the slot: no dense staging buffer on the device, no re-pitch kernel on this path.
+    const size_t fbytes = (size_t)rows * ctx->pitch;
     if (ctx->h_shadow.empty()) {
         ctx->h_shadow.assign(ctx->n_slots, nullptr);
         ctx->h_shadow_bytes.assign(ctx->n_slots, 0);
         ctx->shadow_rows.assign(ctx->n_slots, 0);
         ctx->shadow_cols.assign(ctx->n_slots, 0);
+        ctx->stage_cols.assign(ctx->n_slots, 0);
     }
     if (fbytes > ctx->h_shadow_bytes[slot]) {
         CK(cudaStreamSynchronize(ctx->stream));
@@ -900,11 +914,16 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
         if (ctx->h_shadow[slot]) CK(cudaFreeHost(ctx->h_shadow[slot]));
         ctx->h_shadow[slot] = nullptr;
         ctx->h_shadow_bytes[slot] = 0;
-        const size_t want = std::max(fbytes, (size_t)ctx->max_rows * ctx->max_cols);
+        const size_t want = std::max(fbytes, (size_t)ctx->max_rows * ctx->pitch);
         CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_shadow[slot]), want));
         ctx->h_shadow_bytes[slot] = want;
+        ctx->stage_cols[slot] = 0;
     }
     uint8_t *stage = ctx->h_shadow[slot];
+    if (ctx->stage_cols[slot] != cols) {  // a frame of another width was staged here: its pixels must not remain in the row padding
+        memset(stage, 0, ctx->h_shadow_bytes[slot]);
+        ctx->stage_cols[slot] = cols;
+    }
     const size_t out_ints = 4 + 6 * (size_t)ctx->max_kp, out_bytes = out_ints * 4 + 32 * (size_t)ctx->max_kp;
     if (!ctx->h_fout) {
         CK(cudaMallocHost(reinterpret_cast<void **>(&ctx->h_fout), out_bytes));
@@ -915,9 +934,12 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
     float *h_ks = reinterpret_cast<float *>(h_bi + ctx->max_kp);
     uint8_t *h_desc = ctx->h_fout + out_ints * 4;
     // the previous call's graph has been waited for: the staging buffers are free
-    if (stride == cols) memcpy(stage, pixels, fbytes);
-    else
-        for (int r = 0; r < rows; r++) memcpy(stage + (size_t)r * cols, pixels + (size_t)r * stride, cols);
+    for (int r = 0; r < rows; r++) memcpy(stage + (size_t)r * ctx->pitch, pixels + (size_t)r * stride, cols);
+    // host-side bookkeeping of an upload (what launch_repitch does on the batch paths)
+    ctx->slot_rows[slot] = rows;
+    ctx->slot_cols[slot] = cols;
+    ctx->slot_blur_valid[slot] = 0;
+    ctx->slot_pyr[slot] = 0;
     cudaGraphExec_t exec = nullptr;
     int graph_launches = 0;
     for (auto &g : ctx->frame_graphs)
@@ -933,8 +955,7 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
         int rc = 0;
         do {
             const size_t o = (size_t)slot * ctx->max_kp;
-            if (cudaMemcpyAsync(ctx->d_raw, stage, fbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = YAVO_ERR_CUDA; break; }
-            if ((rc = launch_repitch(ctx, ctx->d_raw, cols, slot, 1, rows, cols))) break;
+            if (cudaMemcpyAsync(ctx->d_frames + ctx->frame_stride * slot, stage, fbytes, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { rc = YAVO_ERR_CUDA; break; }
             if ((rc = launch_detect(ctx, slot, 1, true, true))) break;
             if ((rc = launch_select(ctx, slot, 1, K))) break;
             const int kp_per_block = (K4_THREADS / 32) * BP_KPW;
@@ -967,11 +988,7 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
             return rc;
         }
     } else {
-        // host-side bookkeeping the captured launch helpers did when the graph was recorded
-        ctx->slot_rows[slot] = rows;
-        ctx->slot_cols[slot] = cols;
-        ctx->slot_pyr[slot] = 0;
-        ctx->launches += graph_launches;
+        ctx->launches += graph_launches;  // the launch counter the captured helpers advanced when the graph was recorded
     }
     if (exec && !ctx->profiling) CK(cudaGraphLaunch(exec, ctx->stream));
     ctx->slot_blur_valid[slot] = 1;
@@ -999,10 +1016,9 @@ int yavo_frame_features(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows
 int yavo_slot_holds(yavo_ctx *ctx, int slot, const uint8_t *pixels, int rows, int cols, int stride) {
     if (!ctx || slot < 0 || slot >= ctx->n_slots || !pixels || stride < cols) return YAVO_ERR_INVALID;
     if (ctx->shadow_rows.empty() || ctx->shadow_rows[slot] != rows || ctx->shadow_cols[slot] != cols || rows < 1) return 0;
-    const uint8_t *sh = ctx->h_shadow[slot];
-    if (stride == cols) return memcmp(sh, pixels, (size_t)rows * cols) == 0 ? 1 : 0;
+    const uint8_t *sh = ctx->h_shadow[slot];  // rows at the device pitch
     for (int r = 0; r < rows; r++)
-        if (memcmp(sh + (size_t)r * cols, pixels + (size_t)r * stride, cols) != 0) return 0;
+        if (memcmp(sh + (size_t)r * ctx->pitch, pixels + (size_t)r * stride, cols) != 0) return 0;
     return 1;
 }
 

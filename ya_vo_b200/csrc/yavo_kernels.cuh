@@ -506,8 +506,8 @@ gather_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, in
 #ifndef YAVO_SEL_SLEEP
 #define YAVO_SEL_SLEEP 64
 #endif
-constexpr int SEL_THREADS = YAVO_SEL_THREADS;
-constexpr int SEL_WARPS = SEL_THREADS / 32;
+constexpr int SEL_THREADS_BATCH = YAVO_SEL_THREADS;  // CTA size of the batch instance (many frames in flight, two CTAs per SM)
+constexpr int SEL_THREADS_SINGLE = 768;              // the single-frame instance: one CTA on an idle GPU, twice the warps for phase 2
 #ifndef YAVO_SEL_SMEM_ENTS
 #define YAVO_SEL_SMEM_ENTS 6144  // measured on B200: 6144 entries at 2 CTAs/SM beat 4096@3, 4096@2 and 8192@2 (leaves L1 for the scoring loads)
 #endif
@@ -521,6 +521,9 @@ constexpr int SEL_SMEM_ENTS = YAVO_SEL_SMEM_ENTS;  // candidates kept in shared 
 constexpr int SEL_WARP_MAX = YAVO_SEL_WARP_MAX;  // ranges up to this size are partitioned by one warp
 constexpr int SEL_QCAP = 512;           // shared work queue (ring)
 constexpr int SEL_STACK = 48;           // per-warp private stack
+#ifndef YAVO_SEL_LOCAL_SINGLE
+#define YAVO_SEL_LOCAL_SINGLE 16  // the single-frame instance hands almost every right child to the queue (idle warps): 62.6 -> 58 us
+#endif
 constexpr int SEL_LOCAL = 64;           // right children up to this size stay with the warp that produced them
 constexpr int SEL_BIG = 64;             // per-level list of CTA-partitioned ranges
 
@@ -528,7 +531,9 @@ struct SelRange {
     int f, l, d;
 };
 
-struct SelShared {
+template <int NT>
+struct SelSharedT {
+    static constexpr int SEL_WARPS = NT / 32;
     SelRange ring[SEL_QCAP];
     int ready[SEL_QCAP];
     SelRange stack[SEL_WARPS][SEL_STACK];
@@ -542,7 +547,9 @@ struct SelShared {
 };
 
 // queue a range for phase 2 (one thread).  Returns false when the ring is full.
-__device__ __forceinline__ bool sel_push(SelShared &S, const SelRange &r) {
+template <int NT>
+__device__ __forceinline__ bool sel_push(SelSharedT<NT> &S, const SelRange &r) {
+    constexpr int SEL_WARPS = NT / 32;
     const int head = *(volatile int *)&S.q_head, tail = *(volatile int *)&S.q_tail;
     if (tail - head >= SEL_QCAP - 2 * SEL_WARPS) return false;
     const int idx = atomicAdd(&S.q_tail, 1);
@@ -553,7 +560,8 @@ __device__ __forceinline__ bool sel_push(SelShared &S, const SelRange &r) {
 }
 
 // warp-collective pop; returns false once no work is left anywhere in the CTA
-__device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
+template <int NT>
+__device__ __forceinline__ bool sel_pop(SelSharedT<NT> &S, SelRange &out) {
     const int lane = threadIdx.x & 31;
     int got = -1;
     if (lane == 0) {
@@ -591,8 +599,9 @@ __device__ __forceinline__ bool sel_pop(SelShared &S, SelRange &out) {
 // Each thread classifies SEL_ITEMS consecutive positions per pass (one block-wide scan per 4096 elements).
 constexpr int SEL_ITEMS = 8;
 
-template <typename PosT>
-__device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, PosT *Lpos, PosT *Rpos) {
+template <int NT, typename PosT>
+__device__ int sel_block_partition(SelSharedT<NT> &S, yavo_ent *A, int f, int l, PosT *Lpos, PosT *Rpos) {
+    constexpr int SEL_THREADS = NT, SEL_WARPS = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = l - f;
     // __move_median_to_first(first, first+1, mid, last-1): every thread works the pivot out for itself (four broadcast
@@ -712,7 +721,8 @@ __device__ int sel_block_partition(SelShared &S, yavo_ent *A, int f, int l, PosT
 // shuffles) and classifies against the list as it will look after __move_median_to_first — the entry at `mpos` read
 // as the old first element — so the move itself (lane 0) happens off the critical path; two 32-element chunks are
 // loaded before either is classified.
-__device__ int sel_warp_partition(SelShared &S, yavo_ent *A, int f, int l) {
+template <int NT>
+__device__ int sel_warp_partition(SelSharedT<NT> &S, yavo_ent *A, int f, int l) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t *Lpos = S.wscratch[warp][0], *Rpos = S.wscratch[warp][1];
     const int n = l - f;
@@ -814,7 +824,8 @@ __device__ long long g_sel_dbg[8];  // [0] partition cycles [1] partitions [2] l
 #define SEL_DBG_ADD(i, v) do { } while (0)
 #endif
 
-__device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
+template <int NT>
+__device__ void sel_warp_work(SelSharedT<NT> &S, yavo_ent *A, SelRange cur, int K) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // Right children of at most SEL_LOCAL elements stay on this warp's private stack: no queue traffic, no
     // atomics — most partitions are of small ranges.  Larger ones go to the shared queue so idle warps can take
@@ -857,7 +868,7 @@ __device__ void sel_warp_work(SelShared &S, yavo_ent *A, SelRange cur, int K) {
             const bool vR = cut < K && cur.l - cut > 1;
             if (vL && vR) {
                 bool stacked = false;
-                if (right.l - right.f <= SEL_LOCAL && sp < SEL_STACK) {
+                if (right.l - right.f <= (NT == SEL_THREADS_BATCH ? SEL_LOCAL : YAVO_SEL_LOCAL_SINGLE) && sp < SEL_STACK) {
                     stacked = true;
                 } else {
                     int pushed = 0;
@@ -1169,11 +1180,11 @@ __device__ __forceinline__ bool brief_admits(int row, int col, int H, int W) {
     return !(col - 8 < 0 || col + 8 > W || row - 8 < 0 || row + 8 > H);
 }
 
-#ifdef YAVO_SEL_MAXREG  // tuning experiments: cap the registers so that other kernels' CTAs fit beside two select CTAs
-__global__ void __maxnreg__(YAVO_SEL_MAXREG)
-#else
-__global__ void __launch_bounds__(SEL_THREADS, YAVO_SEL_MIN_CTAS)
-#endif
+// Two instances: NT = SEL_THREADS_BATCH for batches (hundreds of frames in flight, two CTAs per SM) and
+// NT = SEL_THREADS_SINGLE for the single-frame path (yavo_frame_features / yavo_fast_detect on one slot: the GPU is
+// otherwise idle, so the one CTA takes twice the warps for the work queue of phase 2).
+template <int NT>
+__global__ void __launch_bounds__(NT, NT == SEL_THREADS_BATCH ? YAVO_SEL_MIN_CTAS : 1)
 select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, int ntx,
                    const yavo_ent *__restrict__ pool, yavo_ent *__restrict__ cand_all, int max_cand,
                    const int *__restrict__ ncand, uint32_t *__restrict__ scratch_all, int K, int H, int W, int kp_stride,
@@ -1186,6 +1197,8 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
                    int team = 1 /* CTAs per frame (> 1 only together with the cluster pre-partition) */,
                    int *__restrict__ team_done = nullptr) {
     extern __shared__ __align__(16) unsigned char sel_smem_raw[];
+    constexpr int SEL_THREADS = NT, SEL_WARPS = NT / 32;
+    using SelShared = SelSharedT<NT>;
     SelShared &S = *reinterpret_cast<SelShared *>(sel_smem_raw);
     yavo_ent *sbuf = reinterpret_cast<yavo_ent *>(sel_smem_raw + ((sizeof(SelShared) + 15) & ~size_t(15)));
 
@@ -1265,8 +1278,8 @@ select_topk_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_allo
                 __syncthreads();
                 continue;
             }
-            cut = in_smem ? sel_block_partition<uint16_t>(S, A, r.f, r.l, S.bscratch[0], S.bscratch[1])
-                          : sel_block_partition<uint32_t>(S, A, r.f, r.l, Lbase + 2 * (size_t)r.f,
+            cut = in_smem ? sel_block_partition<NT, uint16_t>(S, A, r.f, r.l, S.bscratch[0], S.bscratch[1])
+                          : sel_block_partition<NT, uint32_t>(S, A, r.f, r.l, Lbase + 2 * (size_t)r.f,
                                                           Lbase + 2 * (size_t)r.f + ((r.l - r.f) / 2 + 2));
             if (tid == 0) {
                 const SelRange ch[2] = {{r.f, cut, r.d - 1}, {cut, r.l, r.d - 1}};
