@@ -318,3 +318,23 @@ def test_blur_on_the_tensor_cores_variant_is_bit_exact(cuda_lib):
     r = subprocess.run([sys.executable, "-c", _UMMA_SNIPPET % {"root": root}], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert "UMMA_BLUR_MISMATCHES 0" in r.stdout, r.stdout[-500:]
+
+
+def test_frame_features_frames_of_different_widths_on_one_slot(cuda_lib, oracle, offsets):
+    """The single-frame path stages a frame at the device pitch and copies it straight into the slot: after a wide frame a
+    narrower one must not see the wide frame's pixels in its row padding (blur reflects at the new width, the detector's
+    staged tiles read beyond it), and the slot must download as the narrow frame."""
+    wide = synth.synth_frame("G30", 41, 120, 500)
+    narrow = synth.synth_frame("G30", 42, 90, 333)
+    with cuda_lib.Context(device=0, n_slots=1, max_rows=120, max_cols=500, max_kp=600) as ctx:
+        ctx.set_brief_offsets(offsets)
+        for img in (wide, narrow, wide, narrow):
+            ff = ctx.frame_features(0, img, 600)
+            er, ec, es, enc = oracle.fast_detect(img, 600)
+            d, v, _ = oracle.brief(img, offsets, er, ec)
+            assert ff["n_cand"] == enc and np.array_equal(ff["rows"], er) and np.array_equal(ff["cols"], ec)
+            assert np.array_equal(ff["scores"].view(np.uint32), es.view(np.uint32))
+            assert np.array_equal(ff["desc"], d[v])
+            ctx._shape[0] = img.shape
+            assert np.array_equal(ctx.download(0), img)
+            assert np.array_equal(ctx.blurred(0), oracle.gaussian_blur(img))

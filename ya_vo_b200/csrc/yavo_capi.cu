@@ -675,6 +675,7 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     CKC(cudaMemset(c->d_nbk, 0, S * sizeof(int)));
     CKC(cudaMemset(c->d_nkp, 0, S * sizeof(int)));
     CKC(cudaMallocHost(reinterpret_cast<void **>(&c->h_small), 64 * sizeof(int)));
+    if (BIG_CL > 8) CKC(cudaFuncSetAttribute(select_big_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     CKC(cudaFuncSetAttribute(select_topk_kernel<SEL_THREADS_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)select_smem_bytes<SEL_THREADS_BATCH>()));
     CKC(cudaFuncSetAttribute(select_topk_kernel<SEL_THREADS_SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -932,7 +932,10 @@ __device__ void sel_warp_work(SelSharedT<NT> &S, yavo_ent *A, SelRange cur, int 
 // Counts travel through a small global exchange block: the cluster barrier (release / acquire at cluster scope)
 // orders them, and the 8 CTAs of a cluster are co-scheduled by construction, so the barrier cannot deadlock.
 // ================================================================================================
-constexpr int BIG_CL = 8;          // CTAs per cluster (portable maximum)
+#ifndef YAVO_BIG_CL
+#define YAVO_BIG_CL 8
+#endif
+constexpr int BIG_CL = YAVO_BIG_CL;  // CTAs per cluster (8 = the portable maximum; 16 needs the non-portable opt-in)
 constexpr int BIG_THREADS = 512;
 constexpr int BIG_ITEMS = 8;
 constexpr int BIG_PRE = 64;        // ranges handed to the select kernel per frame
