@@ -425,18 +425,31 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
 // segment's position in the candidate list.  The select kernel calls this while it loads its sort buffer; the
 // stand-alone kernel serves yavo_fast_candidates.  All threads of the CTA take part.
 // ================================================================================================
+// Latency matters here (the select kernel cannot start before its list is loaded, and a thread's segments are few):
+// a thread's segment entries are loaded GC at a time, and the first two pool entries of each of those segments are in
+// flight together before any of them is stored (a tile row holds 1.4 corners on average on the benchmark's frames;
+// longer segments finish in a plain loop).
+constexpr int GC = 8;
+
 template <int NTHREADS>
 __device__ int gather_candidates(const uint32_t *__restrict__ seg_f, int seg_cols, int H, int ntx,
                                  const yavo_ent *__restrict__ pool_f, yavo_ent *dst, int dst_cap, int *s_wtot /* NTHREADS / 32 ints */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int S = H * ntx, per = (S + NTHREADS - 1) / NTHREADS;
     const int e0 = min(S, tid * per), e1 = min(S, e0 + per);
+    constexpr uint32_t CNT_MASK = (1u << SEG_CNT_BITS) - 1u;
     int mine = 0;
     {
         int row = e0 / ntx, tx = e0 - row * ntx;
-        for (int e = e0; e < e1; e++) {
-            mine += (int)(seg_f[(size_t)row * seg_cols + tx] & ((1u << SEG_CNT_BITS) - 1u));
-            if (++tx == ntx) { tx = 0; row++; }
+        for (int b = e0; b < e1; b += GC) {
+            uint32_t sg[GC];
+#pragma unroll
+            for (int j = 0; j < GC; j++) {
+                sg[j] = b + j < e1 ? seg_f[(size_t)row * seg_cols + tx] : 0u;
+                if (++tx == ntx) { tx = 0; row++; }
+            }
+#pragma unroll
+            for (int j = 0; j < GC; j++) mine += (int)(sg[j] & CNT_MASK);
         }
     }
     int incl = mine;
@@ -457,13 +470,32 @@ __device__ int gather_candidates(const uint32_t *__restrict__ seg_f, int seg_col
     if (total <= dst_cap) {
         int o = pre + incl - mine;
         int row = e0 / ntx, tx = e0 - row * ntx;
-        for (int e = e0; e < e1; e++) {
-            const uint32_t sg = seg_f[(size_t)row * seg_cols + tx];
-            const int cnt = (int)(sg & ((1u << SEG_CNT_BITS) - 1u));
-            const yavo_ent *src = pool_f + (sg >> SEG_CNT_BITS);
-            for (int k = 0; k < cnt; k++) dst[o + k] = src[k];
-            o += cnt;
-            if (++tx == ntx) { tx = 0; row++; }
+        for (int b = e0; b < e1; b += GC) {
+            uint32_t sg[GC];
+#pragma unroll
+            for (int j = 0; j < GC; j++) {
+                sg[j] = b + j < e1 ? seg_f[(size_t)row * seg_cols + tx] : 0u;
+                if (++tx == ntx) { tx = 0; row++; }
+            }
+            yavo_ent v0[GC], v1[GC];
+#pragma unroll
+            for (int j = 0; j < GC; j++) {
+                const int cnt = (int)(sg[j] & CNT_MASK);
+                const yavo_ent *src = pool_f + (sg[j] >> SEG_CNT_BITS);
+                v0[j] = cnt > 0 ? src[0] : 0ull;
+                v1[j] = cnt > 1 ? src[1] : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < GC; j++) {
+                const int cnt = (int)(sg[j] & CNT_MASK);
+                if (cnt > 0) dst[o] = v0[j];
+                if (cnt > 1) dst[o + 1] = v1[j];
+                if (cnt > 2) {
+                    const yavo_ent *src = pool_f + (sg[j] >> SEG_CNT_BITS);
+                    for (int k = 2; k < cnt; k++) dst[o + k] = src[k];
+                }
+                o += cnt;
+            }
         }
     }
     __syncthreads();
