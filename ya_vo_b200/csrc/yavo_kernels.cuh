@@ -833,7 +833,9 @@ __device__ int sel_warp_partition(SelSharedT<NT> &S, yavo_ent *A, int f, int l) 
 
 // stable sort of a range of <= 16 elements by one warp (what __final_insertion_sort does to it):
 // rank = elements that sort strictly before + equal elements that come earlier.  (Sixteen unrolled shuffles instead of
-// the loop over the range's length: measured slower, 0.398 vs 0.366 ms per 1024 frames — the leaves are short.)
+// the loop over the range's length: measured slower, 0.398 vs 0.366 ms per 1024 frames — the leaves are short; eight
+// shuffles per half-warp + one to combine: 0.348 vs 0.334.  The kernel is sensitive to the number of shuffle / shared-
+// memory instructions, not only to their latency.)
 __device__ __forceinline__ void sel_warp_leaf(yavo_ent *A, int f, int l) {
     const int lane = threadIdx.x & 31, n = l - f;
     const yavo_ent e = (lane < n) ? A[f + lane] : 0ull;
