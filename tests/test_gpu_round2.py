@@ -303,15 +303,18 @@ print("UMMA_BLUR_MISMATCHES", bad)
 """
 
 
-def test_blur_on_the_tensor_cores_variant_is_bit_exact(cuda_lib):
-    """build/libyavo_umma.so (-DYAVO_BLUR_UMMA=1, built by __graft_entry__.build()): the 9x9 Gaussian as two banded
-    tcgen05.mma kind::i8 products (blur_umma.cuh).  Not the default (measured slower), but kept exact: blurred planes,
-    descriptors and score bits against the oracle on interior, edge, tiny and saturated frames."""
+@pytest.mark.parametrize("variant", ["umma", "hyb"])
+def test_blur_on_the_tensor_cores_variant_is_bit_exact(cuda_lib, variant):
+    """build/libyavo_umma.so (-DYAVO_BLUR_UMMA=1: the 9x9 Gaussian as two banded tcgen05.mma kind::i8 products) and
+    build/libyavo_hyb.so (-DYAVO_BLUR_UMMA=2: horizontal pass on the tensor cores, the operand arriving by a 4-D tensor
+    copy, vertical pass from the accumulator registers), both built by __graft_entry__.build() from blur_umma.cuh.  Not
+    the default (measured slower), but kept exact: blurred planes, descriptors and score bits against the oracle on
+    interior, edge, tiny and saturated frames."""
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    lib = os.path.join(root, "build", "libyavo_umma.so")
+    lib = os.path.join(root, "build", "libyavo_%s.so" % variant)
     if not os.path.exists(lib):
         pytest.skip("variant library not built")
     env = dict(os.environ, YAVO_LIB_PATH=lib)

@@ -24,6 +24,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fast_core.h"  // yavo_blur_v2_raw (hybrid variant)
+
 namespace yavo {
 namespace bu {
 
@@ -283,6 +285,42 @@ __device__ __forceinline__ void bu_finish(uint32_t tmem_base, const uint8_t *ob,
     const int r = tid >> 3, c = (tid & 7) * 16, gr = y0 + r, gc = x0 + c;
     if (gr < H && gc < pitch)
         *reinterpret_cast<uint4 *>(blur_frame + (uint32_t)(gr * pitch + gc)) = *reinterpret_cast<const uint4 *>(ob + r * 128 + c);
+}
+
+// ---- hybrid: pass 1 on the tensor cores, pass 2 from the accumulator registers on the integer pipe -----------------
+// After pass 1 (bu_pass1_issue + the mbarrier) a thread holds the row sums of ONE output column: warp w takes lane
+// quarter w % 4 and output rows 16 (w / 4) .. + 15, i.e. the 24 sums D1[x, 16 h .. 16 h + 23].  Vertical pairs of them
+// are the operands of the IDP.2A vertical pass (yavo_blur_v2_raw, the same arithmetic as the integer-pipe kernel);
+// the bytes go to `ob` (32 rows of 128 bytes) for bu_copy_out.  One MMA round trip per tile, no byte split, no
+// operands written back to TMEM.
+// `part` 0 / 1 = the first / last eight of the warp's sixteen output rows (the accumulator stays in TMEM, so the second
+// part can run later — the detect kernel puts it behind the pool reservation's atomic, whose latency it hides).
+__device__ __forceinline__ void bu_vpass_from_tmem(uint64_t *bars, uint32_t tmem_base, uint8_t *ob, int part) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, h = warp >> 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + 16 * h + 8 * part;
+    if (part == 0) {
+        // every thread waits on the mbarrier itself (no CTA barrier: the segment test's first pass has run in between,
+        // the first try_wait succeeds) — warps go on as they arrive
+        bu_bar_wait(bu_saddr(&bars[1]), 0);
+        bu_fence_after();
+    }
+    uint32_t P[8];
+#pragma unroll
+    for (int g8 = 0; g8 < 2; g8++) {
+        uint32_t v[8];
+        bu_ld8(lane_base + 8 * g8, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++) P[4 * g8 + i] = __byte_perm(v[2 * i], v[2 * i + 1], 0x5410);  // sums < 2^16: low halves
+    }
+    uint8_t *o = ob + (16 * h + 8 * part) * 128 + 32 * q + lane;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        uint32_t a, b;
+        yavo_blur_v2_raw(&P[j], &a, &b);
+        o[(2 * j) * 128] = (uint8_t)(a >> 16);
+        o[(2 * j + 1) * 128] = (uint8_t)(b >> 16);
+    }
 }
 
 #endif  // __CUDACC__

@@ -43,6 +43,7 @@ struct yavo_ctx {
     // device buffers (per slot)
     uint8_t *d_frames = nullptr, *d_blur = nullptr;
     CUtensorMap frames_map;  // d_frames as a 3-D tensor (byte in row, row, slot): K1 stages a tile with one tensor copy
+    CUtensorMap frames_cmap; // d_frames as a 4-D tensor (byte in 16-byte chunk, row, chunk, slot): the same tile in core-matrix order (blur_umma.cuh)
     bool batch_select_only = false;    // YAVO_SELECT_SINGLE=0: the batch instance of the select kernel on single frames too (A/B runs)
     uint8_t *d_blur_consts = nullptr;  // the blur's constant band matrices in their shared-memory layout (blur_umma.cuh)
     CUtensorMap blur_map;    // d_blur likewise, box = the 32 x 17 byte patch the BRIEF kernel stages per keypoint
@@ -231,6 +232,27 @@ int encode_slot_map(yavo_ctx *ctx, CUtensorMap *map, void *base, int box_w, int 
     return 0;
 }
 
+// The frame slots once more as a 4-D tensor (byte in a 16-byte chunk, row, chunk of the row, slot): a box {16, SH, SROW / 16, 1}
+// lands in shared memory as [chunk][row][16 bytes], the K-major core-matrix order of the tensor cores' pixel operand.
+int encode_chunk_map(yavo_ctx *ctx, CUtensorMap *map, void *base) {
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, YAVO_ERR_CUDA, "the driver does not export cuTensorMapEncodeTiled");
+    const cuuint64_t gdim[4] = {16, (cuuint64_t)ctx->rows_alloc, (cuuint64_t)(ctx->pitch / 16), (cuuint64_t)ctx->n_slots};
+    const cuuint64_t gstride[3] = {(cuuint64_t)ctx->pitch, 16, (cuuint64_t)ctx->frame_stride};  // bytes, dims 1..3
+    const cuuint32_t box[4] = {16u, (cuuint32_t)SH, (cuuint32_t)(SROW / 16), 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    const CUresult r = reinterpret_cast<encode_fn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, base, gdim, gstride, box, estr,
+                                                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, YAVO_ERR_CUDA, "cuTensorMapEncodeTiled (chunk map) failed (%d)", (int)r);
+    return 0;
+}
+
 template <int NT>
 size_t select_smem_bytes() { return ((sizeof(SelSharedT<NT>) + 15) & ~size_t(15)) + sizeof(yavo_ent) * SEL_SMEM_ENTS; }
 
@@ -339,13 +361,13 @@ int launch_detect(yavo_ctx *ctx, int slot0, int n, bool do_fast, bool do_blur) {
     if (do_fast) CK(cudaMemsetAsync(ncand, 0, sizeof(int) * (size_t)n, ctx->ls));
     if (do_fast && do_blur)
         PROF(KC_DETECT, detect_blur_kernel<true, true><<<grid, K1_THREADS, 0, ctx->ls>>>(
-            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
+            ctx->frames_map, ctx->frames_cmap, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
     else if (do_fast)
         PROF(KC_DETECT, detect_blur_kernel<true, false><<<grid, K1_THREADS, 0, ctx->ls>>>(
-            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
+            ctx->frames_map, ctx->frames_cmap, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
     else
         PROF(KC_DETECT, detect_blur_kernel<false, true><<<grid, K1_THREADS, 0, ctx->ls>>>(
-            ctx->frames_map, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
+            ctx->frames_map, ctx->frames_cmap, slot0, frames, fs, ctx->pitch, H, W, blur, pool, ctx->max_cand, ncand, seg, ctx->seg_cols, ctx->rows_alloc, ctx->d_blur_consts));
     CK_LAUNCH();
     if (do_blur)
         for (int s = slot0; s < slot0 + n; s++) ctx->slot_blur_valid[s] = 1;
@@ -666,7 +688,8 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     // eight CTAs of the detect kernel per SM need the largest shared-memory carve-out
     CKC(cudaFuncSetAttribute(detect_blur_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(detect_blur_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    if (encode_slot_map(c, &c->frames_map, c->d_frames, SROW, SH) != 0 || encode_slot_map(c, &c->blur_map, c->d_blur, BP_ROWB, BP_ROWS) != 0) {
+    if (encode_slot_map(c, &c->frames_map, c->d_frames, SROW, SH) != 0 || encode_slot_map(c, &c->blur_map, c->d_blur, BP_ROWB, BP_ROWS) != 0 ||
+        encode_chunk_map(c, &c->frames_cmap, c->d_frames) != 0) {
         g_create_error = c->err;
         yavo_destroy(c);
         return YAVO_ERR_CUDA;

@@ -63,7 +63,8 @@ constexpr int K1_THREADS = 256;
 #define YAVO_K1_MIN_CTAS 8  // 32 registers per thread: eight CTAs per SM keep the issue slots of this issue-bound kernel full
 #endif
 #ifndef YAVO_BLUR_UMMA
-#define YAVO_BLUR_UMMA 0  // 1: the blur on the tensor cores (blur_umma.cuh: bit-exact, measured slower); 0: IDP.4A / IDP.2A on the integer pipes
+#define YAVO_BLUR_UMMA 0  // 0: IDP.4A / IDP.2A on the integer pipes; 1: both passes on the tensor cores (blur_umma.cuh: bit-exact, measured slower, see
+                          // DESIGN.md); 2: hybrid — horizontal pass on the tensor cores, vertical pass from the accumulator registers
 #endif
 constexpr int K1_LIST = 1024;            // corners of a tile listed (and scored densely) per round; a tile with more takes more rounds
 constexpr int SEG_CNT_BITS = 8;          // segment table entry = pool offset << 8 | count (count <= 128 per tile row)
@@ -92,6 +93,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
                  "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar))
                  : "memory");
 }
+// the same for a 4-D tensor map (16-byte chunk of a row, row, chunk index, frame slot): the box {16, rows, chunks, 1}
+// lands in shared memory as [chunk][row][16 bytes], the K-major core-matrix order tcgen05.mma reads (blur_umma.cuh)
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                     smem_addr(dst)),
+                 "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_addr(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -114,7 +123,7 @@ __device__ __forceinline__ int reflect101(int p, int n) {
 
 template <bool DO_FAST, bool DO_BLUR>
 __global__ void __launch_bounds__(K1_THREADS, YAVO_K1_MIN_CTAS)
-detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base,
+detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_constant__ CUtensorMap frames_cmap, int slot_base,
                    const uint8_t *__restrict__ frames, size_t frame_stride, int pitch, int H, int W,
                    uint8_t *__restrict__ blur, yavo_ent *__restrict__ pool, int max_cand, int *__restrict__ ncand,
                    uint32_t *__restrict__ seg, int seg_cols, int rows_alloc, const uint8_t *__restrict__ blur_consts) {
@@ -153,7 +162,15 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         if (tid == 0) mbar_init(&tile_bar, 1);
         if (y0 - HALO >= 0 && y0 + TH + HALO <= H) {  // CTA-uniform
             if (tid == 0) {
+#if YAVO_BLUR_UMMA == 2
+                // + the same pixels once more, in core-matrix order, as the tensor cores' operand (unless reflected
+                // columns have to be patched in first: then the CTA re-lays the patched tile out itself)
+                const bool direct = UMMA && !(x0 == 0 || x0 + TW + HALO > W);
+                mbar_expect_tx(&tile_bar, direct ? 2 * SROW * SH : SROW * SH);
+                if (direct) tma_load_4d(ub, &frames_cmap, 0, y0 - HALO, (x0 - SLEAD) / 16, slot_base + f, &tile_bar);
+#else
                 mbar_expect_tx(&tile_bar, SROW * SH);
+#endif
                 tma_load_3d(&tile[0][0], &frames_map, x0 - SLEAD, y0 - HALO, slot_base + f, &tile_bar);
             }
         } else {
@@ -193,8 +210,15 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
 #if YAVO_BLUR_UMMA
     uint32_t tmem_base = 0;
     if (UMMA) {
-        bu::bu_relayout(reinterpret_cast<const uint8_t *>(&tile[0][0]), ub);
-        __syncthreads();
+#if YAVO_BLUR_UMMA == 2
+        const bool direct = (y0 - HALO >= 0 && y0 + TH + HALO <= H) && !edge_cols;  // CTA-uniform: the operand arrived by tensor copy
+#else
+        const bool direct = false;
+#endif
+        if (!direct) {
+            bu::bu_relayout(reinterpret_cast<const uint8_t *>(&tile[0][0]), ub);
+            __syncthreads();
+        }
         tmem_base = tmem_base_s;
         bu::bu_pass1_issue(ub, bcst, bu_bars, tmem_base);  // the horizontal pass runs under the segment test
     }
@@ -238,14 +262,16 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         // that every tcgen05.mma round trip has a few hundred instructions per warp to hide under.
         pass_a(0);
         pass_a(1);
-#if YAVO_BLUR_UMMA
+#if YAVO_BLUR_UMMA == 1
         if (UMMA) bu::bu_pass1_drain(bcst, bu_bars, tmem_base);  // row sums -> byte operands, first half of the vertical pass issued
 #endif
         pass_a(2);
         pass_a(3);
         static_assert(RPW == 4, "pass A is written out for four rows per warp");
-#if YAVO_BLUR_UMMA
+#if YAVO_BLUR_UMMA == 1
         if (UMMA) bu::bu_pass2_drain(bcst, bu_bars, tmem_base, ub, 0);  // first half drained, second half issued
+#elif YAVO_BLUR_UMMA == 2
+        if (UMMA) bu::bu_vpass_from_tmem(bu_bars, tmem_base, ub, 0);  // the horizontal pass ran under pass A; vertical pass from its accumulator
 #endif
         __syncwarp();
         for (int i = lane; i < cnt; i += 32) {
@@ -312,6 +338,7 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
 
 #if YAVO_BLUR_UMMA
     if (UMMA) {
+#if YAVO_BLUR_UMMA == 1
         if (!DO_FAST) {
             bu::bu_pass1_drain(bcst, bu_bars, tmem_base);
             bu::bu_pass2_drain(bcst, bu_bars, tmem_base, ub, 0);
@@ -319,11 +346,19 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         // second half of the vertical pass drained (its CTA barrier also publishes the masks and counts of the segment
         // test), TMEM freed, the blurred tile written
         bu::bu_pass2_drain(bcst, bu_bars, tmem_base, ub, 1);
+        // (the CTA barrier inside also publishes the masks and counts of the segment test)
         bu::bu_finish(tmem_base, ub, blur + (size_t)f * frame_stride, pitch, H, x0, y0);
+#else
+        if (!DO_FAST) {
+            bu::bu_vpass_from_tmem(bu_bars, tmem_base, ub, 0);
+            bu::bu_vpass_from_tmem(bu_bars, tmem_base, ub, 1);
+            bu::bu_finish(tmem_base, ub, blur + (size_t)f * frame_stride, pitch, H, x0, y0);
+        }
+#endif
     }
 #endif
     if (DO_FAST) {
-        if (!UMMA) __syncthreads();  // masks, counts (and the horizontal blur pass) are complete
+        if (YAVO_BLUR_UMMA != 1 || !UMMA) __syncthreads();  // masks, counts (and the horizontal blur pass) are complete
         if (tid < 128) {
             int total, row_start, row_cnt;
             build_list(0, &total, &row_start, &row_cnt);
@@ -344,6 +379,15 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         }
     }
 
+#if YAVO_BLUR_UMMA == 2
+    if (UMMA && DO_FAST) {
+        // second half of the vertical pass behind the pool reservation (its atomic's round trip is hidden here, as it is
+        // behind the vertical pass of the integer-pipe kernel); then TMEM freed and the tile written.  The CTA barrier
+        // inside also publishes s_base / s_total for the scoring below.
+        bu::bu_vpass_from_tmem(bu_bars, tmem_base, ub, 1);
+        bu::bu_finish(tmem_base, ub, blur + (size_t)f * frame_stride, pitch, H, x0, y0);
+    }
+#endif
 #if !YAVO_BLUR_UMMA
     if (DO_BLUR) {
         if (!DO_FAST) __syncthreads();
@@ -390,7 +434,7 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, int slot_base
         // Harris response of every corner from the staged pixels (the kernel's unbalanced tail: a tile's ~45 corners
         // occupy two warps) (reference src/FastDetector.cc:244-273; the 5x5 window
         // of an interior pixel lies inside the tile + halo), densely: thread i takes corner i of the list
-        __syncthreads();
+        if (!(YAVO_BLUR_UMMA == 2 && UMMA)) __syncthreads();
         const int total = s_total, base = s_base;
         const bool fits = base + total <= max_cand;  // otherwise the select kernel reports the overflow (ncand > max_cand)
         const uint8_t *tb = reinterpret_cast<const uint8_t *>(&tile[0][0]);
