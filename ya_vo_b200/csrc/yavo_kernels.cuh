@@ -62,6 +62,9 @@ constexpr int K1_THREADS = 256;
 #ifndef YAVO_K1_MIN_CTAS
 #define YAVO_K1_MIN_CTAS 8  // 32 registers per thread: eight CTAs per SM keep the issue slots of this issue-bound kernel full
 #endif
+#ifndef YAVO_K1_PREFETCH
+#define YAVO_K1_PREFETCH 0  // tiles ahead (in launch order) whose pixels a CTA prefetches into L2; 0 = off
+#endif
 #ifndef YAVO_BLUR_UMMA
 #define YAVO_BLUR_UMMA 0  // 0: IDP.4A / IDP.2A on the integer pipes; 1: both passes on the tensor cores (blur_umma.cuh: bit-exact, measured slower, see
                           // DESIGN.md); 2: hybrid — horizontal pass on the tensor cores, vertical pass from the accumulator registers
@@ -91,6 +94,12 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *tmap, 
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                      smem_addr(dst)),
                  "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar))
+                 : "memory");
+}
+// L2 prefetch of a box of the 3-D tensor (no shared-memory destination, no completion to wait for)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *tmap, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y),
+                 "r"(z)
                  : "memory");
 }
 // the same for a 4-D tensor map (16-byte chunk of a row, row, chunk index, frame slot): the box {16, rows, chunks, 1}
@@ -185,6 +194,16 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
                          &tile_bar);
             }
         }
+#if YAVO_K1_PREFETCH > 0
+        // the frames come from HBM (a batch is far larger than L2): pull the tile of a CTA that will start a few waves
+        // from now into L2, so that its staging wait is an L2 round trip
+        if (tid == 0) {
+            const int gx = (int)gridDim.x, gy = (int)gridDim.y;
+            const int lin = (int)blockIdx.x + gx * ((int)blockIdx.y + gy * (int)blockIdx.z) + YAVO_K1_PREFETCH;
+            const int t = lin / gx, fx = lin - t * gx, fz = t / gy, fy = t - fz * gy;
+            if (fz < (int)gridDim.z) tma_prefetch_3d(&frames_map, fx * TW - SLEAD, fy * TH - HALO, slot_base + fz);
+        }
+#endif
         if (tid == 0) mbar_wait(&tile_bar, 0);
     }
     const bool edge_cols = DO_BLUR && (x0 == 0 || x0 + TW + HALO > W);
