@@ -300,9 +300,11 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
             uint32_t nib = yavo_fast4(&tile[sr - 3][q + SPX], &tile[sr - 2][q + SPX], &tile[sr - 1][q + SPX],
                                       &tile[sr][q + SPX], &tile[sr + 1][q + SPX], &tile[sr + 2][q + SPX],
                                       &tile[sr + 3][q + SPX], &pre);
+            if (x0 < 4 || x0 + TW > W - 4) {  // CTA-uniform: only the first / last tile column holds excluded columns
 #pragma unroll
-            for (int bb = 0; bb < 4; bb++)  // interior columns only: 4 <= col < W-4
-                if (x0 + 4 * q + bb < 4 || x0 + 4 * q + bb >= W - 4) nib &= ~(1u << bb);
+                for (int bb = 0; bb < 4; bb++)  // interior columns only: 4 <= col < W-4
+                    if (x0 + 4 * q + bb < 4 || x0 + 4 * q + bb >= W - 4) nib &= ~(1u << bb);
+            }
             fnib[warp][k][q] = (uint8_t)nib;
         }
         __syncwarp();
