@@ -263,16 +263,19 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
         // per-warp list; pass B runs the full 16-position test only on the survivors, densely packed 32 to a
         // warp step (on real frames a few percent of the quads); pass C assembles the 32-pixel mask words.
         constexpr int NW = K1_THREADS / 32, RPW = TH / NW;
-        __shared__ __align__(8) uint8_t fnib[NW][RPW][32];
+        __shared__ __align__(16) uint8_t fnib[NW][RPW][32];
         __shared__ uint8_t flist[NW][RPW * 32];
         const unsigned lt = (1u << lane) - 1u;
         int cnt = 0;
+        // the warp's four rows of nibbles start at zero (one 16-byte store by each of eight lanes; pass B, behind a
+        // __syncwarp, fills in the survivors)
+        if (lane < RPW * 32 / 16) reinterpret_cast<uint4 *>(&fnib[warp][0][0])[lane] = make_uint4(0u, 0u, 0u, 0u);
         auto pass_a = [&](int k) {
             const int tr = warp + NW * k, gr = y0 + tr, sr = tr + HALO;
-            bool live = false;
-            if (gr >= 4 && gr < H - 4)  // warp-uniform
-                live = yavo_fast4_core(&tile[sr][lane + SPX], &tile[sr + 1][lane + SPX], &tile[sr + 3][lane + SPX]) != 0;
-            fnib[warp][k][lane] = 0;
+            uint32_t core = 0;  // the word itself, tested after the (warp-uniform) branch: no boolean to materialise
+            if (gr >= 4 && gr < H - 4)
+                core = yavo_fast4_core(&tile[sr][lane + SPX], &tile[sr + 1][lane + SPX], &tile[sr + 3][lane + SPX]);
+            const bool live = core != 0;
             const unsigned bl = __ballot_sync(0xffffffffu, live);
             if (live) flist[warp][cnt + __popc(bl & lt)] = (uint8_t)(k * 32 + lane);
             cnt += __popc(bl);
