@@ -251,8 +251,9 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
             uint32_t ha[4], hb[4];
             yavo_blur_h4(ra[-1], ra[0], ra[1], ha);
             yavo_blur_h4(rb[-1], rb[0], rb[1], hb);
-            hpair[rp][q] = make_uint4(ha[0] | (hb[0] << 16), ha[1] | (hb[1] << 16),
-                                      ha[2] | (hb[2] << 16), ha[3] | (hb[3] << 16));
+            // sums < 2^16: the low halves of the two rows' sums side by side, one PRMT per pair
+            hpair[rp][q] = make_uint4(__byte_perm(ha[0], hb[0], 0x5410), __byte_perm(ha[1], hb[1], 0x5410),
+                                      __byte_perm(ha[2], hb[2], 0x5410), __byte_perm(ha[3], hb[3], 0x5410));
         }
     }
 #endif
