@@ -254,7 +254,21 @@ YAVO_HD void yavo_structure_tensor(F px, int row, int col, int *oa, int *ob, int
 
 // horizontal pass for 4 adjacent outputs x..x+3 from the three words covering x-4..x+7:
 // out[i] = sum_k g[k] * p[x+i+k-4]; three dp4a per output with pre-shifted weight vectors
+#ifdef __CUDACC__
+// the twelve weight words of the horizontal pass in constant memory: IDP.4A takes them as constant-bank operands, so no
+// instruction is spent on materialising them (as immediates they cost a UMOV each, re-issued in every loop iteration)
+__constant__ uint32_t yavo_hw[12] = {
+    YAVO_PK(YAVO_G0, YAVO_G1, YAVO_G2, YAVO_G3), YAVO_PK(YAVO_G4, YAVO_G3, YAVO_G2, YAVO_G1), YAVO_PK(YAVO_G0, 0u, 0u, 0u),
+    YAVO_PK(0u, YAVO_G0, YAVO_G1, YAVO_G2),      YAVO_PK(YAVO_G3, YAVO_G4, YAVO_G3, YAVO_G2), YAVO_PK(YAVO_G1, YAVO_G0, 0u, 0u),
+    YAVO_PK(0u, 0u, YAVO_G0, YAVO_G1),           YAVO_PK(YAVO_G2, YAVO_G3, YAVO_G4, YAVO_G3), YAVO_PK(YAVO_G2, YAVO_G1, YAVO_G0, 0u),
+    YAVO_PK(0u, 0u, 0u, YAVO_G0),                YAVO_PK(YAVO_G1, YAVO_G2, YAVO_G3, YAVO_G4), YAVO_PK(YAVO_G3, YAVO_G2, YAVO_G1, YAVO_G0)};
+#endif
 YAVO_HD void yavo_blur_h4(uint32_t wm, uint32_t w0, uint32_t wp, uint32_t out[4]) {
+#ifdef __CUDA_ARCH__
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        out[i] = yavo_dp4a(wm, yavo_hw[3 * i], yavo_dp4a(w0, yavo_hw[3 * i + 1], yavo_dp4a(wp, yavo_hw[3 * i + 2], 0u)));
+#else
     out[0] = yavo_dp4a(wm, YAVO_PK(YAVO_G0, YAVO_G1, YAVO_G2, YAVO_G3),
              yavo_dp4a(w0, YAVO_PK(YAVO_G4, YAVO_G3, YAVO_G2, YAVO_G1),
              yavo_dp4a(wp, YAVO_PK(YAVO_G0, 0u, 0u, 0u), 0u)));
@@ -267,6 +281,7 @@ YAVO_HD void yavo_blur_h4(uint32_t wm, uint32_t w0, uint32_t wp, uint32_t out[4]
     out[3] = yavo_dp4a(wm, YAVO_PK(0u, 0u, 0u, YAVO_G0),
              yavo_dp4a(w0, YAVO_PK(YAVO_G1, YAVO_G2, YAVO_G3, YAVO_G4),
              yavo_dp4a(wp, YAVO_PK(YAVO_G3, YAVO_G2, YAVO_G1, YAVO_G0), 0u)));
+#endif
 }
 
 // vertical pass for two vertically adjacent outputs (rows r, r+1; r even in tile coordinates)
