@@ -290,12 +290,21 @@ YAVO_HD void yavo_blur_h4(uint32_t wm, uint32_t w0, uint32_t wp, uint32_t out[4]
 //   out(r+1) = g0 h[r-3] + ... + g8 h[r+5]
 // raw form: the two fixed-point sums with the rounding constant already added; the blurred pixels are
 // bits 16..23 of each (sum < 2^24), which the kernel extracts with byte permutes while packing four outputs
+#ifdef __CUDACC__
+__constant__ uint32_t yavo_vw[5] = {YAVO_PK(YAVO_G0, YAVO_G1, YAVO_G2, YAVO_G3), YAVO_PK(YAVO_G4, YAVO_G3, YAVO_G2, YAVO_G1),
+                                    YAVO_PK(YAVO_G0, 0u, 0u, YAVO_G0), YAVO_PK(YAVO_G1, YAVO_G2, YAVO_G3, YAVO_G4),
+                                    YAVO_PK(YAVO_G3, YAVO_G2, YAVO_G1, YAVO_G0)};  // constant-bank operands, as yavo_hw
+#endif
 YAVO_HD void yavo_blur_v2_raw(const uint32_t P[5], uint32_t *ra, uint32_t *rb) {
+#ifdef __CUDA_ARCH__
+    const uint32_t wA = yavo_vw[0], wB = yavo_vw[1], wC = yavo_vw[2], wD = yavo_vw[3], wE = yavo_vw[4];
+#else
     const uint32_t wA = YAVO_PK(YAVO_G0, YAVO_G1, YAVO_G2, YAVO_G3);  // lo: g0,g1  hi: g2,g3
     const uint32_t wB = YAVO_PK(YAVO_G4, YAVO_G3, YAVO_G2, YAVO_G1);  // lo: g4,g5  hi: g6,g7
     const uint32_t wC = YAVO_PK(YAVO_G0, 0u, 0u, YAVO_G0);            // lo: g8,0   hi: 0,g0
     const uint32_t wD = YAVO_PK(YAVO_G1, YAVO_G2, YAVO_G3, YAVO_G4);  // lo: g1,g2  hi: g3,g4
     const uint32_t wE = YAVO_PK(YAVO_G3, YAVO_G2, YAVO_G1, YAVO_G0);  // lo: g5,g6  hi: g7,g8
+#endif
     uint32_t a = yavo_dp2a_lo(P[0], wA, 32768u);
     a = yavo_dp2a_hi(P[1], wA, a);
     a = yavo_dp2a_lo(P[2], wB, a);
