@@ -133,6 +133,40 @@ YAVO_HD uint32_t yavo_fast4(const WP rm3, const WP rm2, const WP rm1, const WP r
     return (((r >> 7) & 0x01010101u) * 0x01020408u) >> 24;
 }
 
+// The same test for a quad whose necessary condition `core` = d0 & d7 & d4 & d8 (yavo_fast4_core, non-zero) is already
+// known: the remaining twelve ring positions only.
+template <typename WP>
+YAVO_HD uint32_t yavo_fast4_rest(const WP rm3, const WP rm2, const WP rm1, const WP r0, const WP rp1, const WP rp2, const WP rp3,
+                                 uint32_t core) {
+    const uint32_t c4 = r0[0];
+    const uint32_t b0 = rp1[-1], b1 = rp1[0];
+    const uint32_t d1 = yavo_differs4(c4, yavo_shift_bytes<-3>(b0, b1, 0u));
+    const uint32_t e0 = rp2[-1], e1 = rp2[0], e2 = rp2[1];
+    const uint32_t d2 = yavo_differs4(c4, yavo_shift_bytes<-2>(e0, e1, e2));
+    const uint32_t d6 = yavo_differs4(c4, yavo_shift_bytes<2>(e0, e1, e2));
+    const uint32_t f0 = rp3[-1], f1 = rp3[0], f2 = rp3[1];
+    const uint32_t d3 = yavo_differs4(c4, yavo_shift_bytes<-1>(f0, f1, f2));
+    const uint32_t d5 = yavo_differs4(c4, yavo_shift_bytes<1>(f0, f1, f2));
+    const uint32_t g0 = rm1[-1], g1 = rm1[0], g2 = rm1[1];
+    const uint32_t d9 = yavo_differs4(c4, yavo_shift_bytes<3>(g0, g1, g2));
+    const uint32_t d15 = yavo_differs4(c4, yavo_shift_bytes<-3>(g0, g1, g2));
+    const uint32_t h0 = rm2[-1], h1 = rm2[0], h2 = rm2[1];
+    const uint32_t d10 = yavo_differs4(c4, yavo_shift_bytes<2>(h0, h1, h2));
+    const uint32_t d14 = yavo_differs4(c4, yavo_shift_bytes<-2>(h0, h1, h2));
+    const uint32_t i0 = rm3[-1], i1 = rm3[0], i2 = rm3[1];
+    const uint32_t d11 = yavo_differs4(c4, yavo_shift_bytes<1>(i0, i1, i2));
+    const uint32_t d12 = yavo_differs4(c4, i1);
+    const uint32_t d13 = yavo_differs4(c4, yavo_shift_bytes<-1>(i0, i1, i2));
+    core &= d5 & d6 & d9 & d10 & d11;           // d0 & d4..d11
+    const uint32_t lo = d1 & d2 & d3;           // window 0 (d0 already in core)
+    const uint32_t w1 = lo & d12;               // 1..12
+    const uint32_t w2 = d2 & d3 & d12 & d13;    // 2..13
+    const uint32_t w3 = d3 & d12 & d13 & d14;   // 3..14
+    const uint32_t w4 = d12 & d13 & d14 & d15;  // 4..15
+    const uint32_t r = core & (lo | w1 | w2 | w3 | w4);
+    return (((r >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+}
+
 // The four ring positions every 12-window needs besides D0 (0, 4, 7, 8): a cheap necessary condition.  The
 // detect kernel runs it for every quad and the full test only for the quads that survive it.
 template <typename WP>

@@ -266,6 +266,7 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
         constexpr int NW = K1_THREADS / 32, RPW = TH / NW;
         __shared__ __align__(16) uint8_t fnib[NW][RPW][32];
         __shared__ uint8_t flist[NW][RPW * 32];
+        __shared__ uint32_t fcore[NW][RPW * 32];  // the survivors' necessary-condition words (pass B starts from them)
         const unsigned lt = (1u << lane) - 1u;
         int cnt = 0;
         // the warp's four rows of nibbles start at zero (one 16-byte store by each of eight lanes; pass B, behind a
@@ -278,7 +279,11 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
                 core = yavo_fast4_core(&tile[sr][lane + SPX], &tile[sr + 1][lane + SPX], &tile[sr + 3][lane + SPX]);
             const bool live = core != 0;
             const unsigned bl = __ballot_sync(0xffffffffu, live);
-            if (live) flist[warp][cnt + __popc(bl & lt)] = (uint8_t)(k * 32 + lane);
+            if (live) {
+                const int slot = cnt + __popc(bl & lt);
+                flist[warp][slot] = (uint8_t)(k * 32 + lane);
+                fcore[warp][slot] = core;
+            }
             cnt += __popc(bl);
         };
         // With the blur on the tensor cores its steps are interleaved with the balanced parts of the segment test, so
@@ -300,10 +305,9 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
         for (int i = lane; i < cnt; i += 32) {
             const int e = flist[warp][i], k = e >> 5, q = e & 31;
             const int sr = warp + NW * k + HALO;
-            bool pre;
-            uint32_t nib = yavo_fast4(&tile[sr - 3][q + SPX], &tile[sr - 2][q + SPX], &tile[sr - 1][q + SPX],
-                                      &tile[sr][q + SPX], &tile[sr + 1][q + SPX], &tile[sr + 2][q + SPX],
-                                      &tile[sr + 3][q + SPX], &pre);
+            uint32_t nib = yavo_fast4_rest(&tile[sr - 3][q + SPX], &tile[sr - 2][q + SPX], &tile[sr - 1][q + SPX],
+                                           &tile[sr][q + SPX], &tile[sr + 1][q + SPX], &tile[sr + 2][q + SPX],
+                                           &tile[sr + 3][q + SPX], fcore[warp][i]);
             if (x0 < 4 || x0 + TW > W - 4) {  // CTA-uniform: only the first / last tile column holds excluded columns
 #pragma unroll
                 for (int bb = 0; bb < 4; bb++)  // interior columns only: 4 <= col < W-4
