@@ -722,27 +722,31 @@ __device__ int sel_block_partition(SelSharedT<NT> &S, yavo_ent *A, int f, int l,
     const yavo_ent piv = mpos == pa ? va : (mpos == pb ? vb : vc);
     const int cap = n / 2 + 1;
     int runL = 0, runR = 0;
+    // A warp classifies a contiguous chunk of 32 * SEL_ITEMS scan positions per pass, lane l taking positions l, l + 32, ...
+    // of it: consecutive lanes read consecutive entries (eight consecutive entries per THREAD, as before, are 64 bytes
+    // apart across the lanes of a load: a 16-way bank conflict on every shared-memory read).  Ranks inside the chunk come
+    // from ballots (one per side and item), the chunk totals from their population counts, the order across warps from
+    // the per-warp totals as before.
+    const unsigned lt = (1u << lane) - 1u;
     for (int base = 0; base < n - 1; base += SEL_THREADS * SEL_ITEMS) {
-        const int i0 = base + tid * SEL_ITEMS;
-        unsigned fL = 0, fR = 0;
+        const int w0 = base + warp * (32 * SEL_ITEMS) + lane;
+        unsigned bL[SEL_ITEMS], bR[SEL_ITEMS];
+        int packed = 0;
 #pragma unroll
         for (int e = 0; e < SEL_ITEMS; e++) {
-            const int i = i0 + e;
+            const int i = w0 + 32 * e;
+            bool sL = false, sR = false;
             if (i < n - 1) {
                 const int pl = f + 1 + i, pr = l - 1 - i;
                 const yavo_ent el = A[pl], er = A[pr];
-                fL |= (unsigned)(!yavo_before(pl == mpos ? v0 : el, piv)) << e;
-                fR |= (unsigned)(!yavo_before(piv, pr == mpos ? v0 : er)) << e;
+                sL = !yavo_before(pl == mpos ? v0 : el, piv);
+                sR = !yavo_before(piv, pr == mpos ? v0 : er);
             }
+            bL[e] = __ballot_sync(0xffffffffu, sL);
+            bR[e] = __ballot_sync(0xffffffffu, sR);
+            packed += __popc(bL[e]) | (__popc(bR[e]) << 16);
         }
-        const int packed = __popc(fL) | (__popc(fR) << 16);
-        int incl = packed;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        if (lane == 31) S.wtot[warp] = incl;
+        if (lane == 0) S.wtot[warp] = packed;  // the warp's totals (every lane holds them)
         __syncthreads();
         if (base == 0 && tid == 0) {  // the move of the median to the front
             A[f] = piv;
@@ -755,18 +759,20 @@ __device__ int sel_block_partition(SelSharedT<NT> &S, yavo_ent *A, int f, int l,
             if (w < warp) pre += t;
             tot += t;
         }
-        const int excl = pre + incl - packed;
-        int rL = runL + (excl & 0xffff), rR = runR + (excl >> 16);
+        int rL = runL + (pre & 0xffff), rR = runR + (pre >> 16);  // ranks of the warp's first left / right stopper
 #pragma unroll
         for (int e = 0; e < SEL_ITEMS; e++) {
-            if ((fL >> e) & 1u) {
-                if (rL < cap) Lpos[rL] = (PosT)(1 + i0 + e);  // positions relative to f
-                rL++;
+            const int i = w0 + 32 * e;
+            if ((bL[e] >> lane) & 1u) {
+                const int r = rL + __popc(bL[e] & lt);
+                if (r < cap) Lpos[r] = (PosT)(1 + i);  // positions relative to f
             }
-            if ((fR >> e) & 1u) {
-                if (rR < cap) Rpos[rR] = (PosT)(n - 1 - (i0 + e));
-                rR++;
+            if ((bR[e] >> lane) & 1u) {
+                const int r = rR + __popc(bR[e] & lt);
+                if (r < cap) Rpos[r] = (PosT)(n - 1 - i);
             }
+            rL += __popc(bL[e]);
+            rR += __popc(bR[e]);
         }
         runL += tot & 0xffff;
         runR += tot >> 16;
