@@ -1205,30 +1205,50 @@ select_big_kernel(const uint32_t *__restrict__ seg, int seg_cols, int rows_alloc
             // pass 2: positions of the stoppers at [base + rank inside the slice]
             {
                 int runL = baseL, runR = baseR;
+                // warp-contiguous chunks, ranks from ballots (as sel_block_partition): every load of a warp is one
+                // contiguous 256-byte piece of the list
+                const int lane = tid & 31, warp = tid >> 5;
+                const unsigned lt = (1u << lane) - 1u;
                 for (int base = i_lo; base < i_hi; base += BIG_THREADS * BIG_ITEMS) {
-                    const int i0 = base + tid * BIG_ITEMS;
-                    unsigned fL = 0, fR = 0;
+                    const int w0 = base + warp * (32 * BIG_ITEMS) + lane;
+                    unsigned bL[BIG_ITEMS], bR[BIG_ITEMS];
+                    int packed = 0;
 #pragma unroll
                     for (int e = 0; e < BIG_ITEMS; e++) {
-                        const int i = i0 + e;
+                        const int i = w0 + 32 * e;
+                        bool sL = false, sR = false;
                         if (i < i_hi) {
-                            fL |= (unsigned)(!yavo_before(A[rf + 1 + i], piv)) << e;
-                            fR |= (unsigned)(!yavo_before(piv, A[rl - 1 - i])) << e;
+                            sL = !yavo_before(A[rf + 1 + i], piv);
+                            sR = !yavo_before(piv, A[rl - 1 - i]);
                         }
+                        bL[e] = __ballot_sync(0xffffffffu, sL);
+                        bR[e] = __ballot_sync(0xffffffffu, sR);
+                        packed += __popc(bL[e]) | (__popc(bR[e]) << 16);
                     }
-                    int excl, tot;
-                    big_block_scan(S, __popc(fL) | (__popc(fR) << 16), &excl, &tot);
-                    int rL = runL + (excl & 0xffff), rR = runR + (excl >> 16);
+                    __syncthreads();  // the previous use of wtot is over
+                    if (lane == 0) S.wtot[warp] = packed;
+                    __syncthreads();
+                    int pre = 0, tot = 0;
+#pragma unroll
+                    for (int w = 0; w < BIG_THREADS / 32; w++) {
+                        const int t = S.wtot[w];
+                        if (w < warp) pre += t;
+                        tot += t;
+                    }
+                    int rL = runL + (pre & 0xffff), rR = runR + (pre >> 16);
 #pragma unroll
                     for (int e = 0; e < BIG_ITEMS; e++) {
-                        if ((fL >> e) & 1u) {
-                            if (rL < cap) Lpos[rL] = (uint32_t)(1 + i0 + e);  // positions relative to rf
-                            rL++;
+                        const int i = w0 + 32 * e;
+                        if ((bL[e] >> lane) & 1u) {
+                            const int r = rL + __popc(bL[e] & lt);
+                            if (r < cap) Lpos[r] = (uint32_t)(1 + i);  // positions relative to rf
                         }
-                        if ((fR >> e) & 1u) {
-                            if (rR < cap) Rpos[rR] = (uint32_t)(n - 1 - (i0 + e));
-                            rR++;
+                        if ((bR[e] >> lane) & 1u) {
+                            const int r = rR + __popc(bR[e] & lt);
+                            if (r < cap) Rpos[r] = (uint32_t)(n - 1 - i);
                         }
+                        rL += __popc(bL[e]);
+                        rR += __popc(bR[e]);
                     }
                     runL += tot & 0xffff;
                     runR += tot >> 16;
