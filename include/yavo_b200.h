@@ -197,7 +197,7 @@ int yavo_set_pipeline_chunk(yavo_ctx *ctx, int frames);
 int yavo_set_overlap(yavo_ctx *ctx, int chunk_frames, int n_streams);
 /* Large candidate lists (a 3840x2160 frame of noise has 300 k): frames with more than `min_candidates` FAST candidates
  * have the top of their std::sort replay — the partitions that scan hundreds of thousands of elements — spread over a
- * thread-block cluster of 8 CTAs before the select kernel (then a team of 8 CTAs per frame) takes over.  -1 (default) = automatic: 8192, for
+ * thread-block cluster of 8 CTAs before the select kernel (then a team of 8 CTAs per frame) takes over.  -1 (default) = automatic: 6144 (measured best on config 4 with the round-2 kernels: 3072 9.7 k, 4096 9.9 k, 6144 10.06 k, 8192 9.9 k, 12288 9.5 k frames/s), for
  * frames of 2 Mpx and more; 0 = never; results do not depend on the setting. */
 int yavo_set_big_select(yavo_ctx *ctx, int min_candidates);
 /* frames per set of kernel launches inside yavo_frontend_batch (0 = the whole batch at once, the default) */

@@ -55,7 +55,7 @@ struct yavo_ctx {
     // cluster pre-partition of large candidate lists (select_big_kernel): exchange block, handed-over ranges, their count
     int *d_xchg = nullptr, *d_npre = nullptr, *d_team_done = nullptr;
     SelRange *d_pre = nullptr;
-    int big_min = -1;  // candidates above which a frame's list takes the cluster path; 0 = never, -1 = automatic (8192, frames >= 2 Mpx)
+    int big_min = -1;  // candidates above which a frame's list takes the cluster path; 0 = never, -1 = automatic (6144, frames >= 2 Mpx)
     int32_t *d_kp_row = nullptr, *d_kp_col = nullptr;
     float *d_kp_score = nullptr;
     int *d_nkp = nullptr;
@@ -379,7 +379,7 @@ int launch_select(yavo_ctx *ctx, int slot0, int n, int K) {
     const int H = ctx->slot_rows[slot0], W = ctx->slot_cols[slot0];
     const size_t o = (size_t)slot0 * ctx->max_kp;
     // large lists (4K frames: 300 k candidates): the top of the partition tree runs on a thread-block cluster per frame
-    const int big_min = ctx->big_min > 0 ? ctx->big_min : (ctx->big_min < 0 && (long long)H * W >= 2000000 ? 8192 : 0);
+    const int big_min = ctx->big_min > 0 ? ctx->big_min : (ctx->big_min < 0 && (long long)H * W >= 2000000 ? 6144 : 0);
     const bool big = big_min > 0 && ctx->max_cand > big_min;
     if (big) {
         CK(cudaMemsetAsync(ctx->d_npre + slot0, 0, sizeof(int) * (size_t)n, ctx->ls));
