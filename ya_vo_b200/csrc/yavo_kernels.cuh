@@ -629,7 +629,10 @@ constexpr int SEL_STACK = 48;           // per-warp private stack
 #ifndef YAVO_SEL_LOCAL_SINGLE
 #define YAVO_SEL_LOCAL_SINGLE 16  // the single-frame instance hands almost every right child to the queue (idle warps): 62.6 -> 58 us
 #endif
-constexpr int SEL_LOCAL = 64;           // right children up to this size stay with the warp that produced them
+#ifndef YAVO_SEL_LOCAL
+#define YAVO_SEL_LOCAL 32  // measured at the end of round 2: 0 0.309 ms, 16 0.291, 24 0.287, 32 0.286, 64 0.298, 128 0.345 per 1024 frames
+#endif
+constexpr int SEL_LOCAL = YAVO_SEL_LOCAL;           // right children up to this size stay with the warp that produced them
 constexpr int SEL_BIG = 64;             // per-level list of CTA-partitioned ranges
 
 struct SelRange {
