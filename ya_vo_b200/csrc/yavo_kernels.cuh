@@ -272,10 +272,12 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
         // the warp's four rows of nibbles start at zero (one 16-byte store by each of eight lanes; pass B, behind a
         // __syncwarp, fills in the survivors)
         if (lane < RPW * 32 / 16) reinterpret_cast<uint4 *>(&fnib[warp][0][0])[lane] = make_uint4(0u, 0u, 0u, 0u);
-        auto pass_a = [&](int k) {
+        // rows 4 .. H-5 only: a tile whose 32 rows all qualify (every tile row but the first and the last) skips the check
+        const bool rows_inside = y0 >= 4 && y0 + TH <= H - 4;  // CTA-uniform
+        auto pass_a = [&](int k, bool check_row = true) {
             const int tr = warp + NW * k, gr = y0 + tr, sr = tr + HALO;
             uint32_t core = 0;  // the word itself, tested after the (warp-uniform) branch: no boolean to materialise
-            if (gr >= 4 && gr < H - 4)
+            if (!check_row || (gr >= 4 && gr < H - 4))
                 core = yavo_fast4_core(&tile[sr][lane + SPX], &tile[sr + 1][lane + SPX], &tile[sr + 3][lane + SPX]);
             const bool live = core != 0;
             const unsigned bl = __ballot_sync(0xffffffffu, live);
@@ -288,6 +290,19 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
         };
         // With the blur on the tensor cores its steps are interleaved with the balanced parts of the segment test, so
         // that every tcgen05.mma round trip has a few hundred instructions per warp to hide under.
+#if YAVO_BLUR_UMMA == 0
+        if (rows_inside) {
+            pass_a(0, false);
+            pass_a(1, false);
+            pass_a(2, false);
+            pass_a(3, false);
+        } else {
+            pass_a(0);
+            pass_a(1);
+            pass_a(2);
+            pass_a(3);
+        }
+#else
         pass_a(0);
         pass_a(1);
 #if YAVO_BLUR_UMMA == 1
@@ -295,6 +310,7 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
 #endif
         pass_a(2);
         pass_a(3);
+#endif
         static_assert(RPW == 4, "pass A is written out for four rows per warp");
 #if YAVO_BLUR_UMMA == 1
         if (UMMA) bu::bu_pass2_drain(bcst, bu_bars, tmem_base, ub, 0);  // first half drained, second half issued
