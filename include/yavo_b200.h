@@ -105,9 +105,10 @@ int yavo_fast_detect(yavo_ctx *ctx, int slot, int max_kp, int32_t *out_rows, int
 /* The reference's per-frame sequence in ONE call (LoopHandler::insertFrameFeatures, src/LoopHandler.cc:468-485:
  * FastDetector::getFastFeatures on a fresh frame, then Brief::computeBrief on the points it returned): uploads the host
  * frame (rows x cols, row pitch `stride`) into `slot`, detects, orders and cuts to max_kp as yavo_fast_detect does, and
- * describes the points checkBoundry admits as yavo_brief_describe would.  The whole sequence — copy in, kernels, copy
- * out — is captured once per (slot, frame size, max_kp) as a CUDA graph between pinned staging buffers, so a call costs
- * one graph launch and one synchronisation.  yavo_set_brief_offsets must have been called.
+ * describes the points checkBoundry admits as yavo_brief_describe would.  The frame is staged in pinned memory at the
+ * device row pitch and copied straight into the slot (no re-pitch kernel on this path); the whole sequence — copy in,
+ * kernels, copy out — is captured once per (slot, frame size, max_kp) as a CUDA graph between pinned staging buffers, so
+ * a call costs one graph launch and one synchronisation.  One frame runs the select kernel's 768-thread instance.  yavo_set_brief_offsets must have been called.
  *   kp_rows / kp_cols / kp_scores [max_kp], *n_kp: the detector's output (kp_scores may be NULL)
  *   d_rows / d_cols / d_ids [max_kp], desc [max_kp x 32], *n_desc: the admitted points in order; d_ids = index of the
  *   point in the kp list (the `id` Brief::computeBrief gives the KeyPoint, src/BriefDescriptor.cc:95)
