@@ -244,7 +244,11 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
 #else
     if (DO_BLUR) {
         // horizontal pass: (SH/2) row pairs x 32 quads; thread -> one quad of one row pair
-        for (int i = tid; i < (SH / 2) * (TW / 4); i += K1_THREADS) {
+        // (three rounds written out — the third for half of the threads: the loop's address increments become immediates)
+#pragma unroll
+        for (int it = 0; it < ((SH / 2) * (TW / 4) + K1_THREADS - 1) / K1_THREADS; it++) {
+            const int i = tid + it * K1_THREADS;
+            if (i >= (SH / 2) * (TW / 4)) break;
             const int rp = i >> 5, q = i & 31;
             const uint32_t *ra = &tile[2 * rp][q + SPX];
             const uint32_t *rb = &tile[2 * rp + 1][q + SPX];
