@@ -468,12 +468,14 @@ detect_blur_kernel(const __grid_constant__ CUtensorMap frames_map, const __grid_
             const uint32_t w0 = __byte_perm(__byte_perm(o0[0], o0[1], 0x0062), __byte_perm(o0[2], o0[3], 0x0062), 0x5410);
             const uint32_t w1 = __byte_perm(__byte_perm(o1[0], o1[1], 0x0062), __byte_perm(o1[2], o1[3], 0x0062), 0x5410);
             const int gr = y0 + 2 * j, gc = x0 + 4 * q;
-            if (gc < pitch) {
-                uint8_t *dst = blur + (size_t)f * frame_stride + (size_t)gr * pitch + gc;
-                if (gr < H)
-                    *reinterpret_cast<uint32_t *>(dst) = w0;
-                if (gr + 1 < H)
-                    *reinterpret_cast<uint32_t *>(dst + pitch) = w1;
+            // (x0 + 4 q < pitch always: the pitch is a multiple of the tile width and covers every tile column)
+            uint8_t *dst = blur + (size_t)f * frame_stride + (size_t)gr * pitch + gc;
+            if (y0 + TH <= H) {  // CTA-uniform: every row of the tile lies inside the frame
+                *reinterpret_cast<uint32_t *>(dst) = w0;
+                *reinterpret_cast<uint32_t *>(dst + pitch) = w1;
+            } else {
+                if (gr < H) *reinterpret_cast<uint32_t *>(dst) = w0;
+                if (gr + 1 < H) *reinterpret_cast<uint32_t *>(dst + pitch) = w1;
             }
         }
     }
