@@ -728,7 +728,7 @@ __device__ __forceinline__ bool sel_pop(SelSharedT<NT> &S, SelRange &out) {
 // whole-CTA partition of [f,l); returns the cut to every thread.  Lpos/Rpos: global scratch.
 // Each thread classifies SEL_ITEMS consecutive positions per pass (one block-wide scan per 4096 elements).
 #ifndef YAVO_SEL_ITEMS
-#define YAVO_SEL_ITEMS 4  // measured with the ballot form: 4 0.299 ms, 6 0.300, 8 0.315, 12 0.339 per 1024 frames
+#define YAVO_SEL_ITEMS 5  // measured with the ballot form: 4 0.299 ms, 6 0.300, 8 0.315, 12 0.339 per 1024 frames; at the end of the round 4 0.2864, 5 0.2849
 #endif
 constexpr int SEL_ITEMS = YAVO_SEL_ITEMS;
 
