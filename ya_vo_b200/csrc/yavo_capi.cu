@@ -688,8 +688,9 @@ int yavo_create(int device, int n_slots, int max_rows, int max_cols, int max_kp,
     // eight CTAs of the detect kernel per SM need the largest shared-memory carve-out
     CKC(cudaFuncSetAttribute(detect_blur_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CKC(cudaFuncSetAttribute(detect_blur_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    memset(&c->frames_cmap, 0, sizeof c->frames_cmap);  // read only by the hybrid tensor-core blur (build variant -DYAVO_BLUR_UMMA=2)
     if (encode_slot_map(c, &c->frames_map, c->d_frames, SROW, SH) != 0 || encode_slot_map(c, &c->blur_map, c->d_blur, BP_ROWB, BP_ROWS) != 0 ||
-        encode_chunk_map(c, &c->frames_cmap, c->d_frames) != 0) {
+        (YAVO_BLUR_UMMA == 2 && encode_chunk_map(c, &c->frames_cmap, c->d_frames) != 0)) {
         g_create_error = c->err;
         yavo_destroy(c);
         return YAVO_ERR_CUDA;
